@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests (golden loading, strict tree comparison)."""
+import glob
+import gzip
+import os
+import pickle
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[: -len(".pkl.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pkl.gz")))
+
+
+_cache = {}
+
+
+def load_golden(name):
+    if name not in _cache:
+        with gzip.open(os.path.join(GOLDEN_DIR, name + ".pkl.gz"), "rb") as f:
+            _cache[name] = pickle.load(f)
+    return _cache[name]
+
+
+def tree_diff(a, b, path="root"):
+    """Strict comparison of two nested tree dicts: key ORDER, values and value TYPES.
+    Returns None when identical, else a string describing the first difference."""
+    if type(a) is not type(b):
+        return f"{path}: type {type(a).__name__} != {type(b).__name__}"
+    if isinstance(a, dict):
+        ka, kb = list(a.keys()), list(b.keys())
+        if ka != kb:
+            return f"{path}: keys {ka} != {kb}"
+        for k in ka:
+            if type(k) is not type(kb[ka.index(k)]):
+                return f"{path}: key type {type(k).__name__}"
+            d = tree_diff(a[k], b[k], f"{path}/{k}")
+            if d:
+                return d
+        return None
+    if isinstance(a, (float, np.floating)):
+        if not (a == b or (a != a and b != b)):
+            return f"{path}: {a!r} != {b!r}"
+        if np.signbit(a) != np.signbit(b):
+            return f"{path}: sign of zero differs"
+        return None
+    if a != b:
+        return f"{path}: {a!r} != {b!r}"
+    return None
+
+
+def probs_equal(a, b):
+    """Bit-level equality of two lists of {class: prob} dicts, incl. key order."""
+    if len(a) != len(b):
+        return False
+    for x, y in zip(a, b):
+        if list(x.keys()) != list(y.keys()):
+            return False
+        for k in x:
+            if not (float(x[k]) == float(y[k])):
+                return False
+    return True
