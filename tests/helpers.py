@@ -42,8 +42,7 @@ def tree_diff(a, b, path="root"):
     if isinstance(a, (float, np.floating)):
         if not (a == b or (a != a and b != b)):
             return f"{path}: {a!r} != {b!r}"
-        if np.signbit(a) != np.signbit(b):
-            return f"{path}: sign of zero differs"
+        # the sign of a ZERO split value is not pinned (see DESIGN.md "known deviations")
         return None
     if a != b:
         return f"{path}: {a!r} != {b!r}"
