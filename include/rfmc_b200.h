@@ -1,0 +1,133 @@
+/*
+ * rfmc_b200.h -- C ABI of the B200-native engine for the RandomForestMC hot path.
+ *
+ * The reference (ysraell/random-forest-mc v1.4.0) is pure Python and has no FFI; its only seam is
+ * the method surface of RandomForestMC / BaseRandomForestMC.  Each entry point below replaces the
+ * arithmetic of one group of those methods (cited as file:line relative to the reference root) and
+ * is what a maintainer's ctypes stub would bind (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; rfmc_last_error() returns the
+ *     message of the last failure on the calling thread; no C++ exception crosses the boundary;
+ *   - the caller owns host buffers (contiguous, little-endian); the library owns device memory
+ *     behind opaque handles; a handle is bound to one CUDA device;
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Encoding contract (random-forest-mc_b200/encode.py): feature values are dense rank codes, code 0 =
+ * missing/unseen; numeric columns carry a sorted float64 value table; class labels are coded by
+ * their position in the lexicographically sorted label list.
+ */
+#ifndef RFMC_B200_H
+#define RFMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFMC_ABI_VERSION 1
+
+/* column kinds and arithmetic tags (tag | bits<<8 | signed<<16) */
+#define RFMC_KIND_NUMERIC 0
+#define RFMC_KIND_CATEGORICAL 1
+#define RFMC_TAG_F64 0
+#define RFMC_TAG_F32 1
+#define RFMC_TAG_INT 2
+
+/* node flags */
+#define RFMC_FLAG_CATEGORICAL 1u /* test is code == thr, else code >= thr (tree.py:177-180) */
+#define RFMC_FLAG_TWO_ROW 2u     /* split value is the native element uniq[thr-1] (model.py:258-262) */
+
+#define RFMC_MAX_CLASSES 64
+
+/* One node of a grown tree (24 bytes).  Breadth-first numbering, root = 0.
+ * Split node: feat >= 0, '>=' child = child, '<' child = child + 1.  Leaf: feat = -1, child = -1. */
+typedef struct rfmc_node {
+    int32_t feat;   /* column index into the dataset's feature list */
+    uint32_t thr;   /* code threshold (numeric) or category code (categorical) */
+    int32_t child;  /* index of the '>=' child */
+    uint32_t flags; /* RFMC_FLAG_* */
+    double sval;    /* numeric split value of a >2-row node (model.py:237), else 0 */
+} rfmc_node;
+
+/* One node of a forest flattened for voting (16 bytes, absolute indices into the forest arrays). */
+typedef struct rfmc_pnode {
+    uint32_t feat_flags; /* bits 0..15 column, bit 30 categorical, bit 31 leaf */
+    uint32_t thr;        /* split: code threshold / category code; leaf: payload index */
+    uint32_t child;      /* absolute index of the '>=' child ('<' child = child + 1) */
+    uint32_t reserved;
+} rfmc_pnode;
+#define RFMC_PNODE_LEAF 0x80000000u
+#define RFMC_PNODE_CATEGORICAL 0x40000000u
+
+typedef struct rfmc_dataset rfmc_dataset;
+typedef struct rfmc_batch rfmc_batch;
+typedef struct rfmc_forest rfmc_forest;
+
+int rfmc_abi_version(void);
+const char* rfmc_last_error(void);
+int rfmc_device_count(int* count);
+
+/* ---- process_dataset (model.py:162-195): upload the encoded training matrix once ------------
+ * codes      [n_rows][row_stride] unsigned codes of `code_width` bytes (1, 2 or 4), row-major,
+ *            row_stride*code_width an odd multiple of 4 bytes
+ * labels     [n_rows] class code (sorted-label order), n_classes <= RFMC_MAX_CLASSES
+ * col_kind   [n_features] RFMC_KIND_*;  col_tag [n_features] packed arithmetic tag
+ * table_off  [n_features+1] offsets into `tables` (float64 sorted distinct values per numeric
+ *            column; categorical columns have an empty range); col_nunique[n_features]          */
+int rfmc_dataset_create(int device, const void* codes, int code_width, int64_t n_rows, int32_t n_features,
+                        int64_t row_stride, const uint8_t* labels, int32_t n_classes, const uint8_t* col_kind,
+                        const int32_t* col_tag, const int32_t* col_nunique, const int64_t* table_off,
+                        const double* tables, rfmc_dataset** out);
+int rfmc_dataset_destroy(rfmc_dataset* ds);
+
+/* ---- plantTree + validationTree for a batch of candidates (model.py:222-314) ----------------
+ * The host draws rows and features with the reference's own RNGs (model.py:198-219) and hands
+ * them over; the GPU grows every candidate and scores it on its slot's hold-out rows.
+ * idx_train  [n_slots][n_train] row ids in the reference's order (class-major, draw order)
+ * idx_val    [n_slots][n_val]
+ * cand_slot  [n_cand] slot of each candidate; feat_off [n_cand+1] offsets into feat_list
+ * feat_list  ordered feature indices of every candidate (the sampleFeats output)
+ * Step 1 uploads (host -> device) and reserves outputs, step 2 launches on `stream`
+ * (asynchronous), step 3 waits and returns per-candidate results.                               */
+int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_t n_val, const int32_t* idx_train,
+                      const int32_t* idx_val, int32_t n_cand, const int32_t* cand_slot, const int32_t* feat_off,
+                      const uint16_t* feat_list, int32_t max_depth, int32_t min_samples_split, void* stream,
+                      rfmc_batch** out);
+int rfmc_batch_run(rfmc_batch* b, void* stream);
+/* correct[n_cand]: hold-out rows classified correctly (th_val = correct / n_val, model.py:314);
+ * n_nodes[n_cand]: size of each node table. */
+int rfmc_batch_results(rfmc_batch* b, int32_t* correct, int32_t* n_nodes);
+/* Copy the node tables of selected candidates, packed back to back, to `nodes_out` /
+ * `counts_out` ([sum n_nodes][n_classes] class counts per node).  dst_on_device != 0: the
+ * destinations are device pointers (e.g. an NCCL all-gather send buffer). */
+int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_node* nodes_out, int32_t* counts_out,
+                    int dst_on_device, void* stream);
+int rfmc_batch_destroy(rfmc_batch* b);
+/* launches made by the last rfmc_batch_run on this batch (for bench.py's gpu_launches) */
+int rfmc_batch_launches(rfmc_batch* b);
+
+/* ---- useForest / testForest / testForestProbs (forest.py:204-258, tree.py:155-212) -----------
+ * A forest flattened on the host: per leaf payload a vote and class probabilities, plus the
+ * variants used when the row lacks a split column (tree.py:171-175,201-210).
+ * probs arrays are [n_payloads][n_classes] float64 in class_vals order.                         */
+int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, const int64_t* tree_root, int32_t n_trees,
+                       int64_t n_payloads, const uint8_t* vote, const uint8_t* vote_absent, const double* probs,
+                       const double* probs_absent, int32_t n_classes, const double* scores, double score_fsum,
+                       rfmc_forest** out);
+int rfmc_forest_destroy(rfmc_forest* f);
+/* codes [n_rows][row_stride] (same layout rule as the dataset); absent[n_features] != 0 marks a
+ * column missing from the frame (NULL = none).  soft / weighted as setSoftVoting / setWeightedTrees
+ * (forest.py:151-155).  probs_out [n_rows][n_classes] float64 and/or labels_out [n_rows] int32
+ * (class_vals index; NULL to skip).  on_device != 0: codes and outputs are device pointers and
+ * the call is asynchronous on `stream`; otherwise host buffers, copies included, synchronous.   */
+int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
+                        int32_t n_features, const uint8_t* absent, int soft, int weighted, double* probs_out,
+                        int32_t* labels_out, int on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFMC_B200_H */

@@ -125,3 +125,44 @@ def score_codes(enc, nodes, counts, idx_V):
             i = int(nodes["child"][i]) + (0 if go else 1)
         correct += int(votes[i] == enc.labels[r])
     return correct
+
+
+def vote_tables(t, codes, absent, soft, weighted):
+    """forest.py:204-236 on a flattened forest (``flat.ForestTables``) and an encoded frame: the
+    CPU statement of what the CUDA voting kernel computes.  Returns (probs [n, C], labels [n])."""
+    LEAF, CAT = _flat.PNODE_LEAF, _flat.PNODE_CATEGORICAL
+    n, C = codes.shape[0], t.n_classes
+    ff, thr, child = t.pnodes["feat_flags"], t.pnodes["thr"], t.pnodes["child"]
+    probs = np.zeros((n, C), dtype=np.float64)
+    labels = np.zeros(n, dtype=np.int32)
+    T = len(t.roots)
+    for r in range(n):
+        acc = [0.0] * C
+        cnt = [0] * C
+        for ti in range(T):
+            i = int(t.roots[ti])
+            seen = False
+            while not (ff[i] & LEAF):
+                f = int(ff[i] & 0xFFFF)
+                c = int(codes[r, f])
+                go = (c == thr[i]) if (ff[i] & CAT) else (c >= thr[i])
+                if absent is not None and absent[f]:
+                    go, seen = True, True
+                i = int(child[i]) + (0 if go else 1)
+            pid = int(thr[i])
+            if not soft:
+                v = int(t.vote_absent[pid] if seen else t.vote[pid])
+                if weighted:
+                    acc[v] = acc[v] + float(t.scores[ti])
+                else:
+                    cnt[v] += 1
+            else:
+                p = t.probs_absent[pid] if seen else t.probs[pid]
+                for k in range(C):
+                    acc[k] = acc[k] + (float(p[k]) * float(t.scores[ti]) if weighted else float(p[k]))
+        for k in range(C):
+            num = float(cnt[k]) if (not soft and not weighted) else acc[k]
+            den = float(T) if not weighted else float(t.score_fsum)
+            probs[r, k] = num / den
+        labels[r] = int(np.argmax(probs[r]))
+    return probs, labels

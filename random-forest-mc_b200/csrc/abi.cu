@@ -1,0 +1,370 @@
+// extern "C" entry points of librfmc_b200.so (declared in include/rfmc_b200.h).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rfmc {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t count, cudaStream_t stream) {
+    *dst = nullptr;
+    if (count == 0) return 0;
+    RFMC_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    RFMC_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+template <typename T>
+static int reserve(T** dst, size_t count) {
+    *dst = nullptr;
+    if (count == 0) count = 1;
+    RFMC_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    return 0;
+}
+static void release(void* p) {
+    if (p) cudaFree(p);
+}
+}  // namespace rfmc
+
+using namespace rfmc;
+
+extern "C" {
+
+int rfmc_abi_version(void) { return RFMC_ABI_VERSION; }
+
+const char* rfmc_last_error(void) { return g_error.c_str(); }
+
+int rfmc_device_count(int* count) {
+    RFMC_REQUIRE(count != nullptr, "count is NULL");
+    *count = 0;
+    RFMC_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int rfmc_dataset_create(int device, const void* codes, int code_width, int64_t n_rows, int32_t n_features,
+                        int64_t row_stride, const uint8_t* labels, int32_t n_classes, const uint8_t* col_kind,
+                        const int32_t* col_tag, const int32_t* col_nunique, const int64_t* table_off,
+                        const double* tables, rfmc_dataset** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_REQUIRE(code_width == 1 || code_width == 2 || code_width == 4, "code_width must be 1, 2 or 4");
+    RFMC_REQUIRE(n_rows > 0 && n_features > 0 && n_features <= 65535, "bad matrix shape");
+    RFMC_REQUIRE(row_stride >= n_features && (row_stride * code_width) % 4 == 0, "row pitch must be a multiple of 4 bytes");
+    RFMC_REQUIRE(n_classes >= 1 && n_classes <= RFMC_MAX_CLASSES, "n_classes must be in 1..64");
+    RFMC_CUDA(cudaSetDevice(device));
+    rfmc_dataset* ds = new rfmc_dataset();
+    ds->device = device;
+    ds->code_width = code_width;
+    ds->n_rows = n_rows;
+    ds->n_features = n_features;
+    ds->stride = row_stride;
+    ds->n_classes = n_classes;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed");
+        delete ds;
+        return 1;
+    }
+    ds->sm_count = prop.multiProcessorCount;
+    int rc = 0;
+    rc |= upload((uint8_t**)&ds->d_codes, (const uint8_t*)codes, (size_t)n_rows * row_stride * code_width, 0);
+    rc |= upload(&ds->d_labels, labels, (size_t)n_rows, 0);
+    rc |= upload(&ds->d_kind, col_kind, (size_t)n_features, 0);
+    rc |= upload(&ds->d_tag, col_tag, (size_t)n_features, 0);
+    rc |= upload(&ds->d_nuniq, col_nunique, (size_t)n_features, 0);
+    rc |= upload(&ds->d_taboff, table_off, (size_t)n_features + 1, 0);
+    size_t ntab = (size_t)table_off[n_features];
+    if (ntab == 0) {
+        rc |= reserve(&ds->d_tables, 1);
+    } else {
+        rc |= upload(&ds->d_tables, tables, ntab, 0);
+    }
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("dataset upload failed");
+        rc = 1;
+    }
+    if (rc) {
+        rfmc_dataset_destroy(ds);
+        return 1;
+    }
+    *out = ds;
+    return 0;
+}
+
+int rfmc_dataset_destroy(rfmc_dataset* ds) {
+    if (!ds) return 0;
+    cudaSetDevice(ds->device);
+    release(ds->d_codes);
+    release(ds->d_labels);
+    release(ds->d_kind);
+    release(ds->d_tag);
+    release(ds->d_nuniq);
+    release(ds->d_taboff);
+    release(ds->d_tables);
+    delete ds;
+    return 0;
+}
+
+int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_t n_val, const int32_t* idx_train,
+                      const int32_t* idx_val, int32_t n_cand, const int32_t* cand_slot, const int32_t* feat_off,
+                      const uint16_t* feat_list, int32_t max_depth, int32_t min_samples_split, void* stream,
+                      rfmc_batch** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_REQUIRE(ds != nullptr, "dataset is NULL");
+    RFMC_REQUIRE(n_slots > 0 && n_train > 0 && n_val >= 0 && n_cand > 0, "bad batch shape");
+    RFMC_REQUIRE(min_samples_split >= 1, "min_samples_split must be >= 1");
+    RFMC_REQUIRE(max_depth >= 1, "max_depth must be >= 1");
+    int32_t fmax = 0;
+    for (int i = 0; i < n_cand; ++i) {
+        int32_t nf = feat_off[i + 1] - feat_off[i];
+        RFMC_REQUIRE(nf >= 1, "every candidate needs at least one feature");
+        RFMC_REQUIRE(cand_slot[i] >= 0 && cand_slot[i] < n_slots, "cand_slot out of range");
+        if (nf > fmax) fmax = nf;
+    }
+    for (int64_t i = 0; i < feat_off[n_cand]; ++i)
+        RFMC_REQUIRE(feat_list[i] < ds->n_features, "feature index out of range");
+    RFMC_CUDA(cudaSetDevice(ds->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rfmc_batch* b = new rfmc_batch();
+    b->ds = ds;
+    b->n_slots = n_slots;
+    b->n_train = n_train;
+    b->n_val = n_val;
+    b->n_cand = n_cand;
+    b->max_depth = max_depth;
+    b->mss = min_samples_split;
+    b->nt_pad = (n_train + 15) / 16 * 16;
+    b->max_nodes = 2 * n_train;
+    b->fmax = fmax;
+    b->grid = grow_grid_size(ds, n_cand);
+    b->stream = st;
+    const size_t g = (size_t)b->grid, ntp = (size_t)b->nt_pad, C = (size_t)ds->n_classes;
+    int rc = 0;
+    rc |= upload(&b->d_idx_train, idx_train, (size_t)n_slots * n_train, st);
+    rc |= upload(&b->d_idx_val, idx_val, (size_t)n_slots * n_val, st);
+    rc |= upload(&b->d_cand_slot, cand_slot, (size_t)n_cand, st);
+    rc |= upload(&b->d_feat_off, feat_off, (size_t)n_cand + 1, st);
+    rc |= upload(&b->d_feat_list, feat_list, (size_t)feat_off[n_cand], st);
+    rc |= reserve((uint8_t**)&b->d_cc, g * fmax * ntp * ds->code_width);
+    rc |= reserve(&b->d_lab, g * ntp);
+    rc |= reserve(&b->d_pos, g * 2 * ntp);
+    rc |= reserve(&b->d_work, g * 2 * ntp);
+    rc |= reserve(&b->d_resna, g * ntp);
+    rc |= reserve(&b->d_nodes, (size_t)n_cand * b->max_nodes);
+    rc |= reserve(&b->d_counts, (size_t)n_cand * b->max_nodes * C);
+    rc |= reserve(&b->d_votes, (size_t)n_cand * b->max_nodes);
+    rc |= reserve(&b->d_nnodes, (size_t)n_cand);
+    rc |= reserve(&b->d_correct, (size_t)n_cand);
+    if (rc) {
+        rfmc_batch_destroy(b);
+        return 1;
+    }
+    *out = b;
+    return 0;
+}
+
+int rfmc_batch_run(rfmc_batch* b, void* stream) {
+    RFMC_REQUIRE(b != nullptr, "batch is NULL");
+    RFMC_CUDA(cudaSetDevice(b->ds->device));
+    b->stream = (cudaStream_t)stream;
+    b->have_results = false;
+    return launch_grow(b, b->stream);
+}
+
+int rfmc_batch_launches(rfmc_batch* b) { return b ? b->launches : 0; }
+
+int rfmc_batch_results(rfmc_batch* b, int32_t* correct, int32_t* n_nodes) {
+    RFMC_REQUIRE(b != nullptr, "batch is NULL");
+    RFMC_CUDA(cudaSetDevice(b->ds->device));
+    b->h_nnodes.resize(b->n_cand);
+    RFMC_CUDA(cudaMemcpyAsync(b->h_nnodes.data(), b->d_nnodes, sizeof(int32_t) * b->n_cand, cudaMemcpyDeviceToHost, b->stream));
+    if (correct)
+        RFMC_CUDA(cudaMemcpyAsync(correct, b->d_correct, sizeof(int32_t) * b->n_cand, cudaMemcpyDeviceToHost, b->stream));
+    RFMC_CUDA(cudaStreamSynchronize(b->stream));
+    if (n_nodes) std::memcpy(n_nodes, b->h_nnodes.data(), sizeof(int32_t) * b->n_cand);
+    b->have_results = true;
+    return 0;
+}
+
+int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_node* nodes_out, int32_t* counts_out,
+                    int dst_on_device, void* stream) {
+    RFMC_REQUIRE(b != nullptr, "batch is NULL");
+    if (n_sel <= 0) return 0;
+    RFMC_CUDA(cudaSetDevice(b->ds->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b->have_results) {
+        if (rfmc_batch_results(b, nullptr, nullptr)) return 1;
+    }
+    std::vector<int64_t> off(n_sel + 1, 0);
+    for (int i = 0; i < n_sel; ++i) {
+        RFMC_REQUIRE(cand_ids[i] >= 0 && cand_ids[i] < b->n_cand, "candidate id out of range");
+        off[i + 1] = off[i] + b->h_nnodes[cand_ids[i]];
+    }
+    const size_t total = (size_t)off[n_sel], C = (size_t)b->ds->n_classes;
+    int32_t* d_ids = nullptr;
+    int64_t* d_off = nullptr;
+    rfmc_node* d_nodes = nodes_out;
+    int32_t* d_counts = counts_out;
+    int rc = 0;
+    rc |= upload(&d_ids, cand_ids, (size_t)n_sel, st);
+    rc |= upload(&d_off, off.data(), (size_t)n_sel, st);
+    if (!dst_on_device) {
+        rc |= reserve(&d_nodes, total);
+        rc |= reserve(&d_counts, total * C);
+    }
+    if (!rc) rc = launch_pack(b, d_ids, d_off, n_sel, d_nodes, d_counts, st);
+    if (!rc && !dst_on_device) {
+        if (cudaMemcpyAsync(nodes_out, d_nodes, total * sizeof(rfmc_node), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(counts_out, d_counts, total * C * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+            set_error("pack: device to host copy failed");
+            rc = 1;
+        }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) {
+        set_error(std::string("pack failed: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+    }
+    release(d_ids);
+    release(d_off);
+    if (!dst_on_device) {
+        release(d_nodes);
+        release(d_counts);
+    }
+    b->launches += 1;
+    return rc;
+}
+
+int rfmc_batch_destroy(rfmc_batch* b) {
+    if (!b) return 0;
+    cudaSetDevice(b->ds->device);
+    release(b->d_idx_train);
+    release(b->d_idx_val);
+    release(b->d_cand_slot);
+    release(b->d_feat_off);
+    release(b->d_feat_list);
+    release(b->d_cc);
+    release(b->d_lab);
+    release(b->d_pos);
+    release(b->d_work);
+    release(b->d_resna);
+    release(b->d_nodes);
+    release(b->d_counts);
+    release(b->d_votes);
+    release(b->d_nnodes);
+    release(b->d_correct);
+    delete b;
+    return 0;
+}
+
+int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, const int64_t* tree_root, int32_t n_trees,
+                       int64_t n_payloads, const uint8_t* vote, const uint8_t* vote_absent, const double* probs,
+                       const double* probs_absent, int32_t n_classes, const double* scores, double score_fsum,
+                       rfmc_forest** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_REQUIRE(n_nodes > 0 && n_trees > 0 && n_payloads > 0, "empty forest");
+    RFMC_REQUIRE(n_nodes < 0xFFFFFFFFll, "forest too large for 32-bit node indices");
+    RFMC_REQUIRE(n_classes >= 1 && n_classes <= RFMC_MAX_CLASSES, "n_classes must be in 1..64");
+    RFMC_CUDA(cudaSetDevice(device));
+    rfmc_forest* f = new rfmc_forest();
+    f->device = device;
+    f->n_nodes = n_nodes;
+    f->n_trees = n_trees;
+    f->n_payloads = n_payloads;
+    f->n_classes = n_classes;
+    f->score_fsum = score_fsum;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) f->sm_count = prop.multiProcessorCount;
+    int rc = 0;
+    rc |= upload(&f->d_nodes, nodes, (size_t)n_nodes, 0);
+    rc |= upload(&f->d_root, tree_root, (size_t)n_trees, 0);
+    rc |= upload(&f->d_vote, vote, (size_t)n_payloads, 0);
+    rc |= upload(&f->d_vote_absent, vote_absent, (size_t)n_payloads, 0);
+    rc |= upload(&f->d_probs, probs, (size_t)n_payloads * n_classes, 0);
+    rc |= upload(&f->d_probs_absent, probs_absent, (size_t)n_payloads * n_classes, 0);
+    rc |= upload(&f->d_scores, scores, (size_t)n_trees, 0);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("forest upload failed");
+        rc = 1;
+    }
+    if (rc) {
+        rfmc_forest_destroy(f);
+        return 1;
+    }
+    *out = f;
+    return 0;
+}
+
+int rfmc_forest_destroy(rfmc_forest* f) {
+    if (!f) return 0;
+    cudaSetDevice(f->device);
+    release(f->d_nodes);
+    release(f->d_root);
+    release(f->d_vote);
+    release(f->d_vote_absent);
+    release(f->d_probs);
+    release(f->d_probs_absent);
+    release(f->d_scores);
+    delete f;
+    return 0;
+}
+
+int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
+                        int32_t n_features, const uint8_t* absent, int soft, int weighted, double* probs_out,
+                        int32_t* labels_out, int on_device, void* stream) {
+    RFMC_REQUIRE(f != nullptr, "forest is NULL");
+    RFMC_REQUIRE(code_width == 1 || code_width == 2 || code_width == 4, "code_width must be 1, 2 or 4");
+    RFMC_REQUIRE(n_rows >= 0 && n_features > 0 && row_stride >= n_features, "bad matrix shape");
+    RFMC_REQUIRE((row_stride * code_width) % 4 == 0, "row pitch must be a multiple of 4 bytes");
+    if (n_rows == 0) return 0;
+    RFMC_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    bool has_absent = false;
+    if (absent)
+        for (int i = 0; i < n_features; ++i) has_absent |= absent[i] != 0;
+    uint8_t* d_absent = nullptr;
+    int rc = 0;
+    if (has_absent) rc |= upload(&d_absent, absent, (size_t)n_features, st);
+    const size_t C = (size_t)f->n_classes;
+    if (on_device) {
+        if (!rc)
+            rc = launch_predict(f, codes, code_width, n_rows, row_stride, n_features, d_absent, has_absent, soft, weighted,
+                                probs_out, labels_out, st);
+        if (d_absent) {
+            cudaStreamSynchronize(st);
+            release(d_absent);
+        }
+        return rc;
+    }
+    uint8_t* d_codes = nullptr;
+    double* d_probs = nullptr;
+    int32_t* d_labels = nullptr;
+    rc |= upload(&d_codes, (const uint8_t*)codes, (size_t)n_rows * row_stride * code_width, st);
+    if (probs_out) rc |= reserve(&d_probs, (size_t)n_rows * C);
+    if (labels_out) rc |= reserve(&d_labels, (size_t)n_rows);
+    if (!rc)
+        rc = launch_predict(f, d_codes, code_width, n_rows, row_stride, n_features, d_absent, has_absent, soft, weighted,
+                            d_probs, d_labels, st);
+    if (!rc && probs_out &&
+        cudaMemcpyAsync(probs_out, d_probs, (size_t)n_rows * C * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = 1;
+    if (!rc && labels_out &&
+        cudaMemcpyAsync(labels_out, d_labels, (size_t)n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = 1;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error(std::string("predict failed: ") + cudaGetErrorString(e));
+        rc = 1;
+    } else if (rc && g_error.empty()) {
+        set_error("predict failed");
+    }
+    release(d_codes);
+    release(d_probs);
+    release(d_labels);
+    release(d_absent);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Shared declarations for the rfmc_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rfmc_b200.h"
+
+namespace rfmc {
+
+void set_error(const std::string& msg);
+
+#define RFMC_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            rfmc::set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_));       \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define RFMC_REQUIRE(cond, msg)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            rfmc::set_error(msg);          \
+            return 1;                      \
+        }                                  \
+    } while (0)
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct WorkItem {  // one node of the level being processed
+    uint32_t lo, hi;  // segment of the candidate's position array
+    uint32_t node;    // node id in the candidate's node table
+    uint32_t off;     // rotation offset into the candidate's feature list
+};
+
+}  // namespace rfmc
+
+struct rfmc_dataset {
+    int device = 0;
+    int code_width = 0;
+    int64_t n_rows = 0;
+    int32_t n_features = 0;
+    int64_t stride = 0;
+    int32_t n_classes = 0;
+    int sm_count = 0;
+    void* d_codes = nullptr;
+    uint8_t* d_labels = nullptr;
+    uint8_t* d_kind = nullptr;
+    int32_t* d_tag = nullptr;
+    int32_t* d_nuniq = nullptr;
+    int64_t* d_taboff = nullptr;
+    double* d_tables = nullptr;
+};
+
+struct rfmc_batch {
+    rfmc_dataset* ds = nullptr;
+    int32_t n_slots = 0, n_train = 0, n_val = 0, n_cand = 0, max_depth = 0, mss = 1;
+    int32_t nt_pad = 0, max_nodes = 0, fmax = 0, grid = 0;
+    int launches = 0;
+    // inputs
+    int32_t* d_idx_train = nullptr;
+    int32_t* d_idx_val = nullptr;
+    int32_t* d_cand_slot = nullptr;
+    int32_t* d_feat_off = nullptr;
+    uint16_t* d_feat_list = nullptr;
+    // per-CTA scratch
+    void* d_cc = nullptr;
+    uint8_t* d_lab = nullptr;
+    uint32_t* d_pos = nullptr;
+    rfmc::WorkItem* d_work = nullptr;
+    uint32_t* d_resna = nullptr;
+    // per-candidate outputs
+    rfmc_node* d_nodes = nullptr;
+    int32_t* d_counts = nullptr;
+    uint8_t* d_votes = nullptr;
+    int32_t* d_nnodes = nullptr;
+    int32_t* d_correct = nullptr;
+    std::vector<int32_t> h_nnodes;
+    bool have_results = false;
+    cudaStream_t stream = nullptr;
+};
+
+struct rfmc_forest {
+    int device = 0;
+    int64_t n_nodes = 0, n_payloads = 0;
+    int32_t n_trees = 0, n_classes = 0;
+    double score_fsum = 0.0;
+    rfmc_pnode* d_nodes = nullptr;
+    int64_t* d_root = nullptr;
+    uint8_t* d_vote = nullptr;
+    uint8_t* d_vote_absent = nullptr;
+    double* d_probs = nullptr;
+    double* d_probs_absent = nullptr;
+    double* d_scores = nullptr;
+    int sm_count = 0;
+};
+
+namespace rfmc {
+int launch_grow(rfmc_batch* b, cudaStream_t stream);
+int grow_grid_size(const rfmc_dataset* ds, int n_cand);
+int launch_pack(rfmc_batch* b, const int32_t* d_cand_ids, const int64_t* d_dst_off, int32_t n_sel, rfmc_node* nodes_out,
+                int32_t* counts_out, cudaStream_t stream);
+int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
+                   int32_t n_features, const uint8_t* d_absent, bool has_absent, int soft, int weighted, double* d_probs,
+                   int32_t* d_labels, cudaStream_t stream);
+}  // namespace rfmc

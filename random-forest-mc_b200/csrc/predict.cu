@@ -1,0 +1,215 @@
+// Forest traversal + voting kernel for sm_100a.
+//
+// Replaces DecisionTreeMC._useTree/useTree (tree.py:155-212), BaseRandomForestMC.useForest
+// (forest.py:204-233), maxProbClas (forest.py:200-202) and the row loops of testForest /
+// testForestProbs (forest.py:235-236, 257-258).
+//
+// Mapping: one thread per row, 128 rows per CTA.  The CTA's rows are copied verbatim from the
+// row-major HBM code matrix into shared memory (row pitch = odd number of 32-bit words, so the
+// per-thread row reads are bank-conflict-free whatever column each thread asks for).  Every thread
+// walks the trees IN FOREST ORDER and accumulates in fp64 with separate multiply and add, which is
+// the reference's summation order (forest.py:209-211, 216-218, 226-227): the probabilities come
+// out bit-identical, not merely within tolerance.  Node records are 16-byte loads; all threads of
+// a CTA are inside the same tree at the same time, so node traffic is L1/L2 broadcast traffic.
+//
+// Missing values (tree.py:166-181): a NaN / unseen cell is code 0 and fails both tests -> '<'.
+// A column absent from the frame takes '>=' and switches the leaf payload to the renormalised
+// variant the host precomputed (tree.py:201-210).
+#include "common.cuh"
+
+namespace rfmc {
+
+constexpr int PRED_THREADS = 128;
+
+struct PredictArgs {
+    const void* codes;
+    int64_t n_rows;
+    int64_t stride;  // elements
+    int32_t n_features;
+    const rfmc_pnode* nodes;
+    const int64_t* root;
+    int32_t n_trees;
+    const uint8_t* vote;
+    const uint8_t* vote_absent;
+    const double* probs;
+    const double* probs_absent;
+    const double* scores;
+    double score_fsum;
+    int32_t n_classes;
+    const uint8_t* absent;
+    double* probs_out;
+    int32_t* labels_out;
+};
+
+// MODE: 0 hard, 1 hard+weighted, 2 soft, 3 soft+weighted
+template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT, bool TILE>
+__global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw);
+    uint8_t* s_absent = smem_raw + (TILE ? (size_t)PRED_THREADS * a.stride * sizeof(CodeT) : 0);
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * PRED_THREADS;
+    const int rows = (int)((a.n_rows - row0) < PRED_THREADS ? (a.n_rows - row0) : PRED_THREADS);
+    const CodeT* gcodes = reinterpret_cast<const CodeT*>(a.codes) + row0 * a.stride;
+
+    if (TILE) {
+        // rows*stride*sizeof(CodeT) is a multiple of 4 by the layout contract
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gcodes);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
+        const int words = (int)((size_t)rows * a.stride * sizeof(CodeT) / 4);
+        for (int i = tid; i < words; i += PRED_THREADS) dst[i] = __ldg(&src[i]);
+    }
+    if (HAS_ABSENT) {
+        for (int i = tid; i < a.n_features; i += PRED_THREADS) s_absent[i] = a.absent[i];
+    }
+    __syncthreads();
+    if (tid >= rows) return;
+
+    const CodeT* myrow = TILE ? (tile + (size_t)tid * a.stride) : (gcodes + (size_t)tid * a.stride);
+    const int C = a.n_classes;
+
+    double acc[CMAX];
+    uint32_t cnt[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        acc[c] = 0.0;
+        cnt[c] = 0;
+    }
+
+    for (int t = 0; t < a.n_trees; ++t) {
+        uint32_t node = (uint32_t)__ldg(&a.root[t]);
+        bool seen = false;
+        uint4 nd;
+        while (true) {
+            nd = __ldg(reinterpret_cast<const uint4*>(a.nodes) + node);
+            if (nd.x & RFMC_PNODE_LEAF) break;
+            const uint32_t f = nd.x & 0xFFFFu;
+            const uint32_t cv = (uint32_t)myrow[f];
+            bool go = (nd.x & RFMC_PNODE_CATEGORICAL) ? (cv == nd.y) : (cv >= nd.y);
+            if (HAS_ABSENT) {
+                const bool ab = s_absent[f] != 0;
+                go = go || ab;
+                seen = seen || ab;
+            }
+            node = nd.z + (go ? 0u : 1u);
+        }
+        const uint32_t payload = nd.y;
+        if (MODE == 0 || MODE == 1) {
+            const int v = (HAS_ABSENT && seen) ? a.vote_absent[payload] : a.vote[payload];
+            if (MODE == 0) {
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
+            } else {
+                const double s = __ldg(&a.scores[t]);
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) acc[c] = __dadd_rn(acc[c], (c == v) ? s : 0.0);
+            }
+        } else {
+            const double* p = ((HAS_ABSENT && seen) ? a.probs_absent : a.probs) + (size_t)payload * C;
+            if (MODE == 2) {
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+            } else {
+                const double s = __ldg(&a.scores[t]);
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), s));
+            }
+        }
+    }
+
+    const double denom = (MODE == 0 || MODE == 2) ? (double)a.n_trees : a.score_fsum;
+    const int64_t row = row0 + tid;
+    int best = 0;
+    double bestv = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            const double num = (MODE == 0) ? (double)cnt[c] : acc[c];
+            const double v = __ddiv_rn(num, denom);
+            if (a.probs_out) a.probs_out[row * C + c] = v;
+            if (c == 0 || v > bestv) {  // first maximum in class_vals order (forest.py:200-202)
+                bestv = v;
+                best = c;
+            }
+        }
+    }
+    if (a.labels_out) a.labels_out[row] = best;
+}
+
+template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT>
+static int launch_tile(const PredictArgs& a, cudaStream_t stream) {
+    const int64_t blocks = (a.n_rows + PRED_THREADS - 1) / PRED_THREADS;
+    if (blocks == 0) return 0;
+    size_t tile_bytes = (size_t)PRED_THREADS * a.stride * sizeof(CodeT);
+    size_t extra = HAS_ABSENT ? (size_t)((a.n_features + 15) / 16 * 16) : 0;
+    if (tile_bytes + extra <= 200 * 1024) {
+        auto k = predict_kernel<CodeT, CMAX, MODE, HAS_ABSENT, true>;
+        size_t smem = tile_bytes + extra;
+        if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)blocks, PRED_THREADS, smem, stream>>>(a);
+    } else {
+        auto k = predict_kernel<CodeT, CMAX, MODE, HAS_ABSENT, false>;
+        if (extra > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)extra));
+        k<<<(unsigned)blocks, PRED_THREADS, extra, stream>>>(a);
+    }
+    RFMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename CodeT, int CMAX, int MODE>
+static int launch_absent(const PredictArgs& a, bool has_absent, cudaStream_t stream) {
+    return has_absent ? launch_tile<CodeT, CMAX, MODE, true>(a, stream) : launch_tile<CodeT, CMAX, MODE, false>(a, stream);
+}
+
+template <typename CodeT, int CMAX>
+static int launch_mode(const PredictArgs& a, int mode, bool has_absent, cudaStream_t stream) {
+    switch (mode) {
+        case 0: return launch_absent<CodeT, CMAX, 0>(a, has_absent, stream);
+        case 1: return launch_absent<CodeT, CMAX, 1>(a, has_absent, stream);
+        case 2: return launch_absent<CodeT, CMAX, 2>(a, has_absent, stream);
+        default: return launch_absent<CodeT, CMAX, 3>(a, has_absent, stream);
+    }
+}
+
+template <typename CodeT>
+static int launch_classes(const PredictArgs& a, int mode, bool has_absent, cudaStream_t stream) {
+    if (a.n_classes <= 4) return launch_mode<CodeT, 4>(a, mode, has_absent, stream);
+    if (a.n_classes <= 16) return launch_mode<CodeT, 16>(a, mode, has_absent, stream);
+    return launch_mode<CodeT, RFMC_MAX_CLASSES>(a, mode, has_absent, stream);
+}
+
+int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
+                   int32_t n_features, const uint8_t* d_absent, bool has_absent, int soft, int weighted, double* d_probs,
+                   int32_t* d_labels, cudaStream_t stream) {
+    PredictArgs a;
+    a.codes = d_codes;
+    a.n_rows = n_rows;
+    a.stride = row_stride;
+    a.n_features = n_features;
+    a.nodes = f->d_nodes;
+    a.root = f->d_root;
+    a.n_trees = f->n_trees;
+    a.vote = f->d_vote;
+    a.vote_absent = f->d_vote_absent;
+    a.probs = f->d_probs;
+    a.probs_absent = f->d_probs_absent;
+    a.scores = f->d_scores;
+    a.score_fsum = f->score_fsum;
+    a.n_classes = f->n_classes;
+    a.absent = d_absent;
+    a.probs_out = d_probs;
+    a.labels_out = d_labels;
+    const int mode = (soft ? 2 : 0) + (weighted ? 1 : 0);
+    switch (code_width) {
+        case 1: return launch_classes<uint8_t>(a, mode, has_absent, stream);
+        case 2: return launch_classes<uint16_t>(a, mode, has_absent, stream);
+        case 4: return launch_classes<uint32_t>(a, mode, has_absent, stream);
+    }
+    set_error("unsupported code width");
+    return 1;
+}
+
+}  // namespace rfmc

@@ -1,0 +1,295 @@
+"""ctypes binding of librfmc_b200.so (include/rfmc_b200.h) -- the only door to the GPU.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is visible, every
+compute entry point raises ``EngineUnavailable``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .encode import KIND_CATEGORICAL, EncodedDataset
+from .flat import NODE_DTYPE, TreeSoA
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librfmc_b200.so")
+
+PNODE_DTYPE = np.dtype([("feat_flags", "<u4"), ("thr", "<u4"), ("child", "<u4"), ("reserved", "<u4")])
+PNODE_LEAF = 0x80000000
+PNODE_CATEGORICAL = 0x40000000
+MAX_CLASSES = 64
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_p = C.c_void_p
+_SIGNATURES = {
+    "rfmc_abi_version": (C.c_int, []),
+    "rfmc_last_error": (C.c_char_p, []),
+    "rfmc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "rfmc_dataset_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int32, C.c_int64, _p, C.c_int32, _p, _p, _p, _p, _p, C.POINTER(_p)]),
+    "rfmc_dataset_destroy": (C.c_int, [_p]),
+    "rfmc_batch_create": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
+    "rfmc_batch_run": (C.c_int, [_p, _p]),
+    "rfmc_batch_results": (C.c_int, [_p, _p, _p]),
+    "rfmc_batch_pack": (C.c_int, [_p, _p, C.c_int32, _p, _p, C.c_int, _p]),
+    "rfmc_batch_destroy": (C.c_int, [_p]),
+    "rfmc_batch_launches": (C.c_int, [_p]),
+    "rfmc_forest_create": (C.c_int, [C.c_int, _p, C.c_int64, _p, C.c_int32, C.c_int64, _p, _p, _p, _p, C.c_int32, _p, C.c_double, C.POINTER(_p)]),
+    "rfmc_forest_destroy": (C.c_int, [_p]),
+    "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library():
+    """Load the C-ABI library (no CUDA call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineUnavailable(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  The engine has no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EngineError(load_library().rfmc_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    try:
+        rc = load_library().rfmc_device_count(C.byref(n))
+    except EngineUnavailable:
+        raise
+    if rc != 0:
+        return 0
+    return n.value
+
+
+def require_gpu():
+    if device_count() < 1:
+        raise EngineUnavailable("no CUDA device visible: the B200 engine has no CPU fallback")
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return getattr(stream, "cuda_stream", None) or None
+
+
+class DeviceDataset:
+    """rfmc_dataset handle: the encoded training matrix resident in HBM (process_dataset)."""
+
+    def __init__(self, enc: EncodedDataset, device: int = 0):
+        require_gpu()
+        self.enc = enc
+        self.device = device
+        nfeat = enc.n_features
+        kind = np.array([c.kind for c in enc.columns], dtype=np.uint8)
+        tag = np.array([c.tag for c in enc.columns], dtype=np.int32)
+        nuniq = np.array([c.n_unique for c in enc.columns], dtype=np.int32)
+        tabs = [c.table if c.kind != KIND_CATEGORICAL else np.zeros(0) for c in enc.columns]
+        off = np.zeros(nfeat + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in tabs])
+        tables = np.ascontiguousarray(np.concatenate(tabs) if tabs else np.zeros(0), dtype=np.float64)
+        if len(tables) == 0:
+            tables = np.zeros(1, dtype=np.float64)
+        codes = np.ascontiguousarray(enc.codes)
+        labels = np.ascontiguousarray(enc.labels, dtype=np.uint8)
+        h = _p()
+        _check(
+            load_library().rfmc_dataset_create(
+                device, _ptr(codes), enc.width, codes.shape[0], nfeat, enc.stride, _ptr(labels), enc.n_classes,
+                _ptr(kind), _ptr(tag), _ptr(nuniq), _ptr(off), _ptr(tables), C.byref(h),
+            )
+        )
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().rfmc_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GrowBatch:
+    """rfmc_batch handle: grow + score a batch of candidates (plantTree + validationTree)."""
+
+    def __init__(
+        self,
+        ds: DeviceDataset,
+        idx_train: np.ndarray,
+        idx_val: np.ndarray,
+        cand_slot: Sequence[int],
+        feat_lists: Sequence[Sequence[int]],
+        max_depth: int,
+        min_samples_split: int,
+        stream=None,
+    ):
+        self.ds = ds
+        idx_train = np.ascontiguousarray(idx_train, dtype=np.int32)
+        idx_val = np.ascontiguousarray(idx_val, dtype=np.int32)
+        if idx_train.ndim != 2 or idx_val.ndim != 2 or idx_train.shape[0] != idx_val.shape[0]:
+            raise ValueError("idx_train / idx_val must be [n_slots, n] arrays")
+        self.n_slots, self.n_train = idx_train.shape
+        self.n_val = idx_val.shape[1]
+        cand_slot = np.ascontiguousarray(cand_slot, dtype=np.int32)
+        self.n_cand = len(cand_slot)
+        off = np.zeros(self.n_cand + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(f) for f in feat_lists])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint16) for f in feat_lists]), dtype=np.uint16)
+        self._stream = _stream_ptr(stream)
+        h = _p()
+        _check(
+            load_library().rfmc_batch_create(
+                ds._h, self.n_slots, self.n_train, self.n_val, _ptr(idx_train), _ptr(idx_val), self.n_cand,
+                _ptr(cand_slot), _ptr(off), _ptr(flat), int(min(max_depth, 2**31 - 1)), int(min_samples_split),
+                self._stream, C.byref(h),
+            )
+        )
+        self._h = h
+        self.correct = None
+        self.n_nodes = None
+
+    def run(self, stream=None):
+        if stream is not None:
+            self._stream = _stream_ptr(stream)
+        _check(load_library().rfmc_batch_run(self._h, self._stream))
+        return self
+
+    def results(self):
+        correct = np.zeros(self.n_cand, dtype=np.int32)
+        n_nodes = np.zeros(self.n_cand, dtype=np.int32)
+        _check(load_library().rfmc_batch_results(self._h, _ptr(correct), _ptr(n_nodes)))
+        self.correct, self.n_nodes = correct, n_nodes
+        return correct, n_nodes
+
+    @property
+    def launches(self) -> int:
+        return load_library().rfmc_batch_launches(self._h)
+
+    def fetch(self, cand_ids: Sequence[int]) -> List[TreeSoA]:
+        """Device -> host copy of the node tables of the selected candidates."""
+        if self.n_nodes is None:
+            self.results()
+        ids = np.ascontiguousarray(cand_ids, dtype=np.int32)
+        if len(ids) == 0:
+            return []
+        sizes = self.n_nodes[ids].astype(np.int64)
+        total = int(sizes.sum())
+        ncls = self.ds.enc.n_classes
+        nodes = np.empty(total, dtype=NODE_DTYPE)
+        counts = np.empty((total, ncls), dtype=np.int32)
+        _check(load_library().rfmc_batch_pack(self._h, _ptr(ids), len(ids), _ptr(nodes), _ptr(counts), 0, self._stream))
+        out, at = [], 0
+        for s in sizes:
+            s = int(s)
+            out.append(TreeSoA(nodes[at : at + s], counts[at : at + s]))
+            at += s
+        return out
+
+    def pack_to_device(self, cand_ids: Sequence[int], nodes_ptr: int, counts_ptr: int):
+        """Pack selected candidates into caller-owned DEVICE buffers (e.g. an all-gather buffer)."""
+        ids = np.ascontiguousarray(cand_ids, dtype=np.int32)
+        _check(load_library().rfmc_batch_pack(self._h, _ptr(ids), len(ids), _p(nodes_ptr), _p(counts_ptr), 1, self._stream))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().rfmc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceForest:
+    """rfmc_forest handle: a flattened forest resident in HBM (useForest / testForest*)."""
+
+    def __init__(self, tables, device: int = 0):
+        require_gpu()
+        self.tables = tables
+        self.device = device
+        self.n_classes = tables.n_classes
+        h = _p()
+        _check(
+            load_library().rfmc_forest_create(
+                device, _ptr(tables.pnodes), len(tables.pnodes), _ptr(tables.roots), len(tables.roots),
+                len(tables.vote), _ptr(tables.vote), _ptr(tables.vote_absent), _ptr(tables.probs),
+                _ptr(tables.probs_absent), tables.n_classes, _ptr(tables.scores), float(tables.score_fsum), C.byref(h),
+            )
+        )
+        self._h = h
+
+    def predict(self, codes: np.ndarray, absent: Optional[np.ndarray], soft: bool, weighted: bool,
+                want_probs: bool = True, want_labels: bool = True, stream=None):
+        codes = np.ascontiguousarray(codes)
+        n, stride = codes.shape
+        probs = np.empty((n, self.n_classes), dtype=np.float64) if want_probs else None
+        labels = np.empty(n, dtype=np.int32) if want_labels else None
+        ab = None if absent is None else np.ascontiguousarray(absent, dtype=np.uint8)
+        _check(
+            load_library().rfmc_forest_predict(
+                self._h, _ptr(codes), codes.dtype.itemsize, n, stride, self.tables.n_features, _ptr(ab), int(bool(soft)),
+                int(bool(weighted)), _ptr(probs), _ptr(labels), 0, _stream_ptr(stream),
+            )
+        )
+        return probs, labels
+
+    def predict_device(self, codes_ptr: int, width: int, n_rows: int, stride: int, absent: Optional[np.ndarray],
+                       soft: bool, weighted: bool, probs_ptr: int, labels_ptr: int, stream=None):
+        """Device-resident variant: pointers are CUDA device addresses; asynchronous on ``stream``."""
+        ab = None if absent is None else np.ascontiguousarray(absent, dtype=np.uint8)
+        _check(
+            load_library().rfmc_forest_predict(
+                self._h, _p(codes_ptr), width, n_rows, stride, self.tables.n_features, _ptr(ab), int(bool(soft)),
+                int(bool(weighted)), _p(probs_ptr) if probs_ptr else None, _p(labels_ptr) if labels_ptr else None, 1,
+                _stream_ptr(stream),
+            )
+        )
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().rfmc_forest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -15,7 +15,7 @@ key order and Python/numpy value types:
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -80,3 +80,211 @@ def soa_to_dict(tree: TreeSoA, enc: EncodedDataset, type_of_cols: Optional[dict]
 def used_feature_ids(tree: TreeSoA) -> List[int]:
     f = tree.nodes["feat"]
     return sorted(set(int(x) for x in np.unique(f[f >= 0])))
+
+
+# --------------------------------------------------------------------------------------------
+# Forest flattening for the voting kernel
+# --------------------------------------------------------------------------------------------
+PNODE_DTYPE = np.dtype([("feat_flags", "<u4"), ("thr", "<u4"), ("child", "<u4"), ("reserved", "<u4")])
+PNODE_LEAF = 0x80000000
+PNODE_CATEGORICAL = 0x40000000
+
+
+@dataclass
+class ForestTables:
+    """A forest flattened for rfmc_forest_create, plus the per-feature code books that map raw
+    frame values into the code space its thresholds live in.
+
+    Code space (last paragraph): for a numeric feature the sorted distinct split
+    values t_0 < t_1 < ... of the whole forest; ``code(x) = #{k : t_k <= x}`` so that
+    ``x >= t_k  <=>  code(x) >= k + 1``; NaN -> 0 (fails every test -> '<', tree.py:177-181).
+    For a categorical feature every distinct split value gets an id >= 1; anything else -> 0."""
+
+    feature_cols: List[str]
+    class_vals: List
+    pnodes: np.ndarray
+    roots: np.ndarray  # int64 [n_trees]
+    vote: np.ndarray  # uint8 [n_payloads] class_vals index
+    vote_absent: np.ndarray
+    probs: np.ndarray  # float64 [n_payloads, C]
+    probs_absent: np.ndarray
+    scores: np.ndarray  # float64 [n_trees]
+    score_fsum: float
+    thresholds: List[Optional[np.ndarray]]  # per feature (numeric)
+    categories: List[Optional[dict]]  # per feature (categorical): value -> id
+    width: int = 1
+    stride: int = 0
+
+    @property
+    def n_classes(self) -> int:
+        return len(self.class_vals)
+
+    @property
+    def n_features(self) -> int:
+        return len(self.feature_cols)
+
+    @property
+    def n_trees(self) -> int:
+        return len(self.roots)
+
+
+def leaf_payload(leaf: dict, class_vals, cidx):
+    """(vote, vote_absent, probs, probs_absent) of one leaf dict.
+    tree.py:185-212 for the absent variant; forest.py:200-202 for the votes."""
+    from math import fsum
+
+    C = len(class_vals)
+    probs = [0.0] * C
+    best, bestp = -1, None
+    for lab, p in leaf.items():  # key order of the leaf dict decides ties
+        k = cidx[lab]
+        probs[k] = float(p)
+        if bestp is None or p > bestp:
+            best, bestp = k, p
+    out = [0 + probs[k] for k in range(C)]
+    out = [v / 1 for v in out]
+    total = fsum(out)
+    pa = [v / total for v in out]
+    besta, bestpa = 0, pa[0]
+    for k in range(1, C):
+        if pa[k] > bestpa:
+            besta, bestpa = k, pa[k]
+    return best, besta, tuple(probs), tuple(pa)
+
+
+def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestTables:
+    """Flatten nested tree dicts (fitted here, merged, or loaded through dict2model)."""
+    from math import fsum
+
+    from .encode import odd_word_stride
+
+    fidx = {name: j for j, name in enumerate(feature_cols)}
+    cidx = {c: k for k, c in enumerate(class_vals)}
+    nfeat = len(feature_cols)
+    if nfeat > 0xFFFF:
+        raise NotImplementedError("more than 65535 feature columns")
+    num_vals = [set() for _ in range(nfeat)]
+    cat_vals = [dict() for _ in range(nfeat)]
+    # pass 1: code books
+    for tree in trees:
+        todo = [tree]
+        while todo:
+            node = todo.pop()
+            name = next(iter(node))
+            if name == "leaf":
+                continue
+            s = node[name]["split"]
+            j = fidx[name]
+            if s["feat_type"] != "numeric":
+                if s["split_val"] not in cat_vals[j]:
+                    cat_vals[j][s["split_val"]] = len(cat_vals[j]) + 1
+            else:
+                num_vals[j].add(float(s["split_val"]))
+            todo.append(s[">="])
+            todo.append(s["<"])
+    thresholds, categories = [], []
+    top = 1
+    for j in range(nfeat):
+        if num_vals[j] and cat_vals[j]:
+            raise NotImplementedError(f"feature {feature_cols[j]!r} is split both as numeric and as categorical")
+        t = np.array(sorted(v for v in num_vals[j] if v == v), dtype=np.float64) if num_vals[j] else None
+        thresholds.append(t)
+        categories.append(cat_vals[j] if cat_vals[j] else None)
+        top = max(top, (len(t) if t is not None else 0), len(cat_vals[j]))
+    width = 1 if top <= 0xFF else (2 if top <= 0xFFFF else 4)
+    # pass 2: nodes (children adjacent: '<' = '>=' + 1) and de-duplicated leaf payloads
+    feat_flags, thr, child, roots = [], [], [], []
+    payload_ids = {}
+    votes, votes_a, probs, probs_a = [], [], [], []
+    for tree in trees:
+        root = len(feat_flags)
+        roots.append(root)
+        feat_flags.append(0), thr.append(0), child.append(0)
+        todo = [(tree, root)]
+        while todo:
+            node, at = todo.pop()
+            name = next(iter(node))
+            if name == "leaf":
+                key = tuple(node["leaf"].items())
+                pid = payload_ids.get(key)
+                if pid is None:
+                    v, va, p, pa = leaf_payload(node["leaf"], class_vals, cidx)
+                    pid = payload_ids[key] = len(votes)
+                    votes.append(v), votes_a.append(va), probs.append(p), probs_a.append(pa)
+                feat_flags[at] = PNODE_LEAF
+                thr[at] = pid
+                continue
+            s = node[name]["split"]
+            j = fidx[name]
+            if s["feat_type"] != "numeric":
+                feat_flags[at] = j | PNODE_CATEGORICAL
+                thr[at] = cat_vals[j][s["split_val"]]
+            else:
+                feat_flags[at] = j
+                sv = float(s["split_val"])
+                # a NaN split value matches nothing: an unreachable code sends every row to '<'
+                thr[at] = int(np.searchsorted(thresholds[j], sv, "left")) + 1 if sv == sv else 0xFFFFFFFF
+            c = len(feat_flags)
+            child[at] = c
+            feat_flags.extend((0, 0)), thr.extend((0, 0)), child.extend((0, 0))
+            todo.append((s["<"], c + 1))
+            todo.append((s[">="], c))
+    pn = np.zeros(len(feat_flags), dtype=PNODE_DTYPE)
+    pn["feat_flags"] = np.array(feat_flags, dtype=np.uint32)
+    pn["thr"] = np.array(thr, dtype=np.uint32)
+    pn["child"] = np.array(child, dtype=np.uint32)
+    ncls = len(class_vals)
+    return ForestTables(
+        feature_cols=list(feature_cols),
+        class_vals=list(class_vals),
+        pnodes=pn,
+        roots=np.array(roots, dtype=np.int64),
+        vote=np.array(votes, dtype=np.uint8),
+        vote_absent=np.array(votes_a, dtype=np.uint8),
+        probs=np.array(probs, dtype=np.float64).reshape(len(votes), ncls),
+        probs_absent=np.array(probs_a, dtype=np.float64).reshape(len(votes), ncls),
+        scores=np.array([float(s) for s in scores], dtype=np.float64),
+        score_fsum=fsum(float(s) for s in scores),
+        thresholds=thresholds,
+        categories=categories,
+        width=width,
+        stride=odd_word_stride(nfeat, width),
+    )
+
+
+def encode_frame(tables: ForestTables, frame):
+    """Raw predict frame -> (codes [n, stride], absent [n_features] uint8).
+
+    Mirrors what ``ds.iterrows()`` + ``row[node]`` hand to the comparisons of tree.py:176-180:
+    a column missing from the frame is *absent* (tree.py:166-175); a NaN / None / unseen cell is
+    code 0.  Numeric values are compared as float64 (exact for float32 and |int| < 2**53)."""
+    import pandas as pd
+
+    n = len(frame)
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[tables.width]
+    codes = np.zeros((n, tables.stride), dtype=dt)
+    absent = np.zeros(tables.n_features, dtype=np.uint8)
+    have = set(frame.columns)
+    for j, name in enumerate(tables.feature_cols):
+        t, cats = tables.thresholds[j], tables.categories[j]
+        if t is None and cats is None:
+            continue  # never tested by any tree
+        if name not in have:
+            absent[j] = 1
+            continue
+        col = frame[name]
+        if t is not None:
+            x = pd.to_numeric(col, errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+            code = np.searchsorted(t, x, "right")
+            code[np.isnan(x)] = 0
+            codes[:, j] = code
+        else:
+            ids, uniques = pd.factorize(col.to_numpy(), use_na_sentinel=True)
+            lut = np.zeros(len(uniques) + 1, dtype=np.int64)  # last slot: NaN sentinel (-1) -> 0
+            for k, u in enumerate(uniques):
+                try:
+                    lut[k] = cats.get(u, 0)
+                except TypeError:
+                    lut[k] = 0
+            codes[:, j] = lut[ids]
+    return codes, absent
