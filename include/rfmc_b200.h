@@ -127,6 +127,12 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
                         int32_t n_features, const uint8_t* absent, int soft, int weighted, double* probs_out,
                         int32_t* labels_out, int on_device, void* stream);
 
+/* Per-(row, tree) leaf export for DecisionTreeMC.__call__ (tree.py:112-113) and per-tree votes
+ * (sampleClass2trees, model.py:406-407): leaves_out [n_rows][n_trees] = payload index, bit 31
+ * set when the walk crossed an absent column.  Host buffers, synchronous. */
+int rfmc_forest_leaves(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
+                       int32_t n_features, const uint8_t* absent, int32_t* leaves_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,4 +367,37 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
     return rc;
 }
 
+int rfmc_forest_leaves(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
+                       int32_t n_features, const uint8_t* absent, int32_t* leaves_out, void* stream) {
+    RFMC_REQUIRE(f != nullptr && leaves_out != nullptr, "forest or output is NULL");
+    RFMC_REQUIRE(code_width == 1 || code_width == 2 || code_width == 4, "code_width must be 1, 2 or 4");
+    RFMC_REQUIRE(n_rows >= 0 && n_features > 0 && row_stride >= n_features, "bad matrix shape");
+    if (n_rows == 0) return 0;
+    RFMC_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    bool has_absent = false;
+    if (absent)
+        for (int i = 0; i < n_features; ++i) has_absent |= absent[i] != 0;
+    uint8_t* d_absent = nullptr;
+    uint8_t* d_codes = nullptr;
+    int32_t* d_out = nullptr;
+    int rc = 0;
+    if (has_absent) rc |= upload(&d_absent, absent, (size_t)n_features, st);
+    rc |= upload(&d_codes, (const uint8_t*)codes, (size_t)n_rows * row_stride * code_width, st);
+    rc |= reserve(&d_out, (size_t)n_rows * f->n_trees);
+    if (!rc) rc = launch_leaves(f, d_codes, code_width, n_rows, row_stride, n_features, d_absent, d_out, st);
+    if (!rc && cudaMemcpyAsync(leaves_out, d_out, (size_t)n_rows * f->n_trees * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                               st) != cudaSuccess)
+        rc = 1;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error(std::string("leaves failed: ") + cudaGetErrorString(e));
+        rc = 1;
+    }
+    release(d_absent);
+    release(d_codes);
+    release(d_out);
+    return rc;
+}
+
 }  // extern "C"

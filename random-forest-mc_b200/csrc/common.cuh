@@ -107,4 +107,6 @@ int launch_pack(rfmc_batch* b, const int32_t* d_cand_ids, const int64_t* d_dst_o
 int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
                    int32_t n_features, const uint8_t* d_absent, bool has_absent, int soft, int weighted, double* d_probs,
                    int32_t* d_labels, cudaStream_t stream);
+int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
+                  int32_t n_features, const uint8_t* d_absent, int32_t* d_out, cudaStream_t stream);
 }  // namespace rfmc

@@ -181,6 +181,65 @@ static int launch_classes(const PredictArgs& a, int mode, bool has_absent, cudaS
     return launch_mode<CodeT, RFMC_MAX_CLASSES>(a, mode, has_absent, stream);
 }
 
+// Per-(row, tree) leaf export: payload index, bit 31 set when the walk crossed an absent column.
+// Serves the single-tree API (Tree(row), tree.py:112-113) and per-tree votes (model.py:406-407).
+template <typename CodeT>
+__global__ void __launch_bounds__(PRED_THREADS) leaves_kernel(PredictArgs a, int32_t* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * PRED_THREADS + threadIdx.x;
+    if (row >= a.n_rows) return;
+    const CodeT* myrow = reinterpret_cast<const CodeT*>(a.codes) + row * a.stride;
+    for (int t = 0; t < a.n_trees; ++t) {
+        uint32_t node = (uint32_t)__ldg(&a.root[t]);
+        bool seen = false;
+        uint4 nd;
+        while (true) {
+            nd = __ldg(reinterpret_cast<const uint4*>(a.nodes) + node);
+            if (nd.x & RFMC_PNODE_LEAF) break;
+            const uint32_t f = nd.x & 0xFFFFu;
+            const uint32_t cv = (uint32_t)__ldg(&myrow[f]);
+            bool go = (nd.x & RFMC_PNODE_CATEGORICAL) ? (cv == nd.y) : (cv >= nd.y);
+            if (a.absent != nullptr && a.absent[f]) {
+                go = true;
+                seen = true;
+            }
+            node = nd.z + (go ? 0u : 1u);
+        }
+        out[row * a.n_trees + t] = (int32_t)(nd.y | (seen ? 0x80000000u : 0u));
+    }
+}
+
+int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
+                  int32_t n_features, const uint8_t* d_absent, int32_t* d_out, cudaStream_t stream) {
+    PredictArgs a;
+    a.codes = d_codes;
+    a.n_rows = n_rows;
+    a.stride = row_stride;
+    a.n_features = n_features;
+    a.nodes = f->d_nodes;
+    a.root = f->d_root;
+    a.n_trees = f->n_trees;
+    a.vote = f->d_vote;
+    a.vote_absent = f->d_vote_absent;
+    a.probs = f->d_probs;
+    a.probs_absent = f->d_probs_absent;
+    a.scores = f->d_scores;
+    a.score_fsum = f->score_fsum;
+    a.n_classes = f->n_classes;
+    a.absent = d_absent;
+    a.probs_out = nullptr;
+    a.labels_out = nullptr;
+    const unsigned blocks = (unsigned)((n_rows + PRED_THREADS - 1) / PRED_THREADS);
+    if (blocks == 0) return 0;
+    switch (code_width) {
+        case 1: leaves_kernel<uint8_t><<<blocks, PRED_THREADS, 0, stream>>>(a, d_out); break;
+        case 2: leaves_kernel<uint16_t><<<blocks, PRED_THREADS, 0, stream>>>(a, d_out); break;
+        case 4: leaves_kernel<uint32_t><<<blocks, PRED_THREADS, 0, stream>>>(a, d_out); break;
+        default: set_error("unsupported code width"); return 1;
+    }
+    RFMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
                    int32_t n_features, const uint8_t* d_absent, bool has_absent, int soft, int weighted, double* d_probs,
                    int32_t* d_labels, cudaStream_t stream) {

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "rfmc_forest_create": (C.c_int, [C.c_int, _p, C.c_int64, _p, C.c_int32, C.c_int64, _p, _p, _p, _p, C.c_int32, _p, C.c_double, C.POINTER(_p)]),
     "rfmc_forest_destroy": (C.c_int, [_p]),
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
+    "rfmc_forest_leaves": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -270,6 +271,21 @@ class DeviceForest:
             )
         )
         return probs, labels
+
+    def leaves(self, codes: np.ndarray, absent: Optional[np.ndarray], stream=None):
+        """Per-(row, tree) payload index and crossed-an-absent-column flag."""
+        codes = np.ascontiguousarray(codes)
+        n, stride = codes.shape
+        out = np.empty((n, self.tables.n_trees), dtype=np.int32)
+        ab = None if absent is None else np.ascontiguousarray(absent, dtype=np.uint8)
+        _check(
+            load_library().rfmc_forest_leaves(
+                self._h, _ptr(codes), codes.dtype.itemsize, n, stride, self.tables.n_features, _ptr(ab), _ptr(out),
+                _stream_ptr(stream),
+            )
+        )
+        payload = out & 0x7FFFFFFF
+        return payload, out < 0
 
     def predict_device(self, codes_ptr: int, width: int, n_rows: int, stride: int, absent: Optional[np.ndarray],
                        soft: bool, weighted: bool, probs_ptr: int, labels_ptr: int, stream=None):

@@ -114,6 +114,7 @@ class ForestTables:
     categories: List[Optional[dict]]  # per feature (categorical): value -> id
     width: int = 1
     stride: int = 0
+    payload_leaf: Optional[list] = None  # dict path only: the leaf dict behind every payload
 
     @property
     def n_classes(self) -> int:
@@ -195,7 +196,7 @@ def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestT
     # pass 2: nodes (children adjacent: '<' = '>=' + 1) and de-duplicated leaf payloads
     feat_flags, thr, child, roots = [], [], [], []
     payload_ids = {}
-    votes, votes_a, probs, probs_a = [], [], [], []
+    votes, votes_a, probs, probs_a, leaf_dicts = [], [], [], [], []
     for tree in trees:
         root = len(feat_flags)
         roots.append(root)
@@ -211,6 +212,7 @@ def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestT
                     v, va, p, pa = leaf_payload(node["leaf"], class_vals, cidx)
                     pid = payload_ids[key] = len(votes)
                     votes.append(v), votes_a.append(va), probs.append(p), probs_a.append(pa)
+                    leaf_dicts.append(node["leaf"])
                 feat_flags[at] = PNODE_LEAF
                 thr[at] = pid
                 continue
@@ -249,6 +251,7 @@ def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestT
         categories=categories,
         width=width,
         stride=odd_word_stride(nfeat, width),
+        payload_leaf=leaf_dicts,
     )
 
 
@@ -288,3 +291,89 @@ def encode_frame(tables: ForestTables, frame):
                     lut[k] = 0
             codes[:, j] = lut[ids]
     return codes, absent
+
+
+def forest_tables_from_soa(trees, scores, enc: EncodedDataset, class_vals, feature_cols) -> ForestTables:
+    """Same tables as ``forest_tables_from_dicts`` but straight from the grower's SoA output,
+    vectorised over all nodes of all trees (no nested dict is ever materialised)."""
+    from math import fsum
+
+    from .encode import odd_word_stride
+
+    nfeat = len(feature_cols)
+    sizes = np.array([t.n_nodes for t in trees], dtype=np.int64)
+    roots = np.zeros(len(trees), dtype=np.int64)
+    roots[1:] = np.cumsum(sizes)[:-1]
+    nodes = np.concatenate([t.nodes for t in trees])
+    counts = np.concatenate([t.counts for t in trees])
+    feat = nodes["feat"].astype(np.int64)
+    flags = nodes["flags"]
+    thr_ds = nodes["thr"].astype(np.int64)
+    is_leaf = feat < 0
+    is_cat = (flags & FLAG_CATEGORICAL) != 0
+    two_row = (flags & FLAG_TWO_ROW) != 0
+    base = np.repeat(roots, sizes)
+
+    ff = np.zeros(len(nodes), dtype=np.uint32)
+    thr = np.zeros(len(nodes), dtype=np.uint32)
+    child = np.where(is_leaf, 0, nodes["child"].astype(np.int64) + base).astype(np.uint32)
+    thresholds, categories = [None] * nfeat, [None] * nfeat
+    top = 1
+    for j in np.unique(feat[~is_leaf]):
+        j = int(j)
+        col = enc.columns[j]
+        m = (feat == j) & ~is_leaf
+        if col.kind == KIND_CATEGORICAL:
+            present = np.unique(thr_ds[m])
+            thr[m] = (np.searchsorted(present, thr_ds[m]) + 1).astype(np.uint32)
+            ff[m] = j | PNODE_CATEGORICAL
+            categories[j] = {col.uniq[int(c) - 1]: k + 1 for k, c in enumerate(present)}
+            top = max(top, len(present))
+        else:
+            vals = np.where(two_row[m], col.table[np.clip(thr_ds[m] - 1, 0, len(col.table) - 1)], nodes["sval"][m])
+            ok = vals == vals
+            t = np.unique(vals[ok])
+            code = np.full(len(vals), 0xFFFFFFFF, dtype=np.int64)
+            code[ok] = np.searchsorted(t, vals[ok], "left") + 1
+            thr[m] = code.astype(np.uint32)
+            ff[m] = j
+            thresholds[j] = t
+            top = max(top, len(t))
+    # leaf payloads, de-duplicated on the class-count vector
+    leaf_rows = counts[is_leaf].astype(np.int64)
+    uniq_rows, inverse = np.unique(leaf_rows, axis=0, return_inverse=True)
+    inverse = np.asarray(inverse).reshape(-1)
+    ff[is_leaf] = PNODE_LEAF
+    thr[is_leaf] = inverse.astype(np.uint32)
+    totals = uniq_rows.sum(axis=1)
+    p_sorted = uniq_rows / totals[:, None]  # int64 / int64 -> correctly rounded, == count/total (model.py:227)
+    s2c = np.asarray(enc.sorted_to_classvals, dtype=np.int64)
+    ncls = len(class_vals)
+    probs = np.zeros((len(uniq_rows), ncls), dtype=np.float64)
+    probs[:, s2c] = p_sorted
+    vote = s2c[np.argmax(uniq_rows, axis=1)].astype(np.uint8)  # first max in sorted-label order
+    probs_absent = np.empty_like(probs)
+    for r in range(len(probs)):
+        row = [0 + float(v) for v in probs[r]]
+        total = fsum(row)
+        probs_absent[r] = [v / 1 / total for v in row]
+    vote_absent = np.argmax(probs_absent, axis=1).astype(np.uint8)
+    width = 1 if top <= 0xFF else (2 if top <= 0xFFFF else 4)
+    pn = np.zeros(len(nodes), dtype=PNODE_DTYPE)
+    pn["feat_flags"], pn["thr"], pn["child"] = ff, thr, child
+    return ForestTables(
+        feature_cols=list(feature_cols),
+        class_vals=list(class_vals),
+        pnodes=pn,
+        roots=roots,
+        vote=vote,
+        vote_absent=vote_absent,
+        probs=probs,
+        probs_absent=probs_absent,
+        scores=np.array([float(s) for s in scores], dtype=np.float64),
+        score_fsum=fsum(float(s) for s in scores),
+        thresholds=thresholds,
+        categories=categories,
+        width=width,
+        stride=odd_word_stride(nfeat, width),
+    )

@@ -1,0 +1,274 @@
+"""``BaseRandomForestMC``: the reference's forest container and inference API (forest.py:28-274)
+with the row loops replaced by one launch of the voting kernel.
+
+Public surface kept byte-compatible: ``predict`` / ``predict_proba`` /
+``useForest`` / ``testForest`` / ``testForestProbs`` (+ the ``*Parallel`` spellings),
+``setSoftVoting`` / ``setWeightedTrees``, ``mergeForest``, ``model2dict`` / ``dict2model``,
+``drop_duplicated_trees``, ``reset_forest``, ``maxProbClas``, ``Forest`` / ``Forest_size``.
+
+The forest is flattened once per distinct tree list (``flat.forest_tables_*``), uploaded to HBM
+(``engine.DeviceForest``) and cached until the list or the scores change.
+"""
+
+from __future__ import annotations
+
+from collections import UserList
+from math import fsum
+from random import shuffle
+from typing import List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import __version__
+from . import engine
+from .flat import ForestTables, encode_frame, forest_tables_from_dicts
+from .tree import DecisionTreeMC
+
+
+class BaseRandomForestMC(UserList):
+    typer_error_msg = "Both objects must be instances of 'RandomForestMC' class."
+
+    def __init__(
+        self,
+        n_trees: int = 16,
+        target_col: str = "target",
+        min_feature: Optional[int] = None,
+        max_feature: Optional[int] = None,
+        temporal_features: bool = False,
+    ) -> None:
+        self.__version__ = __version__
+        self.version = __version__
+        self.model_version = __version__
+        self.target_col = target_col
+        self.min_feature = min_feature
+        self.max_feature = max_feature
+        self.temporal_features = temporal_features
+        self.n_trees = n_trees
+        self.feat_types = ["numeric", "categorical"]
+        self.numeric_cols = None
+        self.feature_cols = None
+        self.type_of_cols = None
+        self.class_vals = None
+        self.data = []
+        self.survived_scores = []
+        self.attr_to_save = [
+            "min_feature",
+            "max_feature",
+            "n_trees",
+            "class_vals",
+            "survived_scores",
+            "version",
+            "numeric_cols",
+            "feature_cols",
+            "type_of_cols",
+            "target_col",
+            "class_vals",
+        ]
+        self.soft_voting = False
+        self.weighted_tree = False
+        self.device = 0
+        self._forest_key = None
+        self._forest_dev: Optional[engine.DeviceForest] = None
+        self._forest_tables: Optional[ForestTables] = None
+
+    def __repr__(self) -> str:
+        return "{}(len(Forest)={},n_trees={},model_version={},module_version={})".format(
+            self.__class__.__name__, len(self.data), self.n_trees, self.model_version, self.version
+        )
+
+    def __eq__(self, other):
+        if not isinstance(other, BaseRandomForestMC):
+            raise TypeError(self.typer_error_msg)
+        return all([getattr(self, att) == getattr(other, att) for att in self.attr_to_save])
+
+    __hash__ = None
+
+    # -- switches (forest.py:151-155) ------------------------------------------------------------
+    def setSoftVoting(self, set: bool = True) -> None:
+        self.soft_voting = set
+
+    def setWeightedTrees(self, set: bool = True) -> None:
+        self.weighted_tree = set
+
+    def reset_forest(self) -> None:
+        self.data = []
+        self.survived_scores = []
+
+    def validFeaturesTemporal(self):
+        return all([x.split("_")[-1].isnumeric() for x in self.feature_cols])
+
+    @property
+    def Forest_size(self) -> int:
+        return len(self)
+
+    @property
+    def Forest(self) -> List[DecisionTreeMC]:
+        return self.data
+
+    @staticmethod
+    def maxProbClas(leaf: dict):
+        """forest.py:200-202: stable descending sort -> first key among equal maxima."""
+        return sorted(leaf.items(), key=lambda x: x[1], reverse=True)[0][0]
+
+    # -- persistence / merge (forest.py:114-190) ---------------------------------------------------
+    def model2dict(self) -> dict:
+        out = {attr: getattr(self, attr) for attr in self.attr_to_save}
+        out["Forest"] = [Tree.tree2dict() for Tree in self.data]
+        return out
+
+    def dict2model(self, dict_model: dict, add: bool = False) -> None:
+        new_trees = [
+            DecisionTreeMC(t["data"], t["class_vals"], t["survived_score"], t["features"], t["used_features"])
+            for t in dict_model["Forest"]
+        ]
+        if add:
+            self.data.extend(new_trees)
+            self.survived_scores.extend(dict_model["survived_scores"])
+        for attr in self.attr_to_save:
+            setattr(self, attr, dict_model[attr])
+        self.model_version = self.version
+        self.version = self.__version__
+        self.data = new_trees  # forest.py:184 -- also on add=True, kept as is
+
+    def mergeForest(self, otherForest, N: int = -1, by: str = "add"):
+        if not isinstance(otherForest, BaseRandomForestMC):
+            raise TypeError(self.typer_error_msg)
+        same = (
+            all(c in otherForest.class_vals for c in self.class_vals)
+            and all(c in self.class_vals for c in otherForest.class_vals)
+            and all(f in otherForest.feature_cols for f in self.feature_cols)
+            and all(f in self.feature_cols for f in otherForest.feature_cols)
+        )
+        if not same:
+            raise ValueError("Both forests must have the same set of features and classes.")
+        if by == "add":
+            self.data.extend(otherForest.data)
+        if by == "score":
+            self.data = sorted(self.data + otherForest.data)[::-1][:N]
+        if by == "random":
+            data = self.data + otherForest.data
+            shuffle(data)
+            self.data = data[:N]
+        self.survived_scores = [Tree.survived_score for Tree in self.data]
+
+    def drop_duplicated_trees(self) -> int:
+        seen, keep = set(), []
+        for Tree in self.data:
+            h = Tree.md5hexdigest
+            keep.append(h not in seen)
+            seen.add(h)
+        self.data = [Tree for Tree, k in zip(self.data, keep) if k]
+        self.survived_scores = [s for s, k in zip(self.survived_scores, keep) if k]
+        return sum(keep)
+
+    # -- the GPU forest ------------------------------------------------------------------------------
+    def _device_forest(self) -> engine.DeviceForest:
+        if len(self.data) == 0:
+            raise ZeroDivisionError("the forest is empty")
+        key = (tuple(id(t) for t in self.data), tuple(float(s) for s in self.survived_scores), tuple(self.class_vals))
+        if key != self._forest_key or self._forest_dev is None:
+            if self._forest_dev is not None:
+                self._forest_dev.close()
+            tables = self._flatten()
+            self._forest_dev = engine.DeviceForest(tables, self.device)
+            self._forest_tables = tables
+            self._forest_key = key
+        return self._forest_dev
+
+    def _flatten(self) -> ForestTables:
+        from .flat import forest_tables_from_soa
+
+        scores = list(self.survived_scores)
+        if len(scores) != len(self.data):  # dict2model(add=True) leaves them out of step (forest.py:177-184)
+            scores = scores[: len(self.data)] + [0.0] * max(0, len(self.data) - len(scores))
+        if all(getattr(t, "soa", None) is not None and t._data is None for t in self.data):
+            enc = self.data[0]._enc
+            if all(t._enc is enc for t in self.data):
+                return forest_tables_from_soa([t.soa for t in self.data], scores, enc, self.class_vals, self.feature_cols)
+        return forest_tables_from_dicts([t.data for t in self.data], scores, self.class_vals, self.feature_cols)
+
+    def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool):
+        dev = self._device_forest()
+        codes, absent = encode_frame(self._forest_tables, frame)
+        return dev.predict(codes, absent, self.soft_voting, self.weighted_tree, want_probs, want_labels)
+
+    # -- inference API (forest.py:100-112, 204-274) ----------------------------------------------
+    def useForest(self, row) -> dict:
+        if isinstance(row, dict):
+            row = pd.Series(row)
+        frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
+        probs, _ = self._vote_frame(frame, True, False)
+        return {c: float(p) for c, p in zip(self.class_vals, probs[0])}
+
+    def testForest(self, ds: pd.DataFrame) -> list:
+        if len(ds) == 0:
+            return []
+        _, labels = self._vote_frame(ds, False, True)
+        cv = self.class_vals
+        return [cv[k] for k in labels]
+
+    def testForestProbs(self, ds: pd.DataFrame) -> List[dict]:
+        if len(ds) == 0:
+            return []
+        probs, _ = self._vote_frame(ds, True, False)
+        cv = self.class_vals
+        return [dict(zip(cv, row)) for row in probs.tolist()]
+
+    def _testForest_func(self, row):
+        return self.maxProbClas(self.useForest(row))
+
+    def testForestParallel(self, ds: pd.DataFrame, max_workers: Optional[int] = None, chunksize: Optional[int] = None):
+        """Same result as ``testForest``; the row parallelism lives in the kernel."""
+        return self.testForest(ds)
+
+    def testForestProbsParallel(self, ds: pd.DataFrame, max_workers: Optional[int] = None, chunksize: Optional[int] = None):
+        return self.testForestProbs(ds)
+
+    def predict_proba(self, row_or_matrix, prob_output: bool = True):
+        return self.predict(row_or_matrix, prob_output)
+
+    def predict(self, row_or_matrix, prob_output: bool = False):
+        if isinstance(row_or_matrix, pd.Series):
+            return self.useForest(row_or_matrix)
+        if isinstance(row_or_matrix, pd.DataFrame):
+            if prob_output:
+                return self.testForestProbs(row_or_matrix)
+            return self.testForest(row_or_matrix)
+        raise TypeError("The input argument must be a Pandas Series or a Pandas DataFrame.")
+
+
+def _single_tree_output(tree: DecisionTreeMC, row) -> dict:
+    """``Tree(row)`` (tree.py:185-212): a one-tree forest through the leaf-export kernel; the
+    payload index maps back to the leaf dict, or to the renormalised all-classes dict when the
+    walk crossed a column the row does not have (tree.py:201-212)."""
+    if isinstance(row, dict):
+        row = pd.Series(row)
+    feats = tree.features
+    if feats is None:
+        feats = sorted(_features_of(tree.data))
+    tables = forest_tables_from_dicts([tree.data], [1.0], tree.class_vals, feats)
+    dev = engine.DeviceForest(tables)
+    try:
+        frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
+        codes, absent = encode_frame(tables, frame)
+        payload, seen = dev.leaves(codes, absent)
+    finally:
+        dev.close()
+    pid = int(payload[0, 0])
+    if seen[0, 0]:
+        return {c: float(p) for c, p in zip(tree.class_vals, tables.probs_absent[pid])}
+    return tables.payload_leaf[pid]
+
+
+def _features_of(node, out=None):
+    out = set() if out is None else out
+    todo = [node]
+    while todo:
+        n = todo.pop()
+        name = next(iter(n))
+        if name != "leaf":
+            out.add(name)
+            todo.append(n[name]["split"][">="])
+            todo.append(n[name]["split"]["<"])
+    return out

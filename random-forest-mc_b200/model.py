@@ -1,0 +1,536 @@
+"""``RandomForestMC``: the reference's training API (model.py:90-404) driving the CUDA engine.
+
+What stays on the host, bit-for-bit as in the reference:
+  * ``process_dataset`` semantics (model.py:162-195) -- plus the one-time rank-code encode + upload;
+  * every random draw: ``split_train_val`` (model.py:198-210, numpy's global legacy RNG) and
+    ``sampleFeats`` (model.py:213-219, numpy + CPython ``random``), in the reference's call order;
+  * the Monte-Carlo keep/discard policy of ``survivedTree`` (model.py:317-348).
+
+What moves to the GPU: growing every candidate (``plantTree``) and scoring it on its hold-out rows
+(``validationTree``), for many slots and candidates per launch.
+
+Batching without changing the RNG streams: how many ``sampleFeats`` draws a slot
+consumes depends on the scores, so the planner draws a batch of slots *speculatively* (assuming
+each slot uses all ``max_discard_trees`` candidates, or one when trees mostly pass), snapshots both
+RNG states after every draw, lets the GPU grow and score everything, replays the reference's
+policy over the returned scores and -- at the first slot that stopped earlier or later than
+assumed -- rewinds both RNGs to the snapshot after that slot's last consumed draw and replans from
+there.  The committed sequence of draws is therefore exactly the serial reference's.
+"""
+
+from __future__ import annotations
+
+import logging as log
+import random as _pyrandom
+from sys import getrecursionlimit
+from typing import List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import engine
+from .encode import EncodedDataset, encode_dataset
+from .flat import encode_frame, forest_tables_from_dicts, used_feature_ids
+from .forest import BaseRandomForestMC
+from .tree import DecisionTreeMC
+
+
+class MissingValuesNotFound(Exception):
+    def __init__(
+        self,
+        message="Dataset or row without missing values! Please, give a dataset or row with missing values using 'NaN'.",
+    ):
+        super().__init__(message)
+
+
+class DatasetNotFound(Exception):
+    def __init__(self, message="Dataset not found! Please, give a dataset for functions fit() or process_dataset()."):
+        super().__init__(message)
+
+
+class DictValuesAllFeaturesMissing(Exception):
+    def __init__(
+        self,
+        message="All features in the given dictionary 'dict_values' are not found int he trained model (forest).",
+    ):
+        super().__init__(message)
+
+
+class _SlotJudge:
+    """The keep/discard state machine of one ``survivedTree`` call (model.py:319-342)."""
+
+    def __init__(self, th_start, delta_th, max_discard_trees, get_best_tree):
+        self.threshold = th_start
+        self.delta_th = delta_th
+        self.max_discard = max_discard_trees
+        self.get_best = get_best_tree
+        self.failures = 0
+        self.best = None
+        self.best_score = 0.0
+        self.choice = None
+        self.done = False
+        self.used = 0
+
+    def feed(self, cand, score) -> bool:
+        self.used += 1
+        if score < self.threshold:
+            if self.get_best and self.best_score < score:
+                self.best, self.best_score = cand, score
+        else:
+            self.best_score = score
+            self.choice = cand
+            self.done = True
+            return True
+        self.failures += 1
+        if self.failures >= self.max_discard:
+            if self.get_best:
+                self.choice = self.best  # None when every score was 0.0: the reference raises here
+                self.done = True
+                return True
+            self.threshold -= self.delta_th
+            log.info("New threshold for drop: {:.4f}".format(self.threshold))
+        return False
+
+
+class RandomForestMC(BaseRandomForestMC):
+    def __init__(
+        self,
+        n_trees: int = 16,
+        target_col: str = "target",
+        batch_train_pclass: int = 10,
+        batch_val_pclass: int = 10,
+        max_discard_trees: int = 10,
+        delta_th: float = 0.1,
+        th_start: float = 1.0,
+        get_best_tree: bool = True,
+        min_feature: Optional[int] = None,
+        max_feature: Optional[int] = None,
+        th_decease_verbose: bool = False,
+        temporal_features: bool = False,
+        split_with_replace: bool = False,
+        max_depth: Optional[int] = None,
+        min_samples_split: int = 1,
+        got_best_tree_verbose: bool = False,
+        threaded_fit: bool = False,
+    ) -> None:
+        super().__init__(
+            n_trees=n_trees,
+            target_col=target_col,
+            min_feature=min_feature,
+            max_feature=max_feature,
+            temporal_features=temporal_features,
+        )
+        self.split_with_replace = split_with_replace
+        if th_decease_verbose:
+            log.basicConfig(level=log.INFO)
+        self.batch_train_pclass = batch_train_pclass
+        self.batch_val_pclass = batch_val_pclass
+        self._N = batch_train_pclass + batch_val_pclass
+        self.th_start = th_start
+        self.delta_th = delta_th
+        self.max_discard_trees = max_discard_trees
+        self.dataset = None
+        self.dataset_numpy = None
+        self.max_depth = getrecursionlimit() if max_depth is None else int(max_depth)
+        self.min_samples_split = int(min_samples_split)
+        self.got_best_tree_verbose = got_best_tree_verbose
+        self.get_best_tree = get_best_tree
+        self.threaded_fit = threaded_fit
+        # engine state
+        self.encoded: Optional[EncodedDataset] = None
+        self._dev_dataset: Optional[engine.DeviceDataset] = None
+        self.fit_stats = {}
+        self.max_candidates_per_launch = 4096
+        self.max_batch_bytes = 24 << 30
+
+    # ---------------------------------------------------------------------------------------------
+    # process_dataset (model.py:162-195)
+    # ---------------------------------------------------------------------------------------------
+    def process_dataset(self, dataset: pd.DataFrame) -> None:
+        dataset[self.target_col] = dataset[self.target_col].astype(str)
+        feature_cols = [col for col in dataset.columns if col != self.target_col]
+        numeric_cols = dataset.select_dtypes([np.number]).columns.to_list()
+        categorical_cols = list(set(feature_cols) - set(numeric_cols))
+        type_of_cols = {col: "numeric" for col in numeric_cols}
+        type_of_cols.update({col: "categorical" for col in categorical_cols})
+        if self.min_feature is None:
+            self.min_feature = 2
+        if self.max_feature is None:
+            self.max_feature = len(feature_cols)
+        self.numeric_cols = numeric_cols
+        self.feature_cols = feature_cols
+        self.type_of_cols = type_of_cols
+        dataset = dataset.dropna()
+        log.warning("Rows with missing values were dropped from the dataset.")
+        self.class_vals = dataset[self.target_col].unique().tolist()
+        if self.temporal_features and (not self.validFeaturesTemporal()):
+            self.temporal_features = False
+            log.warning("Temporal features ordering disable: you do not have all orderable features!")
+        min_class = dataset[self.target_col].value_counts().min()
+        self._N = min(self._N, min_class)
+        self.dataset_numpy = {col: dataset[col].to_numpy() for col in dataset.columns}
+        self.n_samples = len(dataset)
+        # engine: encode once, upload once
+        if self.min_samples_split < 1:
+            raise ValueError("min_samples_split must be >= 1")
+        self.encoded = encode_dataset(self.dataset_numpy, feature_cols, numeric_cols, self.target_col, self.class_vals)
+        if self._dev_dataset is not None:
+            self._dev_dataset.close()
+        self._dev_dataset = engine.DeviceDataset(self.encoded, self.device)
+
+    # ---------------------------------------------------------------------------------------------
+    # host RNG draws, exactly the reference's (model.py:198-219)
+    # ---------------------------------------------------------------------------------------------
+    def split_train_val(self) -> Tuple[np.ndarray, np.ndarray]:
+        idx_train: list = []
+        idx_val: list = []
+        for class_indices in self.encoded.class_rows:  # == indices[target_vals == val], cached (no RNG use)
+            selected = np.random.choice(class_indices, self._N, replace=False)
+            idx_train.extend(selected[: self.batch_train_pclass])
+            idx_val.extend(selected[self.batch_train_pclass :])
+        return np.array(idx_train), np.array(idx_val)
+
+    def sampleFeats(self, feature_cols: List[str]) -> List[str]:
+        n_samples = np.random.randint(self.min_feature, self.max_feature + 1)
+        out = _pyrandom.sample(feature_cols, min(len(feature_cols), n_samples))
+        if not self.temporal_features:
+            return out
+        return sorted(out, key=lambda x: int(x.split("_")[-1]))
+
+    # ---------------------------------------------------------------------------------------------
+    # single-candidate API (model.py:264-314), one launch each
+    # ---------------------------------------------------------------------------------------------
+    def _require_dataset(self):
+        if self.dataset_numpy is None or self._dev_dataset is None:
+            raise DatasetNotFound
+
+    def _feat_ids(self, feature_list: List[str]) -> List[int]:
+        pos = {name: j for j, name in enumerate(self.feature_cols)}
+        return [pos[f] for f in feature_list]
+
+    def _wrap(self, soa, score=None) -> DecisionTreeMC:
+        t = DecisionTreeMC.from_soa(soa, self.encoded, self.type_of_cols, self.class_vals)
+        t.survived_score = score
+        return t
+
+    def plantTree(self, indices: np.ndarray, feature_list: List[str]) -> DecisionTreeMC:
+        self._require_dataset()
+        idx = np.asarray(indices).reshape(1, -1)
+        b = engine.GrowBatch(
+            self._dev_dataset, idx, np.zeros((1, 0), dtype=np.int32), [0], [self._feat_ids(feature_list)],
+            self.max_depth, self.min_samples_split,
+        ).run()
+        try:
+            return self._wrap(b.fetch([0])[0])
+        finally:
+            b.close()
+
+    def validationTree(self, Tree: DecisionTreeMC, indices: np.ndarray):
+        """model.py:296-314: hold-out accuracy of one tree, through the voting kernel."""
+        self._require_dataset()
+        indices = np.asarray(indices)
+        tables = forest_tables_from_dicts([Tree.data], [1.0], self.class_vals, self.feature_cols)
+        frame = pd.DataFrame({c: self.dataset_numpy[c][indices] for c in self.feature_cols})
+        dev = engine.DeviceForest(tables, self.device)
+        try:
+            codes, absent = encode_frame(tables, frame)
+            _, labels = dev.predict(codes, absent, False, False, False, True) if len(indices) else (None, np.zeros(0, dtype=np.int32))
+        finally:
+            dev.close()
+        y_val = self.dataset_numpy[self.target_col][indices]
+        y_pred = [self.class_vals[k] for k in labels]
+        return np.mean(y_val == y_pred)
+
+    def tree2feats(self, Tree) -> List[str]:
+        soa = getattr(Tree, "soa", None)
+        if soa is not None and Tree._data is None:
+            return [self.feature_cols[j] for j in used_feature_ids(soa)]
+        found, todo = set(), [Tree.data]
+        while todo:
+            node = todo.pop()
+            name = next(iter(node))
+            if name != "leaf":
+                found.add(name)
+                todo.append(node[name]["split"][">="])
+                todo.append(node[name]["split"]["<"])
+        return [f for f in self.feature_cols if f in found]
+
+    # ---------------------------------------------------------------------------------------------
+    # the batched, speculative fit loop
+    # ---------------------------------------------------------------------------------------------
+    def _snapshot(self):
+        return np.random.get_state(), _pyrandom.getstate()
+
+    @staticmethod
+    def _restore(snap):
+        np.random.set_state(snap[0])
+        _pyrandom.setstate(snap[1])
+
+    def _draw_slot(self, n_cands: int, idx=None):
+        """One slot's draws: rows once (unless continuing a slot), then ``n_cands`` feature lists.
+        Returns (idx_T, idx_V, [feature id lists], [RNG snapshots after each sampleFeats])."""
+        if idx is None:
+            idx = self.split_train_val()
+        feats, snaps = [], []
+        for _ in range(n_cands):
+            feats.append(self._feat_ids(self.sampleFeats(self.feature_cols[:])))
+            snaps.append(self._snapshot())
+        return idx[0], idx[1], feats, snaps
+
+    def _candidate_bytes(self) -> int:
+        n_train = self.batch_train_pclass * len(self.class_vals) if self._N > self.batch_train_pclass else self._N * len(self.class_vals)
+        return 2 * max(1, n_train) * (24 + 4 * len(self.class_vals) + 1)
+
+    def _grow_plan(self, plan, stream=None):
+        """One launch for every (slot, candidate) of the plan.  Returns (batch, first cand id per slot)."""
+        idx_T = np.stack([p[0] for p in plan])
+        idx_V = np.stack([p[1] for p in plan])
+        slot_of, feats, first = [], [], []
+        for s, p in enumerate(plan):
+            first.append(len(feats))
+            for f in p[2]:
+                slot_of.append(s)
+                feats.append(f)
+        b = engine.GrowBatch(self._dev_dataset, idx_T, idx_V, slot_of, feats, self.max_depth, self.min_samples_split, stream)
+        b.run()
+        return b, first
+
+    def _score(self, correct, n_val):
+        """th_val = np.mean(y_val == y_pred) (model.py:314); NaN for an empty hold-out set."""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.float64(correct) / np.float64(n_val) if n_val else np.float64("nan")
+
+    def _fit_slots(self, n_slots: int, stream=None):
+        """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's."""
+        self._require_dataset()
+        trees: List[DecisionTreeMC] = []
+        stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0)
+        K = max(1, int(self.max_discard_trees))
+        cap = max(1, min(self.max_candidates_per_launch, self.max_batch_bytes // max(1, self._candidate_bytes())))
+        assume_pass = False  # hypothesis on the candidates a slot consumes: K, or 1 when trees mostly pass
+        recent_used: List[int] = []
+        avg_commit = float("inf")
+        while len(trees) < n_slots:
+            spec = 1 if assume_pass else K
+            n_plan = min(n_slots - len(trees), max(1, cap // spec))
+            if avg_commit != float("inf"):
+                n_plan = min(n_plan, max(4, int(4 * avg_commit) + 1))
+            plan = [self._draw_slot(spec) for _ in range(n_plan)]
+            batch, first = self._grow_plan(plan, stream)
+            try:
+                correct, _ = batch.results()
+                stats["batches"] += 1
+                stats["gpu_launches"] += batch.launches
+                stats["candidates_grown"] += batch.n_cand
+                chosen: List[Tuple[int, float]] = []
+                resume = extend = None
+                for s, p in enumerate(plan):
+                    judge = _SlotJudge(self.th_start, self.delta_th, self.max_discard_trees, self.get_best_tree)
+                    for k in range(spec):
+                        if judge.feed(first[s] + k, self._score(correct[first[s] + k], batch.n_val)):
+                            break
+                    if not judge.done:
+                        # needs more candidates than were drawn: everything drawn after this slot is
+                        # off-stream; continue the slot from the state right after its last draw
+                        resume, extend = p[3][-1], (p, judge)
+                        break
+                    chosen.append((judge.choice, judge.best_score))
+                    stats["candidates_used"] += judge.used
+                    recent_used.append(judge.used)
+                    if judge.used != spec:
+                        resume = p[3][judge.used - 1]
+                        break
+                self._collect(batch, chosen, trees)
+                committed = len(chosen)
+                if resume is not None:
+                    stats["rewinds"] += 1
+                    self._restore(resume)
+                if extend is not None:
+                    trees.append(self._extend_slot(extend[0], extend[1], batch, stream, stats))
+                    recent_used.append(extend[1].used)
+                    committed += 1
+            finally:
+                batch.close()
+            avg_commit = committed if avg_commit == float("inf") else 0.5 * avg_commit + 0.5 * committed
+            if len(recent_used) >= 4:
+                tail = recent_used[-16:]
+                assume_pass = K > 1 and (sum(1 for u in tail if u == 1) * 2 > len(tail))
+        for t in trees:
+            t.features = self.feature_cols
+            t.used_features = self.tree2feats(t)
+        self.fit_stats = stats
+        return trees
+
+    def _collect(self, batch, chosen, trees_out):
+        ids = []
+        for cid, _ in chosen:
+            if cid is None:
+                raise AttributeError("'NoneType' object has no attribute 'survived_score'")  # model.py:345
+            ids.append(cid)
+        for soa, (_, score) in zip(batch.fetch(ids), chosen):
+            trees_out.append(self._wrap(soa, score))
+
+    def _extend_slot(self, p, judge, batch, stream, stats) -> DecisionTreeMC:
+        """A slot that outlived its speculation (a decaying threshold with get_best_tree=False, or a
+        first candidate that failed under the trees-mostly-pass hypothesis): keep drawing feature
+        lists for the same rows until the reference's policy stops."""
+        K = max(1, int(self.max_discard_trees))
+        kept = {}
+        if judge.best is not None:
+            kept[judge.best] = batch.fetch([judge.best])[0]
+        it = 0
+        while True:
+            it += 1
+            _, _, feats, snaps = self._draw_slot(K, idx=(p[0], p[1]))
+            b, _ = self._grow_plan([(p[0], p[1], feats, snaps)], stream)
+            try:
+                correct, _ = b.results()
+                stats["gpu_launches"] += b.launches
+                stats["candidates_grown"] += b.n_cand
+                stop = None
+                for k in range(K):
+                    ref = ("ext", it, k)
+                    done = judge.feed(ref, self._score(correct[k], b.n_val))
+                    if judge.best == ref and ref not in kept:
+                        kept = {ref: b.fetch([k])[0]}
+                    if done:
+                        stop = k
+                        break
+                if stop is None:
+                    continue
+                choice = judge.choice
+                if choice is None:
+                    raise AttributeError("'NoneType' object has no attribute 'survived_score'")  # model.py:345
+                soa = kept.get(choice)
+                if soa is None:
+                    soa = b.fetch([choice[2]])[0]  # the candidate that met the threshold, in this launch
+                if stop != K - 1:
+                    stats["rewinds"] += 1
+                    self._restore(snaps[stop])
+                stats["candidates_used"] += judge.used
+                return self._wrap(soa, judge.best_score)
+            finally:
+                b.close()
+
+    # ---------------------------------------------------------------------------------------------
+    # public training API (model.py:317-404)
+    # ---------------------------------------------------------------------------------------------
+    def survivedTree(self, _=None) -> DecisionTreeMC:
+        tree = self._fit_slots(1)[0]
+        if self.got_best_tree_verbose:
+            log.info("Got best tree: {:.4f}".format(tree.survived_score))
+        return tree
+
+    def fit(self, dataset: Optional[pd.DataFrame] = None, disable_progress_bar: bool = False) -> None:
+        if dataset is not None:
+            self.process_dataset(dataset)
+        if self.dataset_numpy is None:
+            raise DatasetNotFound
+        Forest = self._fit_slots(self.n_trees)
+        self.data.extend(Forest)
+        self.survived_scores.extend([Tree.survived_score for Tree in Forest])
+
+    def fitParallel(
+        self,
+        dataset: Optional[pd.DataFrame] = None,
+        disable_progress_bar: bool = False,
+        max_workers: Optional[int] = None,
+    ):
+        """The multi-GPU analogue of the reference's process pool (model.py:372-404): tree slots are
+        sharded over the ranks of the default torch.distributed group (one process per GPU), each
+        rank replays the serial algorithm on its own seeded streams, survivors are all-gathered.
+        Without an initialised process group this is ``fit``."""
+        if dataset is not None:
+            self.process_dataset(dataset)
+        if self.dataset_numpy is None:
+            raise DatasetNotFound
+        from . import dist
+
+        if not dist.is_distributed():
+            Forest = self._fit_slots(self.n_trees)
+        else:
+            Forest = dist.fit_sharded(self)
+        self.data.extend(Forest)
+        self.survived_scores.extend([Tree.survived_score for Tree in Forest])
+
+    # ---------------------------------------------------------------------------------------------
+    # explainability helpers on top of used_features / per-tree votes (model.py:406-493)
+    # ---------------------------------------------------------------------------------------------
+    def sampleClass2trees(self, row, Class) -> List[DecisionTreeMC]:
+        """Trees whose own vote for ``row`` is ``Class`` (model.py:406-407), via the leaf-export kernel."""
+        if isinstance(row, dict):
+            row = pd.Series(row)
+        dev = self._device_forest()
+        frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
+        codes, absent = encode_frame(self._forest_tables, frame)
+        payload, seen = dev.leaves(codes, absent)
+        t = self._forest_tables
+        votes = np.where(seen[0], t.vote_absent[payload[0]], t.vote[payload[0]])
+        return [Tree for Tree, v in zip(self.data, votes) if self.class_vals[int(v)] == Class]
+
+    @property
+    def trees2depths(self) -> List[List[int]]:
+        return [tree.depths for tree in self.data]
+
+    def featCount(self, Forest=None):
+        if Forest is None:
+            Forest = self.data
+        out = [len(Tree.used_features) for Tree in Forest]
+        return (np.mean(out), np.std(out), min(out), max(out)), out
+
+    def featImportance(self, Forest=None):
+        if Forest is None:
+            Forest = self.data
+        n, seen = len(Forest), {}
+        for tree in Forest:
+            for feat in tree.used_features:
+                seen[feat] = seen.get(feat, 0) + 1
+        return {feat: c / n for feat, c in seen.items()}
+
+    def featScoreMean(self, Forest=None):
+        if Forest is None:
+            Forest = self.data
+        acc = {}
+        for Tree, score in zip(Forest, self.survived_scores):
+            for feat in Tree.used_features:
+                acc.setdefault(feat, []).append(score)
+        return {feat: np.mean(s) for feat, s in acc.items()}
+
+    def featPairImportance(self, disable_progress_bar=False, Forest=None):
+        from itertools import combinations
+
+        if Forest is None:
+            Forest = self.data
+        n, out = len(Forest), {}
+        for Tree in Forest:
+            used = set(Tree.used_features)
+            for pair in combinations(self.feature_cols, 2):
+                if pair[0] in used and pair[1] in used:
+                    out[pair] = out.get(pair, 0) + 1 / n
+        return out
+
+    def featCorrDataFrame(self, Forest=None) -> pd.DataFrame:
+        N = len(self.feature_cols)
+        matrix = np.zeros((N, N), dtype=np.float16)
+        for feat, count in self.featImportance(Forest=Forest).items():
+            i = self.feature_cols.index(feat)
+            matrix[i][i] = count
+        for pair, count in self.featPairImportance(Forest=Forest).items():
+            a, b = self.feature_cols.index(pair[0]), self.feature_cols.index(pair[1])
+            matrix[a][b], matrix[b][a] = count, count
+        return pd.DataFrame(matrix, index=self.feature_cols, columns=self.feature_cols)
+
+    def sampleClassFeatCount(self, row, Class):
+        return self.featCount(self.sampleClass2trees(row=row, Class=Class))
+
+    def sampleClassFeatImportance(self, row, Class):
+        return self.featImportance(self.sampleClass2trees(row=row, Class=Class))
+
+    def sampleClassFeatScoreMean(self, row, Class):
+        return self.featScoreMean(self.sampleClass2trees(row=row, Class=Class))
+
+    def sampleClassFeatPairImportance(self, row, Class):
+        return self.featPairImportance(Forest=self.sampleClass2trees(row=row, Class=Class))
+
+    def sampleClassFeatCorrDataFrame(self, row, Class):
+        return self.featCorrDataFrame(self.sampleClass2trees(row=row, Class=Class))

@@ -114,6 +114,18 @@ CASES = [
 ]
 
 
+def rng_fingerprint():
+    """Position-sensitive fingerprint of both global RNG states (numpy legacy MT19937 + CPython)."""
+    import hashlib
+
+    st = np.random.get_state()
+    h = hashlib.sha256()
+    h.update(st[1].tobytes())
+    h.update(repr(st[2:]).encode())
+    h.update(repr(random.getstate()).encode())
+    return h.hexdigest()
+
+
 def record(name, build, kwargs, seed, n_pred):
     from random_forest_mc.model import RandomForestMC  # the real reference
 
@@ -148,6 +160,7 @@ def record(name, build, kwargs, seed, n_pred):
     random.seed(seed)
     train = frame.copy()
     model.fit(train, disable_progress_bar=True)
+    rng_after = rng_fingerprint()
 
     tcol = kwargs["target_col"]
     base = frame.drop(columns=[tcol]).iloc[:: max(1, len(frame) // n_pred)].head(n_pred).reset_index(drop=True)
@@ -186,6 +199,7 @@ def record(name, build, kwargs, seed, n_pred):
         "md5": [t.md5hexdigest for t in model.data],
         "frames": frames,
         "preds": preds,
+        "rng_after": rng_after,
     }
 
 

@@ -1,0 +1,82 @@
+"""CPU: the drop-in API's host logic (speculative batching + RNG rewind, policy, flattening,
+persistence, merge) on an oracle-backed fake engine, against the reference's recorded vectors."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests import fake_engine, model_checks
+from tests.helpers import golden_names, load_golden
+
+
+@pytest.fixture(autouse=True)
+def _fake(monkeypatch):
+    fake_engine.install(monkeypatch)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fit_and_predict_match_reference(name):
+    g, m = model_checks.check_fit_matches_reference(name)
+    model_checks.check_predictions_match_reference(g, m)
+
+
+@pytest.mark.parametrize("name", ["titanic_c1", "mixed_feat", "mixed_nobest"])
+@pytest.mark.parametrize("cap", [1, 3, 7])
+def test_fit_is_independent_of_batch_size(name, cap):
+    """Tiny launch caps force many plans, rewinds and slot extensions: the forest must not change."""
+    model_checks.check_fit_matches_reference(name, max_candidates_per_launch=cap)
+
+
+def test_persistence_and_merge():
+    g, m = model_checks.fitted_model("mixed_default")
+    model_checks.check_persistence_and_merge(g, m)
+
+
+def test_single_tree_call_and_class_trees():
+    g, m = model_checks.fitted_model("titanic_c1")
+    from oracle import rfmc_oracle as orc
+
+    fr = g["frames"]["absent_nan"]
+    for i in (0, 5, 11):
+        row = fr.iloc[i]
+        for tree, ref in zip(m.data, g["forest"]):
+            want = orc.tree_output(ref, g["class_vals"], row)
+            got = tree(row)
+            assert list(got.keys()) == list(want.keys())
+            assert all(float(got[k]) == float(want[k]) for k in want)
+        for c in g["class_vals"]:
+            want_trees = [k for k, ref in enumerate(g["forest"]) if orc.top_class(orc.tree_output(ref, g["class_vals"], row)) == c]
+            got_trees = [k for k, t in enumerate(m.data) if any(t is x for x in m.sampleClass2trees(row, c))]
+            assert got_trees == want_trees
+
+
+def test_errors_mirror_reference():
+    from random_forest_mc_b200.model import DatasetNotFound, RandomForestMC
+
+    m = RandomForestMC()
+    with pytest.raises(DatasetNotFound):
+        m.fit()
+    with pytest.raises(TypeError):
+        m.predict([1, 2, 3])
+    with pytest.raises(TypeError):
+        m.mergeForest("nope")
+    g, a = model_checks.fitted_model("ties_default")
+    _, b = model_checks.fitted_model("mixed_default")
+    with pytest.raises(ValueError):
+        a.mergeForest(b)
+    assert a.testForest(g["frames"]["clean"].head(0)) == []
+
+
+def test_depths_and_plant_validate_single_calls():
+    g, m = model_checks.fitted_model("mixed_mss3_d6")
+    for t in m.data:
+        assert max(t.depths) <= 6
+        dict_depths = t.depths
+        t.data  # materialise
+        t._soa = None
+        assert t.depths == dict_depths
+    ref = g["trace"][0]
+    t = m.plantTree(ref["idx_T"], ref["F"])
+    from tests.helpers import tree_diff
+
+    assert tree_diff(t.data, ref["tree"]) is None
+    assert float(m.validationTree(t, ref["idx_V"])) == float(ref["th_val"])
