@@ -1,0 +1,526 @@
+#!/usr/bin/env python
+"""Benchmark of the RandomForestMC hot path on B200 (and of the CPU reference arm beside it).
+
+Metric (BASELINE.json): fit candidate-trees/s and predict rows*trees/s.  One JSON line on stdout.
+
+Workload: synthetic 1M rows x 64 mixed numeric/categorical features,
+4 classes, n_trees=256, max_discard_trees=4.  Two regimes of the same config:
+  c2b (default)  batch_train_pclass=2000, batch_val_pclass=500  -> 8000 train + 2000 hold-out rows
+                 per candidate: the regime in which the grower does real work;
+  c2a            the reference's default 10/10 rows per class (40 + 40 rows per candidate).
+
+A "step" = one pass of the hot path over one batch: growing and scoring every candidate of
+``n_trees`` slots (fit), and voting 1M rows through the fitted forest (predict).
+  value  device time only (CUDA events on the launch stream), inputs resident in HBM;
+  e2e    the public API (model.fit / model.testForest) with host buffers: host RNG draws, H2D
+         copies, kernels, D2H of scores / survivors / labels inside the timed region.
+``--impl reference`` times the CPU port of the reference (oracle/rfmc_oracle.py, the same numpy
+calls per node as the reference) on all host cores, one process per core, one slot per process.
+"""
+import argparse
+import json
+import math
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import pandas as pd
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REGIMES = {
+    "c2b": dict(batch_train_pclass=2000, batch_val_pclass=500),
+    "c2a": dict(batch_train_pclass=10, batch_val_pclass=10),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data
+# ------------------------------------------------------------------------------------------------
+def make_frame(n_rows: int, n_feat: int = 64, n_classes: int = 4, seed: int = 0) -> pd.DataFrame:
+    g = np.random.default_rng(seed)
+    q = n_feat // 4
+    cols = {}
+    for j in range(q):
+        cols[f"f64_{j}"] = np.round(g.normal(size=n_rows), 3)
+    for j in range(q):
+        cols[f"i64_{j}"] = g.integers(0, 1000, size=n_rows)
+    for j in range(q):
+        cols[f"f32_{j}"] = np.round(g.normal(size=n_rows), 2).astype(np.float32)
+    for j in range(n_feat - 3 * q):
+        levels = 3 + (j * 7) % 10
+        cols[f"cat_{j}"] = g.choice(np.array([f"v{k}" for k in range(levels)], dtype=object), size=n_rows)
+    df = pd.DataFrame(cols)
+    score = np.zeros(n_rows)
+    for j in range(0, q, 2):
+        score += df[f"f64_{j}"].to_numpy() + df[f"i64_{j}"].to_numpy() / 400.0 + df[f"f32_{j}"].to_numpy()
+    score += (df["cat_0"].to_numpy() == "v1") * 1.5 + g.normal(size=n_rows) * 2.0
+    edges = np.quantile(score, np.linspace(0, 1, n_classes + 1)[1:-1])
+    df["target"] = np.searchsorted(edges, score).astype(str)
+    return df
+
+
+def model_kwargs(args):
+    kw = dict(n_trees=args.n_trees, target_col="target", max_discard_trees=args.max_discard_trees)
+    kw.update(REGIMES[args.regime])
+    return kw
+
+
+def workload_name(args):
+    r = REGIMES[args.regime]
+    return (
+        f"C2{args.regime[-1]}: synthetic {args.rows}x{args.features} mixed numeric/categorical, {args.classes} classes, "
+        f"n_trees={args.n_trees}, max_discard_trees={args.max_discard_trees}, batch_train_pclass={r['batch_train_pclass']}, "
+        f"batch_val_pclass={r['batch_val_pclass']}; predict {args.predict_rows} rows x {args.n_trees} trees"
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        top = sorted(sm)[len(sm) // 2 :] if sm else []
+        return {
+            "sm_mhz": (sorted(top)[len(top) // 2] if top else None),
+            "sm_max_mhz": mx,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU port on all host cores
+# ------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_worker(task):
+    from oracle import rfmc_oracle as orc
+
+    seed, policy = task
+    np.random.seed(seed)
+    random.seed(seed)
+    t0 = time.perf_counter()
+    _, _, grown = orc.select_tree(_REF["ds"], **policy)
+    return grown, time.perf_counter() - t0
+
+
+def reference_fit_rate(frame, args, steps, warmup, cores):
+    """candidate-trees/s of the CPU port: `cores` processes, one tree slot each per step."""
+    import multiprocessing as mp
+
+    from oracle import rfmc_oracle as orc
+
+    kw = model_kwargs(args)
+    ds = orc.ingest(frame, target_col="target", batch_train_pclass=kw["batch_train_pclass"], batch_val_pclass=kw["batch_val_pclass"])
+    _REF["ds"] = ds
+    policy = dict(max_discard_trees=kw["max_discard_trees"])
+    ctx = mp.get_context("fork")
+    times, cands = [], []
+    with ctx.Pool(cores) as pool:
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = pool.map(_ref_worker, [(10_000 + s * cores + c, policy) for c in range(cores)], chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+                cands.append(sum(o[0] for o in out))
+    return sum(cands) / sum(times), sum(times) / len(times) * 1e3, sum(cands) / len(cands)
+
+
+def reference_predict_rate(frame, args, trees, scores, class_vals, rows=256):
+    """rows*trees/s of the CPU port's testForest on a small slice (one process, like the reference)."""
+    from oracle import rfmc_oracle as orc
+
+    part = frame.drop(columns=["target"]).head(rows)
+    t0 = time.perf_counter()
+    orc.forest_labels(trees, scores, class_vals, part, False, False)
+    dt = time.perf_counter() - t0
+    return rows * len(trees) / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = args.ref_cores or os.cpu_count() or 1
+    frame = make_frame(args.rows, args.features, args.classes, seed=0)
+    rate, ms, per_step = reference_fit_rate(frame, args, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference",
+        "metric": "fit_candidate_trees_per_s",
+        "value": rate,
+        "unit": "candidate-trees/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {
+            "value": rate,
+            "unit": "candidate-trees/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{cores} processes x 1 tree slot ({per_step:.0f} candidates) per step; oracle/rfmc_oracle.py = the reference's numpy calls per node",
+        },
+        "e2e": {"value": rate, "unit": "candidate-trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as td
+
+    from random_forest_mc_b200 import dist, engine
+    from random_forest_mc_b200.flat import encode_frame
+    from random_forest_mc_b200.model import RandomForestMC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    engine.require_gpu()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- data + model (not timed: process_dataset is outside the metric) ----
+    frame = make_frame(args.rows, args.features, args.classes, seed=0)
+    kw = model_kwargs(args)
+    model = RandomForestMC(**kw)
+    model.device = local
+    import logging
+
+    logging.disable(logging.WARNING)
+    t0 = time.perf_counter()
+    model.process_dataset(frame.copy())
+    t_process = time.perf_counter() - t0
+    enc = model.encoded
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush.zero_()
+
+    # ---- fit, device-only: a fixed plan (drawn once with the reference's RNGs) resident in HBM ----
+    np.random.seed(1234 + rank)
+    random.seed(1234 + rank)
+    K = kw["max_discard_trees"]
+    plan = [model._draw_slot(K) for _ in range(args.n_trees)]
+    batch, _ = None, None
+    idx_T = np.stack([p[0] for p in plan])
+    idx_V = np.stack([p[1] for p in plan])
+    slot_of, feats = [], []
+    for s, p in enumerate(plan):
+        for f in p[2]:
+            slot_of.append(s)
+            feats.append(f)
+    batch = engine.GrowBatch(model._dev_dataset, idx_T, idx_V, slot_of, feats, model.max_depth, model.min_samples_split, stream)
+    n_cand = batch.n_cand
+    for _ in range(args.warmup):
+        batch.run(stream)
+    torch.cuda.synchronize()
+    correct, n_nodes = batch.results()
+    sampler = ClockSampler(local).start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    for a, b in ev:
+        flush_l2()
+        a.record(stream)
+        batch.run(stream)
+        b.record(stream)
+        launches += batch.launches
+    barrier()
+    fit_ms = [a.elapsed_time(b) for a, b in ev]
+    fit_total_s = max_over_ranks(sum(fit_ms) / 1e3)
+    fit_value = world * n_cand * args.steps / fit_total_s
+    # algorithmic HBM bytes of the grower per launch (DESIGN.md "roofline"): every sampled row's
+    # codes for the candidate's features + its row id and label, plus the node table written
+    w = enc.width
+    C = enc.n_classes
+    nf = np.array([len(f) for f in feats], dtype=np.float64)
+    algo_bytes = float(((batch.n_train + batch.n_val) * (nf * w + 4 + 1)).sum() + (n_nodes.astype(np.float64) * (24 + 4 * C + 1)).sum())
+    hbm_peak, peak_src = peaks()
+    grow_gbs = algo_bytes / (np.mean(fit_ms) / 1e3) / 1e9
+    total_nodes = int(n_nodes.sum())
+
+    # ---- fit, end to end through the public API ----
+    def e2e_fit():
+        model.data, model.survived_scores = [], []
+        np.random.seed(4321 + rank)
+        random.seed(4321 + rank)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        if world > 1:
+            forest = dist.fit_sharded_local(model, args.n_trees)
+        else:
+            forest = model._fit_slots(args.n_trees, stream)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t, forest
+
+    e2e_fit()  # warm-up
+    barrier()
+    e2e_s, e2e_cands, forest = 0.0, 0, None
+    for _ in range(args.e2e_steps):
+        dt, forest = e2e_fit()
+        e2e_s += dt
+        e2e_cands += model.fit_stats["candidates_grown"]
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    stats = dict(model.fit_stats)
+    surv_nodes = sum(t.soa.n_nodes for t in forest[: args.n_trees])
+    h2d = int(args.n_trees * (batch.n_train + batch.n_val) * 4 + sum(len(f) for f in feats) * 2 + n_cand * 8)
+    d2h = int(n_cand * 8 + surv_nodes * (24 + 4 * C))
+    e2e_fit_value = world * e2e_cands / e2e_s
+
+    # ---- predict: vote predict_rows rows through the fitted forest ----
+    model.data = list(forest[: args.n_trees])
+    model.survived_scores = [t.survived_score for t in model.data]
+    dev = model._device_forest()
+    tables = model._forest_tables
+    pframe = frame.drop(columns=["target"]).head(args.predict_rows)
+    t0 = time.perf_counter()
+    codes, absent = encode_frame(tables, pframe)
+    t_encode = time.perf_counter() - t0
+    codes_t = torch.from_numpy(codes).cuda()
+    labels_t = torch.empty(len(codes), dtype=torch.int32, device="cuda")
+    R, T = len(codes), tables.n_trees
+
+    def pred_dev():
+        dev.predict_device(codes_t.data_ptr(), tables.width, R, tables.stride, None, model.soft_voting, model.weighted_tree, 0, labels_t.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        pred_dev()
+    barrier()
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in pev:
+        flush_l2()
+        a.record(stream)
+        pred_dev()
+        b.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    pred_ms = [a.elapsed_time(b) for a, b in pev]
+    pred_total_s = max_over_ranks(sum(pred_ms) / 1e3)
+    pred_value = world * R * T * args.steps / pred_total_s
+    pred_algo = float(R * (args.features * tables.width + 4) + len(tables.pnodes) * 16 + tables.probs.nbytes * 2)
+    pred_gbs = pred_algo / (np.mean(pred_ms) / 1e3) / 1e9
+    # e2e predict: host codes -> H2D -> kernel -> D2H labels (through DeviceForest.predict)
+    dev.predict(codes, absent, False, False, False, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, lab = dev.predict(codes, absent, False, False, False, True)
+    torch.cuda.synchronize()
+    pe2e_s = max_over_ranks(time.perf_counter() - t0)
+    pred_e2e = world * R * T * args.steps / pe2e_s
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = args.ref_cores or os.cpu_count() or 1
+        rate, ms, per_step = reference_fit_rate(frame.copy(), args, 1 if args.regime == "c2b" else 3, 0, cores)
+        from oracle import rfmc_oracle as orc
+
+        small = [t.data for t in model.data[:8]]
+        prate = reference_predict_rate(frame, args, small, model.survived_scores[:8], model.class_vals, rows=64)
+        cpu_baseline = {
+            "value": rate,
+            "unit": "candidate-trees/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{cores} processes x 1 tree slot ({per_step:.0f} candidates) per round of the same workload; oracle/rfmc_oracle.py (the reference's numpy calls per node)",
+            "predict_rows_trees_per_s": prate,
+            "predict_sample": "testForest port, 64 rows x 8 trees of the fitted forest, 1 process (the reference's row loop is serial)",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": "fit_candidate_trees_per_s",
+            "value": fit_value,
+            "unit": "candidate-trees/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": float(np.mean(fit_ms)),
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": {1: "u8", 2: "u16", 4: "u32"}[w],
+            "data": "synthetic",
+            "config": {
+                "workload": workload_name(args),
+                "candidates_per_step": n_cand,
+                "nodes_per_step": total_nodes,
+                "l2": "flushed between timed iterations (256 MiB memset)",
+                "parallelism": f"slots sharded over {world} rank(s), matrix replicated, no data-path collective",
+            },
+            "clocks": clocks,
+            "e2e": {
+                "value": e2e_fit_value,
+                "unit": "candidate-trees/s",
+                "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "api": "RandomForestMC fit loop (_fit_slots): host RNG draws + H2D + grow/score kernel + D2H scores + survivor tables"
+                + ("; + all-gather of survivors" if world > 1 else ""),
+                "ms_per_step": e2e_s / args.e2e_steps * 1e3,
+                "fit_stats": stats,
+            },
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "rfmc::grow_kernel",
+                "bound": "hbm",
+                "achieved": grow_gbs,
+                "peak": hbm_peak,
+                "unit": "GB/s",
+                "frac": grow_gbs / hbm_peak,
+                "traffic": ncu_traffic("grow_kernel"),
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes,
+            },
+            "predict": {
+                "metric": "predict_rows_trees_per_s",
+                "value": pred_value,
+                "unit": "rows*trees/s",
+                "ms_per_step": float(np.mean(pred_ms)),
+                "rows": R,
+                "trees": T,
+                "forest_nodes": int(len(tables.pnodes)),
+                "e2e": {
+                    "value": pred_e2e,
+                    "unit": "rows*trees/s",
+                    "h2d_bytes_per_step": int(codes.nbytes),
+                    "d2h_bytes_per_step": int(R * 4),
+                    "api": "DeviceForest.predict on already-encoded rows (host codes -> H2D -> vote kernel -> D2H labels)",
+                },
+                "encode_s": t_encode,
+                "roofline": {
+                    "kernel": "rfmc::predict_kernel",
+                    "bound": "hbm",
+                    "achieved": pred_gbs,
+                    "peak": hbm_peak,
+                    "unit": "GB/s",
+                    "frac": pred_gbs / hbm_peak,
+                    "traffic": ncu_traffic("predict_kernel"),
+                    "algorithmic_bytes_per_launch": pred_algo,
+                },
+            },
+            "process_dataset_s": t_process,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--regime", default="c2b", choices=list(REGIMES))
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--features", type=int, default=64)
+    ap.add_argument("--classes", type=int, default=4)
+    ap.add_argument("--n-trees", type=int, default=256, dest="n_trees")
+    ap.add_argument("--max-discard-trees", type=int, default=4, dest="max_discard_trees")
+    ap.add_argument("--predict-rows", type=int, default=1_000_000, dest="predict_rows")
+    ap.add_argument("--e2e-steps", type=int, default=2, dest="e2e_steps")
+    ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.predict_rows = min(args.predict_rows, args.rows)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,22 @@ def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
     return forest
 
 
+def fit_sharded_local(model, n_local: int):
+    """Weak-scaling variant used by bench.py: every rank grows ``n_local`` slots from its current
+    RNG state, then the survivors are all-gathered (rank order)."""
+    local = model._fit_slots(n_local)
+    if not is_distributed():
+        return local
+    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals))
+    forest = []
+    for soa, score in gathered:
+        t = model._wrap(soa, score)
+        t.features = model.feature_cols
+        t.used_features = model.tree2feats(t)
+        forest.append(t)
+    return forest
+
+
 def predict_sharded(model, frame, want_probs: bool):
     """Row-sharded voting: this rank's contiguous slice of ``frame``; no collective."""
     rank, world = rank_world()
