@@ -133,6 +133,12 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
 int rfmc_forest_leaves(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
                        int32_t n_features, const uint8_t* absent, int32_t* leaves_out, void* stream);
 
+/* ---- split_train_val (model.py:198-210): the draw behind np.random.choice(a, size, replace=False)
+ * on numpy's global legacy MT19937 stream, restated on the host: out[0..size) =
+ * permutation(n)[:size].  key[624] / *pos are np.random.get_state()[1:3] and are advanced in
+ * place exactly as numpy would advance them. */
+int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos, int64_t n, int64_t size, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

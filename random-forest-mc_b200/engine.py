@@ -51,6 +51,7 @@ _SIGNATURES = {
     "rfmc_forest_destroy": (C.c_int, [_p]),
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
     "rfmc_forest_leaves": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p]),
+    "rfmc_legacy_permutation_prefix": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -104,6 +105,16 @@ def _stream_ptr(stream) -> Optional[int]:
     if isinstance(stream, int):
         return stream or None
     return getattr(stream, "cuda_stream", None) or None
+
+
+def legacy_choice_indices(key: np.ndarray, pos: int, n: int, size: int):
+    """permutation(n)[:size] on the legacy MT19937 stream (key is advanced in place).  Host code."""
+    out = np.empty(size, dtype=np.int64)
+    p = C.c_int32(pos)
+    rc = load_library().rfmc_legacy_permutation_prefix(_ptr(key), C.byref(p), n, size, _ptr(out))
+    if rc != 0:
+        raise EngineError("rfmc_legacy_permutation_prefix: bad arguments")
+    return out, p.value
 
 
 class DeviceDataset:

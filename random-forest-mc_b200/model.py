@@ -182,13 +182,20 @@ class RandomForestMC(BaseRandomForestMC):
     # host RNG draws, exactly the reference's (model.py:198-219)
     # ---------------------------------------------------------------------------------------------
     def split_train_val(self) -> Tuple[np.ndarray, np.ndarray]:
-        idx_train: list = []
-        idx_val: list = []
-        for class_indices in self.encoded.class_rows:  # == indices[target_vals == val], cached (no RNG use)
-            selected = np.random.choice(class_indices, self._N, replace=False)
-            idx_train.extend(selected[: self.batch_train_pclass])
-            idx_val.extend(selected[self.batch_train_pclass :])
-        return np.array(idx_train), np.array(idx_val)
+        """model.py:198-210.  ``np.random.choice(class_indices, _N, replace=False)`` per class in
+        ``class_vals`` order, drawn from numpy's global legacy stream by the host restatement in
+        csrc/host_rng.cpp (same indices, same end state as numpy: tests/test_host_rng.py).  The
+        per-class row lists ``indices[target_vals == val]`` are cached: building them uses no RNG."""
+        st = np.random.get_state()
+        key, pos = st[1].copy(), int(st[2])
+        train, val = [], []
+        for class_indices in self.encoded.class_rows:
+            idx, pos = engine.legacy_choice_indices(key, pos, len(class_indices), self._N)
+            selected = class_indices[idx]
+            train.append(selected[: self.batch_train_pclass])
+            val.append(selected[self.batch_train_pclass :])
+        np.random.set_state((st[0], key, pos, st[3], st[4]))
+        return np.concatenate(train), np.concatenate(val)
 
     def sampleFeats(self, feature_cols: List[str]) -> List[str]:
         n_samples = np.random.randint(self.min_feature, self.max_feature + 1)
@@ -268,14 +275,23 @@ class RandomForestMC(BaseRandomForestMC):
 
     def _draw_slot(self, n_cands: int, idx=None):
         """One slot's draws: rows once (unless continuing a slot), then ``n_cands`` feature lists.
-        Returns (idx_T, idx_V, [feature id lists], [RNG snapshots after each sampleFeats])."""
+        Returns (idx_T, idx_V, [feature id lists], RNG snapshot taken BEFORE the slot's draws)."""
+        start = self._snapshot()
         if idx is None:
             idx = self.split_train_val()
-        feats, snaps = [], []
-        for _ in range(n_cands):
-            feats.append(self._feat_ids(self.sampleFeats(self.feature_cols[:])))
-            snaps.append(self._snapshot())
-        return idx[0], idx[1], feats, snaps
+        feats = [self._feat_ids(self.sampleFeats(self.feature_cols[:])) for _ in range(n_cands)]
+        return idx[0], idx[1], feats, (start, idx is None)
+
+    def _rewind_into_slot(self, p, n_used: int, fresh_rows: bool = True):
+        """Put both RNGs where the serial reference is after ``n_used`` sampleFeats calls of slot
+        ``p``: restore the snapshot taken before the slot and replay its draws (they are pure
+        functions of the stream, so the replay reproduces them)."""
+        start, _ = p[3]
+        self._restore(start)
+        if fresh_rows:
+            self.split_train_val()
+        for _ in range(n_used):
+            self.sampleFeats(self.feature_cols[:])
 
     def _candidate_bytes(self) -> int:
         n_train = self.batch_train_pclass * len(self.class_vals) if self._N > self.batch_train_pclass else self._N * len(self.class_vals)
@@ -304,7 +320,10 @@ class RandomForestMC(BaseRandomForestMC):
         """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's."""
         self._require_dataset()
         trees: List[DecisionTreeMC] = []
-        stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0)
+        stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0,
+                     t_draw=0.0, t_launch=0.0, t_wait=0.0, t_fetch=0.0)
+        from time import perf_counter as _now
+
         K = max(1, int(self.max_discard_trees))
         cap = max(1, min(self.max_candidates_per_launch, self.max_batch_bytes // max(1, self._candidate_bytes())))
         assume_pass = False  # hypothesis on the candidates a slot consumes: K, or 1 when trees mostly pass
@@ -315,10 +334,16 @@ class RandomForestMC(BaseRandomForestMC):
             n_plan = min(n_slots - len(trees), max(1, cap // spec))
             if avg_commit != float("inf"):
                 n_plan = min(n_plan, max(4, int(4 * avg_commit) + 1))
+            t0 = _now()
             plan = [self._draw_slot(spec) for _ in range(n_plan)]
+            t1 = _now()
             batch, first = self._grow_plan(plan, stream)
+            t2 = _now()
+            stats["t_draw"] += t1 - t0
+            stats["t_launch"] += t2 - t1
             try:
                 correct, _ = batch.results()
+                stats["t_wait"] += _now() - t2
                 stats["batches"] += 1
                 stats["gpu_launches"] += batch.launches
                 stats["candidates_grown"] += batch.n_cand
@@ -332,19 +357,21 @@ class RandomForestMC(BaseRandomForestMC):
                     if not judge.done:
                         # needs more candidates than were drawn: everything drawn after this slot is
                         # off-stream; continue the slot from the state right after its last draw
-                        resume, extend = p[3][-1], (p, judge)
+                        resume, extend = (p, spec), (p, judge)
                         break
                     chosen.append((judge.choice, judge.best_score))
                     stats["candidates_used"] += judge.used
                     recent_used.append(judge.used)
                     if judge.used != spec:
-                        resume = p[3][judge.used - 1]
+                        resume = (p, judge.used)
                         break
+                t3 = _now()
                 self._collect(batch, chosen, trees)
+                stats["t_fetch"] += _now() - t3
                 committed = len(chosen)
-                if resume is not None:
+                if resume is not None and not (extend is None and resume[0] is plan[-1] and resume[1] == spec):
                     stats["rewinds"] += 1
-                    self._restore(resume)
+                    self._rewind_into_slot(resume[0], resume[1])
                 if extend is not None:
                     trees.append(self._extend_slot(extend[0], extend[1], batch, stream, stats))
                     recent_used.append(extend[1].used)
@@ -381,8 +408,9 @@ class RandomForestMC(BaseRandomForestMC):
         it = 0
         while True:
             it += 1
-            _, _, feats, snaps = self._draw_slot(K, idx=(p[0], p[1]))
-            b, _ = self._grow_plan([(p[0], p[1], feats, snaps)], stream)
+            _, _, feats, snap = self._draw_slot(K, idx=(p[0], p[1]))
+            ext = (p[0], p[1], feats, snap)
+            b, _ = self._grow_plan([ext], stream)
             try:
                 correct, _ = b.results()
                 stats["gpu_launches"] += b.launches
@@ -406,7 +434,7 @@ class RandomForestMC(BaseRandomForestMC):
                     soa = b.fetch([choice[2]])[0]  # the candidate that met the threshold, in this launch
                 if stop != K - 1:
                     stats["rewinds"] += 1
-                    self._restore(snaps[stop])
+                    self._rewind_into_slot(ext, stop + 1, fresh_rows=False)
                 stats["candidates_used"] += judge.used
                 return self._wrap(soa, judge.best_score)
             finally:
