@@ -10,7 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librfmc_b200.so")
-SOURCES = ["abi.cu", "grow.cu", "predict.cu", "host_rng.cpp"]
+SOURCES = ["abi.cu", "grow.cu", "predict.cu"]
+HOST_SOURCES = ["host_rng.cpp"]  # plain g++ (-O3, AVX2 clones dispatched at load time)
 FLAGS = [
     "-O3",
     "-std=c++17",
@@ -42,7 +43,15 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, src.rsplit(".", 1)[0] + ".o")
+        r = subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-c", src, "-o", obj], cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"g++ failed on {src}")
+        objs.append(obj)
+    cmd = [_nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + objs
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
