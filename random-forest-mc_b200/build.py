@@ -51,7 +51,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"g++ failed on {src}")
         objs.append(obj)
-    cmd = [_nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + objs
+    extra = os.environ.get("RFMC_NVCC_DEFS", "").split()
+    cmd = [_nvcc()] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + objs
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -29,6 +29,69 @@ static void release(void* p) {
 
 using namespace rfmc;
 
+struct PredictPipe {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    uint8_t* pin_in[2] = {nullptr, nullptr};
+    uint8_t* d_in[2] = {nullptr, nullptr};
+    double* pin_probs[2] = {nullptr, nullptr};
+    double* d_probs[2] = {nullptr, nullptr};
+    int32_t* pin_labels[2] = {nullptr, nullptr};
+    int32_t* d_labels[2] = {nullptr, nullptr};
+    size_t cap_in = 0, cap_probs = 0, cap_labels = 0;
+    long launches = 0;
+};
+
+static int pipe_reserve(PredictPipe* p, size_t in_bytes, size_t probs_bytes, size_t labels_bytes) {
+    for (int i = 0; i < 2; ++i) {
+        if (!p->st[i]) RFMC_CUDA(cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking));
+        if (!p->done[i]) RFMC_CUDA(cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming));
+    }
+    if (in_bytes > p->cap_in) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
+            release(p->d_in[i]);
+            RFMC_CUDA(cudaHostAlloc((void**)&p->pin_in[i], in_bytes, cudaHostAllocDefault));
+            RFMC_CUDA(cudaMalloc((void**)&p->d_in[i], in_bytes));
+        }
+        p->cap_in = in_bytes;
+    }
+    if (probs_bytes > p->cap_probs) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->pin_probs[i]) cudaFreeHost(p->pin_probs[i]);
+            release(p->d_probs[i]);
+            RFMC_CUDA(cudaHostAlloc((void**)&p->pin_probs[i], probs_bytes, cudaHostAllocDefault));
+            RFMC_CUDA(cudaMalloc((void**)&p->d_probs[i], probs_bytes));
+        }
+        p->cap_probs = probs_bytes;
+    }
+    if (labels_bytes > p->cap_labels) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->pin_labels[i]) cudaFreeHost(p->pin_labels[i]);
+            release(p->d_labels[i]);
+            RFMC_CUDA(cudaHostAlloc((void**)&p->pin_labels[i], labels_bytes, cudaHostAllocDefault));
+            RFMC_CUDA(cudaMalloc((void**)&p->d_labels[i], labels_bytes));
+        }
+        p->cap_labels = labels_bytes;
+    }
+    return 0;
+}
+
+static void pipe_destroy(PredictPipe* p) {
+    if (!p) return;
+    for (int i = 0; i < 2; ++i) {
+        if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
+        if (p->pin_probs[i]) cudaFreeHost(p->pin_probs[i]);
+        if (p->pin_labels[i]) cudaFreeHost(p->pin_labels[i]);
+        release(p->d_in[i]);
+        release(p->d_probs[i]);
+        release(p->d_labels[i]);
+        if (p->done[i]) cudaEventDestroy(p->done[i]);
+        if (p->st[i]) cudaStreamDestroy(p->st[i]);
+    }
+    delete p;
+}
+
 extern "C" {
 
 int rfmc_abi_version(void) { return RFMC_ABI_VERSION; }
@@ -307,6 +370,7 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     release(f->d_probs);
     release(f->d_probs_absent);
     release(f->d_scores);
+    pipe_destroy(f->pipe);
     delete f;
     return 0;
 }
@@ -338,31 +402,61 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
         }
         return rc;
     }
-    uint8_t* d_codes = nullptr;
-    double* d_probs = nullptr;
-    int32_t* d_labels = nullptr;
-    rc |= upload(&d_codes, (const uint8_t*)codes, (size_t)n_rows * row_stride * code_width, st);
-    if (probs_out) rc |= reserve(&d_probs, (size_t)n_rows * C);
-    if (labels_out) rc |= reserve(&d_labels, (size_t)n_rows);
-    if (!rc)
-        rc = launch_predict(f, d_codes, code_width, n_rows, row_stride, n_features, d_absent, has_absent, soft, weighted,
-                            d_probs, d_labels, st);
-    if (!rc && probs_out &&
-        cudaMemcpyAsync(probs_out, d_probs, (size_t)n_rows * C * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = 1;
-    if (!rc && labels_out &&
-        cudaMemcpyAsync(labels_out, d_labels, (size_t)n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = 1;
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) {
-        set_error(std::string("predict failed: ") + cudaGetErrorString(e));
+    // Host buffers: chunked, double-buffered pipeline.  While chunk c votes on one stream, chunk
+    // c+1 is staged through pinned memory and copied in on the other; results leave through
+    // pinned memory as well, so no copy in the timed path is a blocking pageable transfer.
+    if (rc) {
+        release(d_absent);
+        return rc;
+    }
+    cudaStreamSynchronize(st);
+    PredictPipe* pp = f->pipe;
+    if (!pp) pp = f->pipe = new PredictPipe();
+    const size_t row_bytes = (size_t)row_stride * code_width;
+    const int64_t chunk_rows = 32768;
+    if (pipe_reserve(pp, chunk_rows * row_bytes, probs_out ? chunk_rows * C * sizeof(double) : 0,
+                     labels_out ? chunk_rows * sizeof(int32_t) : 0)) {
+        release(d_absent);
+        return 1;
+    }
+    const int64_t n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
+    auto drain = [&](int64_t c) {  // copy chunk c's results from pinned staging to the caller
+        const int sl = (int)(c & 1);
+        const int64_t r0 = c * chunk_rows, nr = (n_rows - r0) < chunk_rows ? (n_rows - r0) : chunk_rows;
+        if (cudaEventSynchronize(pp->done[sl]) != cudaSuccess) rc = 1;
+        if (probs_out) memcpy(probs_out + r0 * C, pp->pin_probs[sl], (size_t)nr * C * sizeof(double));
+        if (labels_out) memcpy(labels_out + r0, pp->pin_labels[sl], (size_t)nr * sizeof(int32_t));
+    };
+    for (int64_t c = 0; c < n_chunks && !rc; ++c) {
+        const int sl = (int)(c & 1);
+        if (c >= 2) drain(c - 2);
+        const int64_t r0 = c * chunk_rows, nr = (n_rows - r0) < chunk_rows ? (n_rows - r0) : chunk_rows;
+        memcpy(pp->pin_in[sl], (const uint8_t*)codes + (size_t)r0 * row_bytes, (size_t)nr * row_bytes);
+        cudaStream_t cs = pp->st[sl];
+        if (cudaMemcpyAsync(pp->d_in[sl], pp->pin_in[sl], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = 1;
+        if (!rc)
+            rc = launch_predict(f, pp->d_in[sl], code_width, nr, row_stride, n_features, d_absent, has_absent, soft, weighted,
+                                probs_out ? pp->d_probs[sl] : nullptr, labels_out ? pp->d_labels[sl] : nullptr, cs);
+        if (!rc && probs_out &&
+            cudaMemcpyAsync(pp->pin_probs[sl], pp->d_probs[sl], (size_t)nr * C * sizeof(double), cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = 1;
+        if (!rc && labels_out &&
+            cudaMemcpyAsync(pp->pin_labels[sl], pp->d_labels[sl], (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = 1;
+        if (!rc && cudaEventRecord(pp->done[sl], cs) != cudaSuccess) rc = 1;
+        pp->launches += 1;
+    }
+    if (!rc) {
+        if (n_chunks >= 2) drain(n_chunks - 2);
+        drain(n_chunks - 1);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(pp->st[0]), e1 = cudaStreamSynchronize(pp->st[1]);
+    if (e0 != cudaSuccess || e1 != cudaSuccess) {
+        set_error(std::string("predict failed: ") + cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
         rc = 1;
     } else if (rc && g_error.empty()) {
         set_error("predict failed");
     }
-    release(d_codes);
-    release(d_probs);
-    release(d_labels);
     release(d_absent);
     return rc;
 }

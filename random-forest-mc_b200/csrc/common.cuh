@@ -84,6 +84,8 @@ struct rfmc_batch {
     cudaStream_t stream = nullptr;
 };
 
+struct PredictPipe;
+
 struct rfmc_forest {
     int device = 0;
     int64_t n_nodes = 0, n_payloads = 0;
@@ -97,6 +99,7 @@ struct rfmc_forest {
     double* d_probs_absent = nullptr;
     double* d_scores = nullptr;
     int sm_count = 0;
+    PredictPipe* pipe = nullptr;  // pinned staging + streams of the host-buffer voting path
 };
 
 namespace rfmc {

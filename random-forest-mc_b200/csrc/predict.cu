@@ -20,6 +20,10 @@
 namespace rfmc {
 
 constexpr int PRED_THREADS = 128;
+#ifndef RFMC_PRED_ILP
+#define RFMC_PRED_ILP 4
+#endif
+constexpr int PRED_ILP = RFMC_PRED_ILP;
 
 struct PredictArgs {
     const void* codes;
@@ -77,45 +81,72 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
         cnt[c] = 0;
     }
 
-    for (int t = 0; t < a.n_trees; ++t) {
-        uint32_t node = (uint32_t)__ldg(&a.root[t]);
-        bool seen = false;
-        uint4 nd;
-        while (true) {
-            nd = __ldg(reinterpret_cast<const uint4*>(a.nodes) + node);
-            if (nd.x & RFMC_PNODE_LEAF) break;
-            const uint32_t f = nd.x & 0xFFFFu;
-            const uint32_t cv = (uint32_t)myrow[f];
-            bool go = (nd.x & RFMC_PNODE_CATEGORICAL) ? (cv == nd.y) : (cv >= nd.y);
-            if (HAS_ABSENT) {
-                const bool ab = s_absent[f] != 0;
-                go = go || ab;
-                seen = seen || ab;
-            }
-            node = nd.z + (go ? 0u : 1u);
+    // PRED_ILP trees are walked concurrently (their node loads are independent, so PRED_ILP loads
+    // are in flight per thread instead of one); the leaves are then accumulated in forest order.
+    for (int t0 = 0; t0 < a.n_trees; t0 += PRED_ILP) {
+        uint32_t node[PRED_ILP];
+        uint4 nd[PRED_ILP];
+        bool done[PRED_ILP], seen[PRED_ILP];
+#pragma unroll
+        for (int k = 0; k < PRED_ILP; ++k) {
+            const bool valid = t0 + k < a.n_trees;
+            node[k] = valid ? (uint32_t)__ldg(&a.root[t0 + k]) : 0u;
+            done[k] = !valid;
+            seen[k] = false;
+            nd[k] = make_uint4(RFMC_PNODE_LEAF, 0u, 0u, 0u);
         }
-        const uint32_t payload = nd.y;
-        if (MODE == 0 || MODE == 1) {
-            const int v = (HAS_ABSENT && seen) ? a.vote_absent[payload] : a.vote[payload];
-            if (MODE == 0) {
+        bool any = true;
+        while (any) {
+            any = false;
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
-            } else {
-                const double s = __ldg(&a.scores[t]);
+            for (int k = 0; k < PRED_ILP; ++k)
+                if (!done[k]) nd[k] = __ldg(reinterpret_cast<const uint4*>(a.nodes) + node[k]);
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) acc[c] = __dadd_rn(acc[c], (c == v) ? s : 0.0);
+            for (int k = 0; k < PRED_ILP; ++k) {
+                if (done[k]) continue;
+                if (nd[k].x & RFMC_PNODE_LEAF) {
+                    done[k] = true;
+                    continue;
+                }
+                const uint32_t f = nd[k].x & 0xFFFFu;
+                const uint32_t cv = (uint32_t)myrow[f];
+                bool go = (nd[k].x & RFMC_PNODE_CATEGORICAL) ? (cv == nd[k].y) : (cv >= nd[k].y);
+                if (HAS_ABSENT) {
+                    const bool ab = s_absent[f] != 0;
+                    go = go || ab;
+                    seen[k] = seen[k] || ab;
+                }
+                node[k] = nd[k].z + (go ? 0u : 1u);
+                any = true;
             }
-        } else {
-            const double* p = ((HAS_ABSENT && seen) ? a.probs_absent : a.probs) + (size_t)payload * C;
-            if (MODE == 2) {
+        }
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c)
-                    if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+        for (int k = 0; k < PRED_ILP; ++k) {
+            const int t = t0 + k;
+            if (t >= a.n_trees) break;
+            const uint32_t payload = nd[k].y;
+            if (MODE == 0 || MODE == 1) {
+                const int v = (HAS_ABSENT && seen[k]) ? a.vote_absent[payload] : a.vote[payload];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
+                } else {
+                    const double s = __ldg(&a.scores[t]);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) acc[c] = __dadd_rn(acc[c], (c == v) ? s : 0.0);
+                }
             } else {
-                const double s = __ldg(&a.scores[t]);
+                const double* p = ((HAS_ABSENT && seen[k]) ? a.probs_absent : a.probs) + (size_t)payload * C;
+                if (MODE == 2) {
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c)
-                    if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), s));
+                    for (int c = 0; c < CMAX; ++c)
+                        if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+                } else {
+                    const double s = __ldg(&a.scores[t]);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c)
+                        if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), s));
+                }
             }
         }
     }
