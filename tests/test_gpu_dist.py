@@ -1,0 +1,74 @@
+"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): the rank-sharded fit with the real engine.
+Same contract as tests/test_dist_gloo.py: rank r == the serial algorithm under seed s_r, forest =
+concatenation in rank order; row-sharded voting tiles the frame."""
+import os
+import pickle
+import random
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, pickle, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as td
+from tests.helpers import load_golden
+from random_forest_mc_b200.model import RandomForestMC
+from random_forest_mc_b200 import dist
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+td.init_process_group("nccl", device_id=torch.device("cuda", local))
+g = load_golden("mixed_default")
+kw = dict(g["kwargs"]); kw["n_trees"] = 5
+m = RandomForestMC(**kw)
+m.device = local
+m.rank_seeds = [1000, 1001]
+m.fitParallel(g["frame"].copy(), disable_progress_bar=True)
+(lo, hi), labels = dist.predict_sharded(m, g["frames"]["nan"], want_probs=False)
+out = dict(trees=[t.data for t in m.data], scores=[float(s) for s in m.survived_scores], lo=lo, hi=hi, labels=labels)
+with open(os.path.join({tmp!r}, "rank%d.pkl" % td.get_rank()), "wb") as f:
+    pickle.dump(out, f)
+td.destroy_process_group()
+"""
+
+
+def test_sharded_fit_over_nccl_world2():
+    from random_forest_mc_b200 import engine
+
+    if engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import rfmc_oracle as orc
+    from tests.helpers import load_golden, tree_diff
+
+    with tempfile.TemporaryDirectory() as tmp:
+        script = os.path.join(tmp, "worker.py")
+        with open(script, "w") as f:
+            f.write(WORKER.format(root=ROOT, tmp=tmp))
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29513", script]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+        out = [pickle.load(open(os.path.join(tmp, f"rank{r}.pkl"), "rb")) for r in range(2)]
+    g = load_golden("mixed_default")
+    kw = g["kwargs"]
+    want_trees, want_scores = [], []
+    for seed, n in ((1000, 3), (1001, 2)):
+        ds = orc.ingest(g["frame"].copy(), target_col=kw["target_col"])
+        np.random.seed(seed)
+        random.seed(seed)
+        t, s, _ = orc.fit(ds, n, max_discard_trees=kw["max_discard_trees"])
+        want_trees += t
+        want_scores += [float(x) for x in s]
+    for r in range(2):
+        assert out[r]["scores"] == want_scores
+        for a, b in zip(out[r]["trees"], want_trees):
+            assert tree_diff(a, b) is None
+    fr = g["frames"]["nan"]
+    want = orc.forest_labels(want_trees, want_scores, g["class_vals"], fr, False, False)
+    assert out[0]["labels"] + out[1]["labels"] == want
