@@ -137,6 +137,7 @@ class ClockSampler:
 # reference arm: the CPU port on all host cores
 # ------------------------------------------------------------------------------------------------
 _REF = {}
+_emit = print
 
 
 def _ref_worker(task):
@@ -215,7 +216,7 @@ def run_reference(args):
         },
         "e2e": {"value": rate, "unit": "candidate-trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,7 +493,7 @@ def run_b200(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     batch.close()
     if world > 1:
         td.destroy_process_group()
@@ -516,10 +517,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.predict_rows = min(args.predict_rows, args.rows)
+    # stdout carries exactly ONE JSON line: anything a library prints (NCCL's version banner ...)
+    # goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

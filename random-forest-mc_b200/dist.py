@@ -57,52 +57,125 @@ def _comm_device():
     return torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
 
 
-def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int):
-    """All-gather variable-length survivor tables.  Returns [(TreeSoA, score)] in rank order."""
+class GatheredBlock:
+    """The all-gathered survivor tables of every rank, left where the collective put them (HBM on
+    the box) until some tree of the block is actually read on the host."""
+
+    def __init__(self, nodes_t, counts_t, metas, n_classes):
+        self._nodes_t, self._counts_t = nodes_t, counts_t
+        self.metas, self.n_classes = metas, n_classes
+        self._host = None
+
+    def host(self):
+        if self._host is None:
+            nodes = self._nodes_t.cpu().numpy()
+            counts = self._counts_t.cpu().numpy()
+            per_rank = []
+            for r, (nt, nn) in enumerate(self.metas):
+                n = nodes[r][: nn * NODE_DTYPE.itemsize].view(NODE_DTYPE)
+                c = counts[r][: nn * self.n_classes * 4].view(np.int32).reshape(nn, self.n_classes)
+                per_rank.append((n, c))
+            self._host = per_rank
+            self._nodes_t = self._counts_t = None
+        return self._host
+
+
+class LazyTreeSoA:
+    """TreeSoA interface over a slice of a GatheredBlock (materialised on first read)."""
+
+    def __init__(self, block: GatheredBlock, rank: int, start: int, size: int):
+        self._block, self._rank, self._start, self._size = block, rank, start, size
+
+    @property
+    def n_nodes(self) -> int:
+        return self._size
+
+    @property
+    def nodes(self):
+        return self._block.host()[self._rank][0][self._start : self._start + self._size]
+
+    @property
+    def counts(self):
+        return self._block.host()[self._rank][1][self._start : self._start + self._size]
+
+
+def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int, used_masks=None):
+    """All-gather variable-length survivor tables (sizes first, then the padded payload).
+    Returns [(soa, score, used_mask)] in rank order; this rank's own trees are returned as they
+    are, the others as lazy views of the gathered (device-resident) block."""
     import torch
 
     td = _td()
-    world = td.get_world_size()
+    world, rank = td.get_world_size(), td.get_rank()
     dev = _comm_device()
     sizes = np.array([t.n_nodes for t in trees], dtype=np.int64)
     nodes = np.concatenate([t.nodes for t in trees]) if len(trees) else np.zeros(0, dtype=NODE_DTYPE)
     counts = np.concatenate([t.counts for t in trees]) if len(trees) else np.zeros((0, n_classes), dtype=np.int32)
     sc = np.array([float(s) for s in scores], dtype=np.float64)
+    nmask = 0 if used_masks is None else used_masks.shape[1]
     meta = torch.tensor([len(trees), len(nodes)], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    td.all_gather(metas, meta)
-    metas = [m.cpu().numpy() for m in metas]
-    max_trees = max(int(m[0]) for m in metas)
-    max_nodes = max(int(m[1]) for m in metas)
+    metas_t = [torch.zeros_like(meta) for _ in range(world)]
+    td.all_gather(metas_t, meta)
+    metas = [tuple(int(x) for x in m.cpu().numpy()) for m in metas_t]
+    max_trees = max(m[0] for m in metas)
+    max_nodes = max(m[1] for m in metas)
 
-    def padded(raw: bytes, nbytes: int):
-        buf = np.zeros(nbytes, dtype=np.uint8)
-        buf[: len(raw)] = np.frombuffer(raw, dtype=np.uint8)
-        return torch.from_numpy(buf).to(dev)
+    def padded(arr: np.ndarray, nbytes: int):
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        buf = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        if len(raw):
+            buf[: len(raw)] = torch.from_numpy(raw).to(dev)
+        return buf
 
-    def gather(raw: bytes, nbytes: int) -> List[np.ndarray]:
-        mine = padded(raw, max(nbytes, 1))
-        outs = [torch.zeros_like(mine) for _ in range(world)]
-        td.all_gather(outs, mine)
-        return [o.cpu().numpy() for o in outs]
+    def gather(arr: np.ndarray, nbytes: int):
+        mine = padded(arr, nbytes)
+        out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
+        td.all_gather_into_tensor(out, mine)
+        return out.view(world, mine.numel())
 
-    g_sizes = gather(sizes.tobytes(), max_trees * 8)
-    g_scores = gather(sc.tobytes(), max_trees * 8)
-    g_nodes = gather(nodes.tobytes(), max_nodes * NODE_DTYPE.itemsize)
-    g_counts = gather(np.ascontiguousarray(counts).tobytes(), max_nodes * n_classes * 4)
+    # small per-tree metadata travels packed per field: [sizes | scores | masks], each padded to max_trees
+    def field(arr, width):
+        buf = np.zeros(max_trees * width, dtype=np.uint8)
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        buf[: len(raw)] = raw
+        return buf
+
+    packed = np.concatenate([field(sizes, 8), field(sc, 8)] + ([field(used_masks, nmask)] if nmask else [np.zeros(0, dtype=np.uint8)]))
+    g_small = gather(packed, len(packed)).cpu().numpy()
+    g_nodes = gather(nodes, max_nodes * NODE_DTYPE.itemsize)
+    g_counts = gather(counts, max_nodes * n_classes * 4)
+    block = GatheredBlock(g_nodes, g_counts, metas, n_classes)
     out = []
     for r in range(world):
-        nt, nn = int(metas[r][0]), int(metas[r][1])
-        r_sizes = g_sizes[r][: nt * 8].view(np.int64)
-        r_scores = g_scores[r][: nt * 8].view(np.float64)
-        r_nodes = g_nodes[r][: nn * NODE_DTYPE.itemsize].view(NODE_DTYPE)
-        r_counts = g_counts[r][: nn * n_classes * 4].view(np.int32).reshape(nn, n_classes)
+        nt = metas[r][0]
+        row = g_small[r]
+        r_sizes = row[: max_trees * 8].view(np.int64)[:nt]
+        r_scores = row[max_trees * 8 : max_trees * 16].view(np.float64)[:nt]
+        r_masks = row[max_trees * 16 :].reshape(max_trees, nmask)[:nt] if nmask else [None] * nt
         at = 0
         for k in range(nt):
             s = int(r_sizes[k])
-            out.append((TreeSoA(r_nodes[at : at + s].copy(), r_counts[at : at + s].copy()), np.float64(r_scores[k])))
+            soa = trees[k] if r == rank else LazyTreeSoA(block, r, at, s)
+            out.append((soa, np.float64(r_scores[k]), r_masks[k]))
             at += s
     return out
+
+
+def _gather_forest(model, local):
+    nf = len(model.feature_cols)
+    masks = np.zeros((len(local), nf), dtype=np.uint8)
+    pos = {name: j for j, name in enumerate(model.feature_cols)}
+    for i, t in enumerate(local):
+        for f in t.used_features:
+            masks[i, pos[f]] = 1
+    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks)
+    forest = []
+    for soa, score, mask in gathered:
+        t = model._wrap(soa, score)
+        t.features = model.feature_cols
+        t.used_features = [model.feature_cols[j] for j in np.flatnonzero(mask)]
+        forest.append(t)
+    return forest
 
 
 def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
@@ -114,17 +187,7 @@ def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
         np.random.seed(seeds[rank])
         _pyrandom.seed(seeds[rank])
     local = model._fit_slots(hi - lo) if hi > lo else []
-    for t in local:
-        if t.soa is None:
-            raise RuntimeError("sharded fit expects SoA-backed trees")
-    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals))
-    forest = []
-    for soa, score in gathered:
-        t = model._wrap(soa, score)
-        t.features = model.feature_cols
-        t.used_features = model.tree2feats(t)
-        forest.append(t)
-    return forest
+    return _gather_forest(model, local)
 
 
 def fit_sharded_local(model, n_local: int):
@@ -133,14 +196,7 @@ def fit_sharded_local(model, n_local: int):
     local = model._fit_slots(n_local)
     if not is_distributed():
         return local
-    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals))
-    forest = []
-    for soa, score in gathered:
-        t = model._wrap(soa, score)
-        t.features = model.feature_cols
-        t.used_features = model.tree2feats(t)
-        forest.append(t)
-    return forest
+    return _gather_forest(model, local)
 
 
 def predict_sharded(model, frame, want_probs: bool):
