@@ -139,6 +139,20 @@ int rfmc_forest_leaves(rfmc_forest* f, const void* codes, int code_width, int64_
  * place exactly as numpy would advance them. */
 int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos, int64_t n, int64_t size, int64_t* out);
 
+/* The numpy-stream draws of a whole plan of tree slots in one call, in the reference's order
+ * (model.py:198-219 as driven by survivedTree model.py:318-326): per slot, one
+ * choice(class_rows[c], per_class, replace=False) per class, then n_cands times
+ * randint(randint_low, randint_high).  class_rows holds every class's ascending row ids back to
+ * back (class c = [class_off[c], class_off[c+1])).  Outputs: idx_train [n_slots][n_classes *
+ * min(per_class, n_train_pclass)] (class-major, draw order), idx_val [n_slots][the rest],
+ * feat_counts [n_slots][n_cands]; key_snap [n_slots][624] / pos_snap [n_slots] = the stream state
+ * BEFORE each slot (for the exact rewind of a mis-speculated plan; NULL to skip).  The permutation
+ * resolves run on n_threads worker threads while the calling thread walks the stream. */
+int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos, int32_t n_slots, int32_t n_classes, const int64_t* class_rows,
+                          const int64_t* class_off, int64_t per_class, int64_t n_train_pclass, int32_t n_cands,
+                          int64_t randint_low, int64_t randint_high, int32_t* idx_train, int32_t* idx_val,
+                          int32_t* feat_counts, uint32_t* key_snap, int32_t* pos_snap, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

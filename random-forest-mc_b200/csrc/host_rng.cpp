@@ -1,16 +1,20 @@
-// Host-side, bit-exact restatement of the draw behind split_train_val (model.py:198-210):
+// Host-side, bit-exact restatement of the numpy draws behind split_train_val / sampleFeats
+// (model.py:198-219):
 //
-//     np.random.choice(class_indices, N, replace=False)
+//     np.random.choice(class_indices, N, replace=False)       once per class per tree slot
+//     np.random.randint(min_feature, max_feature + 1)         once per candidate
 //
-// on numpy's GLOBAL LEGACY generator.  The algorithm lives in numpy (a dependency of the
+// on numpy's GLOBAL LEGACY generator.  The algorithms live in numpy (a dependency of the
 // reference, not vendored in it; numpy 2.3.5 here: numpy/random/mtrand.pyx `choice` ->
-// `permutation` -> `shuffle` -> `_shuffle_raw`, numpy/random/src/distributions/distributions.c
-// `random_interval`, numpy/random/src/mt19937/mt19937.c):
+// `permutation` -> `shuffle` -> `_shuffle_raw`, `randint` -> `_bounded_integers._rand_int64`,
+// numpy/random/src/distributions/distributions.c `random_interval` /
+// `buffered_bounded_masked_uint32`, numpy/random/src/mt19937/mt19937.c):
 //
 //     idx = permutation(n)[:N]        permutation(n) = shuffle(arange(n))
 //     shuffle: for i = n-1 .. 1:  j_i = random_interval(i);  swap(x[i], x[j_i])
 //     random_interval(max): mask = smallest 2^k-1 >= max; draw 32-bit MT19937 words until
 //                           (word & mask) <= max            (max <= 0xffffffff here)
+//     randint(lo, hi):      lo + the same masked rejection with max = hi-1-lo (no draw if 0)
 //
 // This is host code: the draw is an inherently sequential walk over the MT19937 stream and it is
 // the Amdahl floor of fit() once the grower runs on the GPU (numpy needs ~5 ms
@@ -22,17 +26,26 @@
 //   3. resolve - only the first N entries of the final permutation are needed.  Steps i >= N only
 //                change prefix position p when j_i == p, and what lands there is whatever sat at
 //                position i when step i ran, i.e. the end of the chain i -> (smallest i' > i with
-//                j_i' == i) -> ...  One ascending scan over J with a "current chain head" bitmap
-//                resolves all N chains; steps i < N are then simulated on the N-element prefix.
+//                j_i' == i) -> ...  One ascending scan over the draws with a "current chain head"
+//                bitmap resolves all N chains; steps i < N are then simulated on the prefix.
+//
+// Passes 1+2 are the sequential part (they decide where the next draw starts in the stream);
+// pass 3 only reads that draw's accepted words, so rfmc_legacy_draw_plan hands it to worker
+// threads while the main thread already walks the stream for the next class / slot.
 //
 // State hand-off is np.random.get_state() / set_state(): key[624] + pos.  Parity:
-// tests/test_host_rng.py compares indices AND end state with numpy itself.
+// tests/test_host_rng.py compares indices, randint values AND end state with numpy itself.
 #include <stdint.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
+#define RFMC_HAVE_AVX2 1
 #endif
 
 #include "../../include/rfmc_b200.h"
@@ -73,24 +86,34 @@ RFMC_CLONES void mt_temper(const uint32_t* k, uint32_t* out) {
     }
 }
 
-struct Scratch {
-    std::vector<uint32_t> A;  // accepted draws in stream order: A[k] = j_i for i = n-1-k
-    std::vector<uint32_t> live;
-    std::vector<int32_t> owner;
-    std::vector<int32_t> head;
-};
-thread_local Scratch g_s;
-
 struct Stream {  // numpy's MT19937 state + the tempered copy of the current block
     uint32_t* key;
     int pos;
     uint32_t tw[MT_N];
+    void attach(uint32_t* k, int p) {
+        key = k;
+        pos = p;
+        if (pos < MT_N) mt_temper(key, tw);
+    }
     void refill() {
         mt_regen(key);
         mt_temper(key, tw);
         pos = 0;
     }
+    uint32_t next() {
+        if (pos == MT_N) refill();
+        return tw[pos++];
+    }
 };
+
+inline uint32_t all_ones_at_least(uint32_t v) {
+    v |= v >> 1;
+    v |= v >> 2;
+    v |= v >> 4;
+    v |= v >> 8;
+    v |= v >> 16;
+    return v;
+}
 
 // Branch-free scalar rejection over one mask level: consume words until i reaches lo.
 inline void reject_scalar(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uint32_t* A, int64_t& k, int max_words) {
@@ -112,10 +135,9 @@ inline void reject_scalar(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uin
     }
 }
 
-#if defined(__x86_64__) && defined(__GNUC__)
-#define RFMC_HAVE_AVX2 1
+#ifdef RFMC_HAVE_AVX2
 alignas(32) uint32_t g_compress_lut[256][8];
-bool g_lut_ready = false;
+std::once_flag g_lut_once;
 void build_lut() {
     for (int m = 0; m < 256; ++m) {
         int c = 0;
@@ -123,7 +145,6 @@ void build_lut() {
             if (m & (1 << b)) g_compress_lut[m][c++] = (uint32_t)b;
         for (; c < 8; ++c) g_compress_lut[m][c] = 0;
     }
-    g_lut_ready = true;
 }
 
 // 8 words at a time.  Lane l sees i - (accepted before l) >= i - 7, so u <= i-7 is accepted and
@@ -131,8 +152,46 @@ void build_lut() {
 __attribute__((target("avx2"))) void reject_avx2(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uint32_t* A,
                                                    int64_t& k) {
     const __m256i vmask = _mm256_set1_epi32((int)mask);
+    const bool wide = mask >= 32767;  // 32 words per step while a neighbour-dependent lane stays rare
     while (i > lo) {
         if (st.pos == MT_N) st.refill();
+        if (wide && MT_N - st.pos >= 32 && i - 32 >= lo) {
+            // same argument with a window of 32: u <= i-31 is accepted, u > i rejected, whatever the
+            // other 31 lanes do -> one loop-carried update of i per 32 words
+            const __m256i* w = (const __m256i*)(st.tw + st.pos);
+            const __m256i vi = _mm256_set1_epi32((int)i), vs = _mm256_set1_epi32((int)(i - 31));
+            const __m256i u0 = _mm256_and_si256(_mm256_loadu_si256(w + 0), vmask);
+            const __m256i u1 = _mm256_and_si256(_mm256_loadu_si256(w + 1), vmask);
+            const __m256i u2 = _mm256_and_si256(_mm256_loadu_si256(w + 2), vmask);
+            const __m256i u3 = _mm256_and_si256(_mm256_loadu_si256(w + 3), vmask);
+            const __m256i g0 = _mm256_cmpgt_epi32(u0, vi), g1 = _mm256_cmpgt_epi32(u1, vi);
+            const __m256i g2 = _mm256_cmpgt_epi32(u2, vi), g3 = _mm256_cmpgt_epi32(u3, vi);
+            const __m256i amb = _mm256_or_si256(
+                _mm256_or_si256(_mm256_xor_si256(g0, _mm256_cmpgt_epi32(u0, vs)), _mm256_xor_si256(g1, _mm256_cmpgt_epi32(u1, vs))),
+                _mm256_or_si256(_mm256_xor_si256(g2, _mm256_cmpgt_epi32(u2, vs)), _mm256_xor_si256(g3, _mm256_cmpgt_epi32(u3, vs))));
+            if (_mm256_testz_si256(amb, amb)) {
+                const int m0 = (~_mm256_movemask_ps(_mm256_castsi256_ps(g0))) & 0xFF;
+                const int m1 = (~_mm256_movemask_ps(_mm256_castsi256_ps(g1))) & 0xFF;
+                const int m2 = (~_mm256_movemask_ps(_mm256_castsi256_ps(g2))) & 0xFF;
+                const int m3 = (~_mm256_movemask_ps(_mm256_castsi256_ps(g3))) & 0xFF;
+                const int c0 = __builtin_popcount((unsigned)m0), c1 = __builtin_popcount((unsigned)m1);
+                const int c2 = __builtin_popcount((unsigned)m2), c3 = __builtin_popcount((unsigned)m3);
+                uint32_t* dst = A + k;
+                _mm256_storeu_si256((__m256i*)dst,
+                                    _mm256_permutevar8x32_epi32(u0, _mm256_load_si256((const __m256i*)g_compress_lut[m0])));
+                _mm256_storeu_si256((__m256i*)(dst + c0),
+                                    _mm256_permutevar8x32_epi32(u1, _mm256_load_si256((const __m256i*)g_compress_lut[m1])));
+                _mm256_storeu_si256((__m256i*)(dst + c0 + c1),
+                                    _mm256_permutevar8x32_epi32(u2, _mm256_load_si256((const __m256i*)g_compress_lut[m2])));
+                _mm256_storeu_si256((__m256i*)(dst + c0 + c1 + c2),
+                                    _mm256_permutevar8x32_epi32(u3, _mm256_load_si256((const __m256i*)g_compress_lut[m3])));
+                const int c = c0 + c1 + c2 + c3;
+                k += c;
+                i -= c;
+                st.pos += 32;
+                continue;
+            }
+        }
         if (MT_N - st.pos < 8 || i - 8 < lo) {
             reject_scalar(st, mask, lo, i, A, k, 8);
             continue;
@@ -199,39 +258,21 @@ void resolve_scalar(const uint32_t* A, int64_t n, int64_t size, uint32_t* live, 
     }
 }
 
-}  // namespace
-
-extern "C" int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos_io, int64_t n, int64_t size, int64_t* out) {
-    if (!key || !pos_io || !out || n < 0 || size < 0 || size > n || n > 0x7fffffffll || *pos_io < 0 || *pos_io > MT_N)
-        return 1;
-    if (n == 0) return 0;
-    if (n == 1) {
-        if (size) out[0] = 0;
-        return 0;
-    }
-    Scratch& s = g_s;
-    if ((int64_t)s.A.size() < n + 16) {
-        s.A.resize((size_t)n + 16);
-        s.owner.resize((size_t)n);
-    }
-    uint32_t* A = s.A.data();
-    Stream st;
-    st.key = key;
-    st.pos = *pos_io;
-    if (st.pos < MT_N) mt_temper(key, st.tw);
-    bool avx2 = false;
+bool have_avx2() {
 #ifdef RFMC_HAVE_AVX2
-    avx2 = __builtin_cpu_supports("avx2");
-    if (avx2 && !g_lut_ready) build_lut();
+    static const bool ok = __builtin_cpu_supports("avx2");
+    if (ok) std::call_once(g_lut_once, build_lut);
+    return ok;
+#else
+    return false;
 #endif
+}
 
-    // ---- passes 1+2: words and rejection, i = n-1 .. 1; A[k] = j_(n-1-k) ----
-    uint32_t mask = (uint32_t)(n - 1);
-    mask |= mask >> 1;
-    mask |= mask >> 2;
-    mask |= mask >> 4;
-    mask |= mask >> 8;
-    mask |= mask >> 16;
+// passes 1+2: A[k] = j_(n-1-k), k = 0 .. n-2.  A needs n + 64 entries (vector stores overshoot).
+void draw_accepted(Stream& st, int64_t n, uint32_t* A) {
+    if (n < 2) return;
+    const bool avx2 = have_avx2();
+    uint32_t mask = all_ones_at_least((uint32_t)(n - 1));
     int64_t i = n - 1, k = 0;
     while (i >= 1) {
         const int64_t lo = (int64_t)(mask >> 1);  // this mask serves i in (lo, mask]
@@ -243,13 +284,23 @@ extern "C" int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos_io, in
             reject_scalar(st, mask, lo, i, A, k, 0x7fffffff);
         mask >>= 1;
     }
+}
 
-    // ---- pass 3: resolve the first `size` entries ----
+struct Scratch {
+    std::vector<uint32_t> A, live;
+    std::vector<int32_t> owner, head;
+};
+thread_local Scratch g_s;
+
+// pass 3: head[0..size) = permutation(n)[:size] given the accepted draws.
+const int32_t* resolve_prefix(const uint32_t* A, int64_t n, int64_t size) {
+    Scratch& s = g_s;
     if ((int64_t)s.head.size() < size + 1) s.head.resize((size_t)size + 1);
-    int32_t* head = s.head.data();
-    int32_t* owner = s.owner.data();
+    if ((int64_t)s.owner.size() < n) s.owner.resize((size_t)n);
     const size_t words = (size_t)((n + 31) / 32);
     if (s.live.size() < words) s.live.resize(words);
+    int32_t* head = s.head.data();
+    int32_t* owner = s.owner.data();
     uint32_t* live = s.live.data();
     memset(live, 0, words * sizeof(uint32_t));
     for (int64_t p = 0; p < size; ++p) {
@@ -257,19 +308,164 @@ extern "C" int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos_io, in
         owner[p] = (int32_t)p;
         live[p >> 5] |= 1u << (p & 31);
     }
+    if (n >= 2) {
 #ifdef RFMC_HAVE_AVX2
-    if (avx2)
-        resolve_avx2(A, n, size, live, owner, head);
-    else
+        if (have_avx2())
+            resolve_avx2(A, n, size, live, owner, head);
+        else
 #endif
-        resolve_scalar(A, n, size, live, owner, head);
-    for (int64_t q = size - 1; q >= 1; --q) {  // steps i < size act inside the prefix only
-        const uint32_t j = A[n - 1 - q];
-        const int32_t t = head[q];
-        head[q] = head[j];
-        head[j] = t;
+            resolve_scalar(A, n, size, live, owner, head);
+        for (int64_t q = size - 1; q >= 1; --q) {  // steps i < size act inside the prefix only
+            const uint32_t j = A[n - 1 - q];
+            const int32_t t = head[q];
+            head[q] = head[j];
+            head[j] = t;
+        }
     }
+    return head;
+}
+
+struct Task {
+    uint32_t* A = nullptr;
+    int64_t n = 0, size = 0, n_train = 0;
+    const int64_t* rows = nullptr;
+    int32_t* out_train = nullptr;
+    int32_t* out_val = nullptr;
+};
+
+void run_task(const Task& t) {
+    const int32_t* head = resolve_prefix(t.A, t.n, t.size);
+    for (int64_t p = 0; p < t.size; ++p) {
+        const int32_t row = (int32_t)t.rows[head[p]];
+        if (p < t.n_train)
+            t.out_train[p] = row;
+        else
+            t.out_val[p - t.n_train] = row;
+    }
+}
+
+struct Pool {  // bounded hand-off of resolve tasks to worker threads
+    std::mutex mu;
+    std::condition_variable cv_task, cv_buf;
+    std::deque<Task> tasks;
+    std::vector<uint32_t*> free_bufs;
+    bool closing = false;
+    void worker() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_task.wait(lk, [&] { return closing || !tasks.empty(); });
+                if (tasks.empty()) return;
+                t = tasks.front();
+                tasks.pop_front();
+            }
+            run_task(t);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                free_bufs.push_back(t.A);
+            }
+            cv_buf.notify_one();
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos_io, int64_t n, int64_t size, int64_t* out) {
+    if (!key || !pos_io || !out || n < 0 || size < 0 || size > n || n > 0x7fffffffll || *pos_io < 0 || *pos_io > MT_N)
+        return 1;
+    if (n == 0) return 0;
+    Scratch& s = g_s;
+    if ((int64_t)s.A.size() < n + 64) s.A.resize((size_t)n + 64);
+    Stream st;
+    st.attach(key, *pos_io);
+    draw_accepted(st, n, s.A.data());
+    const int32_t* head = resolve_prefix(s.A.data(), n, size);
     for (int64_t p = 0; p < size; ++p) out[p] = head[p];
+    *pos_io = st.pos;
+    return 0;
+}
+
+extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_slots, int32_t n_classes,
+                                     const int64_t* class_rows, const int64_t* class_off, int64_t per_class,
+                                     int64_t n_train_pclass, int32_t n_cands, int64_t randint_low, int64_t randint_high,
+                                     int32_t* idx_train, int32_t* idx_val, int32_t* feat_counts, uint32_t* key_snap,
+                                     int32_t* pos_snap, int32_t n_threads) {
+    if (!key || !pos_io || !class_rows || !class_off || n_slots < 0 || n_classes < 1 || per_class < 0 ||
+        n_train_pclass < 0 || n_cands < 0 || randint_high <= randint_low || *pos_io < 0 || *pos_io > MT_N)
+        return 1;
+    int64_t max_n = 0;
+    for (int c = 0; c < n_classes; ++c) {
+        const int64_t n = class_off[c + 1] - class_off[c];
+        if (n < per_class || n > 0x7fffffffll) return 1;
+        if (n > max_n) max_n = n;
+    }
+    const int64_t n_tr = per_class < n_train_pclass ? per_class : n_train_pclass;  // selected[:batch_train]
+    const int64_t n_va = per_class - n_tr;                                          // selected[batch_train:]
+    const uint64_t rng = (uint64_t)(randint_high - 1 - randint_low);
+    if (rng > 0xFFFFFFFEull) return 1;
+    const uint32_t rmask = all_ones_at_least((uint32_t)rng);
+    if (n_threads < 0) n_threads = 0;
+    if (n_threads > 32) n_threads = 32;
+
+    Pool pool;
+    std::vector<std::vector<uint32_t>> bufs((size_t)(n_threads ? 2 * n_threads + 2 : 1));
+    for (auto& b : bufs) {
+        b.resize((size_t)max_n + 64);
+        pool.free_bufs.push_back(b.data());
+    }
+    std::vector<std::thread> workers;
+    for (int t = 0; t < n_threads; ++t) workers.emplace_back([&pool] { pool.worker(); });
+
+    Stream st;
+    st.attach(key, *pos_io);
+    for (int32_t s = 0; s < n_slots; ++s) {
+        if (key_snap) memcpy(key_snap + (size_t)s * MT_N, key, MT_N * sizeof(uint32_t));
+        if (pos_snap) pos_snap[s] = st.pos;
+        for (int c = 0; c < n_classes; ++c) {
+            Task t;
+            t.n = class_off[c + 1] - class_off[c];
+            t.size = per_class;
+            t.n_train = n_tr;
+            t.rows = class_rows + class_off[c];
+            t.out_train = idx_train + ((size_t)s * n_classes + c) * n_tr;
+            t.out_val = idx_val + ((size_t)s * n_classes + c) * n_va;
+            if (n_threads) {
+                std::unique_lock<std::mutex> lk(pool.mu);
+                pool.cv_buf.wait(lk, [&] { return !pool.free_bufs.empty(); });
+                t.A = pool.free_bufs.back();
+                pool.free_bufs.pop_back();
+            } else {
+                t.A = bufs[0].data();
+            }
+            draw_accepted(st, t.n, t.A);
+            if (n_threads) {
+                {
+                    std::lock_guard<std::mutex> lk(pool.mu);
+                    pool.tasks.push_back(t);
+                }
+                pool.cv_task.notify_one();
+            } else {
+                run_task(t);
+            }
+        }
+        for (int32_t k = 0; k < n_cands; ++k) {  // np.random.randint(low, high), one per candidate
+            uint32_t v = 0;
+            if (rng != 0) {
+                do {
+                    v = st.next() & rmask;
+                } while (v > (uint32_t)rng);
+            }
+            feat_counts[(size_t)s * n_cands + k] = (int32_t)(randint_low + (int64_t)v);
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        pool.closing = true;
+    }
+    pool.cv_task.notify_all();
+    for (auto& w : workers) w.join();
     *pos_io = st.pos;
     return 0;
 }

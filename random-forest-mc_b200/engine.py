@@ -52,6 +52,8 @@ _SIGNATURES = {
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
     "rfmc_forest_leaves": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p]),
     "rfmc_legacy_permutation_prefix": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, _p]),
+    "rfmc_legacy_draw_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p, C.c_int64, C.c_int64,
+                                        C.c_int32, C.c_int64, C.c_int64, _p, _p, _p, _p, _p, C.c_int32]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -115,6 +117,31 @@ def legacy_choice_indices(key: np.ndarray, pos: int, n: int, size: int):
     if rc != 0:
         raise EngineError("rfmc_legacy_permutation_prefix: bad arguments")
     return out, p.value
+
+
+def legacy_draw_plan(key: np.ndarray, pos: int, n_slots: int, class_rows: Sequence[np.ndarray], per_class: int,
+                     n_train_pclass: int, n_cands: int, low: int, high: int, n_threads: int = 4):
+    """The numpy-stream draws of ``n_slots`` tree slots (rows per class, then ``n_cands`` feature
+    counts per slot) in one host call.  Returns (idx_train, idx_val, feat_counts, key_snap,
+    pos_snap, new_pos); ``key`` is advanced in place."""
+    C_ = len(class_rows)
+    rows = np.ascontiguousarray(np.concatenate(class_rows), dtype=np.int64)
+    off = np.zeros(C_ + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(r) for r in class_rows])
+    n_tr = min(per_class, n_train_pclass)
+    idx_train = np.empty((n_slots, C_ * n_tr), dtype=np.int32)
+    idx_val = np.empty((n_slots, C_ * (per_class - n_tr)), dtype=np.int32)
+    counts = np.empty((n_slots, n_cands), dtype=np.int32)
+    key_snap = np.empty((n_slots, 624), dtype=np.uint32)
+    pos_snap = np.empty(n_slots, dtype=np.int32)
+    p = C.c_int32(pos)
+    rc = load_library().rfmc_legacy_draw_plan(
+        _ptr(key), C.byref(p), n_slots, C_, _ptr(rows), _ptr(off), per_class, n_train_pclass, n_cands, low, high,
+        _ptr(idx_train), _ptr(idx_val), _ptr(counts), _ptr(key_snap), _ptr(pos_snap), n_threads,
+    )
+    if rc != 0:
+        raise EngineError("rfmc_legacy_draw_plan: bad arguments")
+    return idx_train, idx_val, counts, key_snap, pos_snap, p.value
 
 
 class DeviceDataset:

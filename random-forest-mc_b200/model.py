@@ -21,6 +21,7 @@ there.  The committed sequence of draws is therefore exactly the serial referenc
 from __future__ import annotations
 
 import logging as log
+import os
 import random as _pyrandom
 from sys import getrecursionlimit
 from typing import List, Optional, Tuple
@@ -142,6 +143,7 @@ class RandomForestMC(BaseRandomForestMC):
         self.fit_stats = {}
         self.max_candidates_per_launch = 4096
         self.max_batch_bytes = 24 << 30
+        self.rng_threads = max(0, min(6, (os.cpu_count() or 1) - 1))
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -214,6 +216,35 @@ class RandomForestMC(BaseRandomForestMC):
     def _feat_ids(self, feature_list: List[str]) -> List[int]:
         pos = {name: j for j, name in enumerate(self.feature_cols)}
         return [pos[f] for f in feature_list]
+
+    def _draw_plan(self, n_plan: int, spec: int):
+        """All draws of ``n_plan`` slots with ``spec`` candidates each, in the reference's order.
+        numpy's stream (rows per class, then one feature count per candidate) is walked by ONE host
+        call (``rfmc_legacy_draw_plan``); CPython's ``random.sample`` -- a separate stream --
+        then picks and orders the features.  Entry layout as ``_draw_slot``."""
+        if self.min_feature > self.max_feature:
+            raise ValueError("low >= high")  # what np.random.randint raises in the reference
+        st = np.random.get_state()
+        key = st[1].copy()
+        T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
+            key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,
+            int(self.min_feature), int(self.max_feature) + 1, self.rng_threads,
+        )
+        np.random.set_state((st[0], key, pos, st[3], st[4]))
+        cols = self.feature_cols
+        where = {name: j for j, name in enumerate(cols)}
+        plan = []
+        for s in range(n_plan):
+            py_state = _pyrandom.getstate()
+            feats = []
+            for k in range(spec):
+                out = _pyrandom.sample(cols, min(len(cols), int(K[s, k])))
+                if self.temporal_features:
+                    out = sorted(out, key=lambda x: int(x.split("_")[-1]))
+                feats.append([where[f] for f in out])
+            start = ((st[0], ksnap[s], int(psnap[s]), st[3], st[4]), py_state)
+            plan.append((T[s], V[s], feats, (start, True)))
+        return plan
 
     def _wrap(self, soa, score=None) -> DecisionTreeMC:
         t = DecisionTreeMC.from_soa(soa, self.encoded, self.type_of_cols, self.class_vals)
@@ -335,7 +366,7 @@ class RandomForestMC(BaseRandomForestMC):
             if avg_commit != float("inf"):
                 n_plan = min(n_plan, max(4, int(4 * avg_commit) + 1))
             t0 = _now()
-            plan = [self._draw_slot(spec) for _ in range(n_plan)]
+            plan = self._draw_plan(n_plan, spec)
             t1 = _now()
             batch, first = self._grow_plan(plan, stream)
             t2 = _now()

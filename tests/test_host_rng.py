@@ -36,3 +36,35 @@ def test_stream_continues_exactly():
     got.append(np.random.randint(2, 60))
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("threads", [0, 3])
+@pytest.mark.parametrize("per_class,n_train,lo,hi", [(20, 10, 2, 65), (7, 10, 2, 3), (300, 250, 3, 9), (5, 5, 4, 5)])
+def test_draw_plan_matches_numpy_call_sequence(threads, per_class, n_train, lo, hi):
+    """choice x classes then randint x candidates per slot, exactly numpy's values and end state."""
+    g = np.random.default_rng(3)
+    sizes = [700, 1501, 333, 4096]
+    class_rows = [np.sort(g.choice(100000, s, replace=False)).astype(np.int64) for s in sizes]
+    n_slots, n_cands = 5, 3
+    np.random.seed(11)
+    np.random.random_sample(3)
+    st = np.random.get_state()
+    want_T, want_V, want_k, want_state = [], [], [], []
+    for s in range(n_slots):
+        want_state.append(np.random.get_state())
+        tr, va = [], []
+        for rows in class_rows:
+            sel = np.random.choice(rows, per_class, replace=False)
+            tr.extend(sel[:n_train])
+            va.extend(sel[n_train:])
+        want_T.append(tr), want_V.append(va)
+        want_k.append([np.random.randint(lo, hi) for _ in range(n_cands)])
+    after = np.random.get_state()
+    key = st[1].copy()
+    T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(key, int(st[2]), n_slots, class_rows, per_class, n_train, n_cands, lo, hi, threads)
+    assert np.array_equal(T, np.array(want_T, dtype=np.int64).reshape(T.shape))
+    assert np.array_equal(V, np.array(want_V, dtype=np.int64).reshape(V.shape))
+    assert np.array_equal(K, np.array(want_k))
+    assert np.array_equal(key, after[1]) and pos == after[2]
+    for s in range(n_slots):
+        assert np.array_equal(ksnap[s], want_state[s][1]) and psnap[s] == want_state[s][2]
