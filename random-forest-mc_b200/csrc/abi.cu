@@ -1,5 +1,8 @@
 // extern "C" entry points of librfmc_b200.so (declared in include/rfmc_b200.h).
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -7,11 +10,78 @@ namespace rfmc {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+// Device memory comes from a small caching allocator: a fit makes one batch per plan with the
+// same gigabyte-sized scratch and output buffers, and cudaMalloc/cudaFree of those costs tens of
+// milliseconds per batch.  Blocks >= 1 MiB are kept per device on release and handed out again to
+// requests of similar size.  Every release in this file happens after the work that used the
+// block has been synchronised.
+struct DevCache {
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t cached = 0;
+};
+static std::mutex g_mem_mu;
+static std::map<int, DevCache> g_mem;
+constexpr size_t CACHE_MIN_BLOCK = 1u << 20;
+constexpr size_t CACHE_CAP = 48ull << 30;
+
+static void flush_cache_locked(DevCache& dc) {
+    for (auto& kv : dc.free_blocks) cudaFree(kv.second);
+    dc.free_blocks.clear();
+    dc.cached = 0;
+}
+
+static cudaError_t dev_alloc(void** p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    DevCache& dc = g_mem[dev];
+    if (bytes >= CACHE_MIN_BLOCK) {
+        auto it = dc.free_blocks.lower_bound(bytes);
+        if (it != dc.free_blocks.end() && it->first <= bytes + bytes / 2) {
+            *p = it->second;
+            dc.live[*p] = it->first;
+            dc.cached -= it->first;
+            dc.free_blocks.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        flush_cache_locked(dc);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) dc.live[*p] = bytes;
+    return e;
+}
+
+static void release(void* p) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    DevCache& dc = g_mem[dev];
+    auto it = dc.live.find(p);
+    if (it == dc.live.end()) {
+        cudaFree(p);
+        return;
+    }
+    const size_t bytes = it->second;
+    dc.live.erase(it);
+    if (bytes >= CACHE_MIN_BLOCK && dc.cached + bytes <= CACHE_CAP) {
+        dc.free_blocks.emplace(bytes, p);
+        dc.cached += bytes;
+    } else {
+        cudaFree(p);
+    }
+}
+
 template <typename T>
 static int upload(T** dst, const T* src, size_t count, cudaStream_t stream) {
     *dst = nullptr;
     if (count == 0) return 0;
-    RFMC_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    RFMC_CUDA(dev_alloc((void**)dst, count * sizeof(T)));
     RFMC_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
     return 0;
 }
@@ -19,11 +89,27 @@ template <typename T>
 static int reserve(T** dst, size_t count) {
     *dst = nullptr;
     if (count == 0) count = 1;
-    RFMC_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    RFMC_CUDA(dev_alloc((void**)dst, count * sizeof(T)));
     return 0;
 }
-static void release(void* p) {
-    if (p) cudaFree(p);
+
+// One pinned staging buffer per process for device -> host survivor export.
+static void* g_pin = nullptr;
+static size_t g_pin_cap = 0;
+static void* pinned_staging(size_t bytes) {
+    if (bytes > g_pin_cap) {
+        if (g_pin) cudaFreeHost(g_pin);
+        g_pin = nullptr;
+        g_pin_cap = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaHostAlloc(&g_pin, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            g_pin = nullptr;
+            return nullptr;
+        }
+        g_pin_cap = want;
+    }
+    return g_pin;
 }
 }  // namespace rfmc
 
@@ -279,10 +365,23 @@ int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_
     }
     if (!rc) rc = launch_pack(b, d_ids, d_off, n_sel, d_nodes, d_counts, st);
     if (!rc && !dst_on_device) {
-        if (cudaMemcpyAsync(nodes_out, d_nodes, total * sizeof(rfmc_node), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(counts_out, d_counts, total * C * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        // device -> pinned staging (full-rate DMA) -> caller's pageable buffers
+        const size_t nb = total * sizeof(rfmc_node), cb = total * C * sizeof(int32_t);
+        uint8_t* pin = (uint8_t*)pinned_staging(nb + cb);
+        void* h_nodes = pin ? (void*)pin : (void*)nodes_out;
+        void* h_counts = pin ? (void*)(pin + nb) : (void*)counts_out;
+        if (cudaMemcpyAsync(h_nodes, d_nodes, nb, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_counts, d_counts, cb, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
             set_error("pack: device to host copy failed");
             rc = 1;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess && !rc) {
+            set_error(std::string("pack failed: ") + cudaGetErrorString(cudaGetLastError()));
+            rc = 1;
+        }
+        if (!rc && pin) {
+            std::memcpy(nodes_out, h_nodes, nb);
+            std::memcpy(counts_out, h_counts, cb);
         }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && !rc) {
