@@ -345,10 +345,11 @@ def run_b200(args):
 
     e2e_fit()  # warm-up
     barrier()
-    e2e_s, e2e_cands, forest = 0.0, 0, None
+    e2e_s, e2e_cands, forest, e2e_each = 0.0, 0, None, []
     for _ in range(args.e2e_steps):
         dt, forest = e2e_fit()
         e2e_s += dt
+        e2e_each.append(round(dt * 1e3, 2))
         e2e_cands += model.fit_stats["candidates_grown"]
     barrier()
     e2e_s = max_over_ranks(e2e_s)
@@ -448,6 +449,7 @@ def run_b200(args):
                 "api": "RandomForestMC fit loop (_fit_slots): host RNG draws + H2D + grow/score kernel + D2H scores + survivor tables"
                 + ("; + all-gather of survivors" if world > 1 else ""),
                 "ms_per_step": e2e_s / args.e2e_steps * 1e3,
+                "ms_each_rank0": e2e_each,
                 "fit_stats": stats,
             },
             "gpu_launches": int(launches),

@@ -287,7 +287,7 @@ int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_
     b->nt_pad = (n_train + 15) / 16 * 16;
     b->max_nodes = 2 * n_train;
     b->fmax = fmax;
-    b->grid = grow_grid_size(ds, n_cand);
+    b->grid = grow_grid_size(ds, n_cand, n_train);
     b->stream = st;
     const size_t g = (size_t)b->grid, ntp = (size_t)b->nt_pad, C = (size_t)ds->n_classes;
     int rc = 0;
@@ -300,7 +300,9 @@ int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_
     rc |= reserve(&b->d_lab, g * ntp);
     rc |= reserve(&b->d_pos, g * 2 * ntp);
     rc |= reserve(&b->d_work, g * 2 * ntp);
-    rc |= reserve(&b->d_resna, g * ntp);
+    rc |= reserve(&b->d_resna, g * 2 * ntp);
+    rc |= reserve(&b->d_rank, g * ntp);
+    rc |= reserve(&b->d_resfin, g * ntp);
     rc |= reserve(&b->d_nodes, (size_t)n_cand * b->max_nodes);
     rc |= reserve(&b->d_counts, (size_t)n_cand * b->max_nodes * C);
     rc |= reserve(&b->d_votes, (size_t)n_cand * b->max_nodes);
@@ -411,6 +413,8 @@ int rfmc_batch_destroy(rfmc_batch* b) {
     release(b->d_pos);
     release(b->d_work);
     release(b->d_resna);
+    release(b->d_rank);
+    release(b->d_resfin);
     release(b->d_nodes);
     release(b->d_counts);
     release(b->d_votes);

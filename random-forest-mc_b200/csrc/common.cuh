@@ -33,7 +33,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct WorkItem {  // one node of the level being processed
     uint32_t lo, hi;  // segment of the candidate's position array
-    uint32_t node;    // node id in the candidate's node table
+    uint32_t lpos;    // position inside its level (node id = level base + lpos)
     uint32_t off;     // rotation offset into the candidate's feature list
 };
 
@@ -73,6 +73,8 @@ struct rfmc_batch {
     uint32_t* d_pos = nullptr;
     rfmc::WorkItem* d_work = nullptr;
     uint32_t* d_resna = nullptr;
+    uint32_t* d_rank = nullptr;
+    uint16_t* d_resfin = nullptr;
     // per-candidate outputs
     rfmc_node* d_nodes = nullptr;
     int32_t* d_counts = nullptr;
@@ -104,7 +106,7 @@ struct rfmc_forest {
 
 namespace rfmc {
 int launch_grow(rfmc_batch* b, cudaStream_t stream);
-int grow_grid_size(const rfmc_dataset* ds, int n_cand);
+int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train);
 int launch_pack(rfmc_batch* b, const int32_t* d_cand_ids, const int64_t* d_dst_off, int32_t n_sel, rfmc_node* nodes_out,
                 int32_t* counts_out, cudaStream_t stream);
 int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,

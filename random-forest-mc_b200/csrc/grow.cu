@@ -4,20 +4,32 @@
 // (model.py:296-314) of the reference for a whole batch of candidates in one launch.
 //
 // Mapping: one persistent CTA (256 threads = 8 warps) per candidate; the candidate's tree is grown
-// breadth-first.  Within a level every warp takes nodes from a shared ticket counter and does, for
-// its node, exactly what one growTree() call does in the reference:
+// breadth-first.  A node does exactly what one growTree() call does in the reference:
 //   class histogram -> purity / depth test -> for each feature of the rotated list:
 //   order statistics of the node's codes (median) or their mode -> split value in the column's
 //   dtype arithmetic -> code threshold -> side sizes -> accept or rotate -> stable partition.
-// Node numbering is breadth-first and deterministic (a block-wide scan assigns child ids after
-// every level), so the result is comparable array-for-array with oracle/code_model.py.
+//
+// A tree grown to purity on 8,000 rows has ~14,000 nodes; 59 % of its split nodes hold 2-4 rows,
+// 93 % hold <= 32, and every leaf is pure (88 % are single rows).  So the level's work list is kept
+// in three size classes, each with its own execution shape:
+//   tiny  (<= 4 rows)  one THREAD per node (32 nodes in flight per warp, scalar sorting network);
+//   small (5..32 rows) one WARP per node, one row per lane (ballots, shuffles, match.any);
+//   large (> 32 rows)  one WARP per node, 128 rows per iteration (4 independent gathers in flight
+//                      per lane), MSD radix select over per-warp shared-memory histograms.
+// A split's child that is provably a leaf already (a single row, or all rows of one class) is
+// written by the parent and never becomes a work item: that removes ~half of all node visits.
+//
+// Node numbering is breadth-first and deterministic: every node carries its position in its level;
+// after a level, a block-wide scan over the split flags (by level position) assigns child ids, so
+// the output equals oracle/code_model.py array-for-array whatever order the warps ran in.
 //
 // Memory: the candidate's bootstrap rows are gathered ONCE from the row-major HBM code matrix
 // (one coalesced row read per warp) into a compact per-candidate [feature][row] matrix that stays
-// L2-resident; all later accesses index that compact matrix by local row position.
-//
-// On-chip: per-warp shared-memory histograms (warp-aggregated atomics via match.any), ballots and
-// shuffles for rank counting, prefix sums and arg-max.
+// L2-resident; the row-position array and the labels live in shared memory (24 KB at 8,000
+// rows), so a node's dependent-load chain is: work item -> (smem) positions -> codes -> value
+// table.  Nodes of <= 32 rows hold their rows in registers and partition their segment in place;
+// larger nodes partition into a global scratch segment and copy back.  On-chip: per-warp shared-memory histograms with warp-aggregated atomics (match.any),
+// ballots and shuffles for rank counting, prefix sums and arg-max.
 #include "common.cuh"
 
 namespace rfmc {
@@ -25,8 +37,10 @@ namespace rfmc {
 constexpr int GROW_THREADS = 256;
 constexpr int GROW_WARPS = GROW_THREADS / 32;
 constexpr int HIST_WORDS = 512;  // per warp
+constexpr uint32_t NOT_FINAL = 0xFFu;
+constexpr int TINY_MAX = 4, SMALL_MAX = 32;
 
-template <typename CodeT>
+template <typename CodeT, typename PosT>
 struct GrowArgs {
     // dataset
     const CodeT* codes;
@@ -47,10 +61,13 @@ struct GrowArgs {
     const uint16_t* feat_list;
     // scratch (per CTA)
     CodeT* cc;
-    uint8_t* lab;
-    uint32_t* pos;
-    WorkItem* work;
-    uint32_t* resna;
+    uint8_t* lab_g;   // used when the arrays do not fit shared memory
+    PosT* pos_g;
+    WorkItem* work;   // 2 buffers x list capacity
+    uint32_t* resna;  // 2 buffers x nt_pad, indexed by level position
+    uint32_t* rank;   // nt_pad
+    uint16_t* resfin; // nt_pad
+    int32_t use_smem;
     // outputs (per candidate)
     rfmc_node* nodes;
     int32_t* counts;
@@ -113,9 +130,9 @@ __device__ __forceinline__ uint32_t find_bin256(const uint32_t* hist, uint32_t& 
 
 // The two middle order statistics (0-based ranks k0 and k0+1) of a node with more than 32 rows:
 // MSD radix select over 8-bit digits; both ranks share one histogram until their prefixes diverge.
-template <typename CodeT>
-__device__ void select_two(const CodeT* col, const uint32_t* P, uint32_t n, int npass, uint32_t k0, uint32_t* hist,
-                           int lane, uint32_t& ca, uint32_t& cb) {
+template <typename CodeT, typename PosT>
+__device__ void select_two(const CodeT* col, const PosT* P, uint32_t n, int npass, uint32_t k0, uint32_t* hist, int lane,
+                           uint32_t& ca, uint32_t& cb) {
     uint32_t prefA = 0, prefB = 0, rA = k0, rB = k0 + 1;
     bool same = true;
     for (int pass = npass - 1; pass >= 0; --pass) {
@@ -123,13 +140,24 @@ __device__ void select_two(const CodeT* col, const uint32_t* P, uint32_t n, int 
         const uint32_t himask = (pass == npass - 1) ? 0u : (0xFFFFFFFFu << (shift + 8));
         for (int i = lane; i < (same ? 256 : 512); i += 32) hist[i] = 0;
         __syncwarp();
-        for (uint32_t base = 0; base < n; base += 32) {
-            uint32_t i = base + lane;
-            bool act = i < n;
-            uint32_t c = act ? (uint32_t)col[P[i]] : 0u;
-            uint32_t d = (c >> shift) & 255u;
-            hist_add(hist, d, act && ((c & himask) == (prefA & himask)), lane);
-            if (!same) hist_add(hist + 256, d, act && ((c & himask) == (prefB & himask)), lane);
+        for (uint32_t base = 0; base < n; base += 128) {
+            uint32_t c[4];
+            bool act[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * 32 + lane;
+                act[u] = i < n;
+                c[u] = act[u] ? (uint32_t)P[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = act[u] ? (uint32_t)col[c[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base + u * 32 >= n) break;
+                const uint32_t d = (c[u] >> shift) & 255u;
+                hist_add(hist, d, act[u] && ((c[u] & himask) == (prefA & himask)), lane);
+                if (!same) hist_add(hist + 256, d, act[u] && ((c[u] & himask) == (prefB & himask)), lane);
+            }
         }
         __syncwarp();
         uint32_t dA = find_bin256(hist, rA, lane);
@@ -191,6 +219,41 @@ __device__ uint32_t count_less(const double* __restrict__ tab, uint32_t lo, uint
     return lo;
 }
 
+// Same contract, one thread (binary search).
+__device__ uint32_t count_less_scalar(const double* __restrict__ tab, uint32_t lo, uint32_t hi, double sv) {
+    while (hi > lo) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(&tab[mid]) < sv)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// lower_bound(table, sv) + 1 given the codes ca <= cb of the two order statistics that produced sv.
+__device__ __forceinline__ uint32_t threshold_scalar(const double* tab, uint32_t K, double sv, double va, double vb,
+                                                     uint32_t ca, uint32_t cb) {
+    if (sv != sv) return 0xFFFFFFFFu;  // every comparison with NaN is False
+    uint32_t less;
+    if (sv == va) less = ca - 1;
+    else if (sv == vb) less = cb - 1;
+    else if (va < sv && sv < vb) less = count_less_scalar(tab, ca, cb - 1, sv);
+    else less = count_less_scalar(tab, 0, K, sv);
+    return less + 1;
+}
+
+__device__ __forceinline__ uint32_t threshold_warp(const double* tab, uint32_t K, double sv, double va, double vb,
+                                                   uint32_t ca, uint32_t cb, int lane) {
+    if (sv != sv) return 0xFFFFFFFFu;
+    uint32_t less;
+    if (sv == va) less = ca - 1;
+    else if (sv == vb) less = cb - 1;
+    else if (va < sv && sv < vb) less = count_less(tab, ca, cb - 1, sv, lane);
+    else less = count_less(tab, 0, K, sv, lane);
+    return less + 1;
+}
+
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -200,63 +263,224 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
-template <typename CodeT>
+template <typename CodeT, typename PosT>
 struct CandCtx {
-    const GrowArgs<CodeT>* a;
+    const GrowArgs<CodeT, PosT>* a;
     CodeT* cc;
-    uint8_t* lab;
-    uint32_t* pos;
-    uint32_t* resna;
+    const uint8_t* lab;
+    PosT* pos;  // nt_pad: every node owns a segment; small/tiny nodes partition it in place
+    PosT* tmp;  // nt_pad (global): partition target of > 32-row nodes, copied back
+    uint32_t* resna;  // this level's buffer
+    uint16_t* resfin;
     rfmc_node* nodes;
     int32_t* counts;
     uint8_t* votes;
     const uint16_t* flist;
     int nf;
+    uint32_t base;  // node id of level position 0
+    int level;
 };
 
-// One growTree() call (model.py:266-291) for work item j of the current level, by one warp.
-template <typename CodeT>
-__device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j, int level, uint32_t* hist, int lane) {
-    const GrowArgs<CodeT>& a = *c.a;
-    const WorkItem w = cur[j];
+__device__ __forceinline__ void write_leaf(rfmc_node* nd) {
+    nd->feat = -1;
+    nd->thr = 0;
+    nd->child = -1;
+    nd->flags = 0;
+    nd->sval = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiny nodes: one THREAD per node, n in 1..4
+// ---------------------------------------------------------------------------------------------
+template <typename CodeT, typename PosT>
+__device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
+    const GrowArgs<CodeT, PosT>& a = *c.a;
+    const WorkItem w = *item;
     const uint32_t n = w.hi - w.lo;
-    const uint32_t* P = c.pos + (size_t)(level & 1) * a.nt_pad + w.lo;
-    uint32_t* Pn = c.pos + (size_t)((level + 1) & 1) * a.nt_pad + w.lo;
+    PosT* P = c.pos + w.lo;
+    PosT* Pn = P;  // rows are in registers: the partition goes back in place
+    const int C = a.n_classes;
+    const uint32_t node = c.base + w.lpos;
+
+    uint32_t p[TINY_MAX];
+    uint32_t l[TINY_MAX];
+#pragma unroll
+    for (int q = 0; q < TINY_MAX; ++q) {
+        p[q] = (q < (int)n) ? (uint32_t)P[q] : 0u;
+        l[q] = (q < (int)n) ? (uint32_t)c.lab[p[q]] : 0xFFFFu;
+    }
+    // class counts + vote (first max in sorted-label order)
+    int32_t* crow = c.counts + (size_t)node * C;
+    uint32_t best_c = 0, best_n = 0;
+    for (int k = 0; k < C; ++k) {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int q = 0; q < TINY_MAX; ++q) cnt += (l[q] == (uint32_t)k);
+        crow[k] = (int32_t)cnt;
+        if (cnt > best_n) {
+            best_n = cnt;
+            best_c = (uint32_t)k;
+        }
+    }
+    c.votes[node] = (uint8_t)best_c;
+    const bool pure = best_n == n;
+    const int depth = c.level + 1;
+    rfmc_node nd;
+    write_leaf(&nd);
+    uint32_t na_out = 0, fin_out = NOT_FINAL | (NOT_FINAL << 8);
+    if (!(depth >= a.max_depth || pure)) {
+        for (int k = 0; k < c.nf; ++k) {  // model.py:273-280
+            int fl = (int)w.off + k;
+            if (fl >= c.nf) fl -= c.nf;
+            const uint32_t f = c.flist[fl];
+            const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
+            const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
+            uint32_t cv[TINY_MAX];
+#pragma unroll
+            for (int q = 0; q < TINY_MAX; ++q) cv[q] = (q < (int)n) ? (uint32_t)col[p[q]] : 0u;
+            uint32_t t_store, t_part, go = 0, fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
+            double sv = 0.0;
+            if (n == 2) {  // model.py:258-262
+                t_store = t_part = cv[0] > cv[1] ? cv[0] : cv[1];
+                fl_flags |= RFMC_FLAG_TWO_ROW;
+                go = (cv[0] <= cv[1]) ? 2u : 1u;
+            } else if (cat) {  // mode, ties -> lowest code
+                uint32_t bc = 0, bn = 0;
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) {
+                    if (q >= (int)n) break;
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int r = 0; r < TINY_MAX; ++r) cnt += (r < (int)n) && (cv[r] == cv[q]);
+                    if (cnt > bn || (cnt == bn && cv[q] < bc)) {
+                        bn = cnt;
+                        bc = cv[q];
+                    }
+                }
+                t_store = t_part = bc;
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] == bc) ? (1u << q) : 0u;
+            } else {  // median of 3 or 4 (ranks 1 and 2 of the sorted codes)
+                uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = (n == 4) ? cv[3] : 0xFFFFFFFFu;
+                uint32_t t;
+#define RFMC_CSWAP(x, y) if (x > y) { t = x; x = y; y = t; }
+                RFMC_CSWAP(s0, s1) RFMC_CSWAP(s2, s3) RFMC_CSWAP(s0, s2) RFMC_CSWAP(s1, s3) RFMC_CSWAP(s1, s2)
+#undef RFMC_CSWAP
+                const uint32_t ca = s1, cb = s2;
+                const double* tab = a.tables + a.tab_off[f];
+                const uint32_t K = (uint32_t)a.col_nuniq[f];
+                const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
+                sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
+                t_store = t_part = threshold_scalar(tab, K, sv, va, vb, ca, cb);
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] >= t_part) ? (1u << q) : 0u;
+                uint32_t cnt = __popc(go);
+                if ((cnt == 0 || cnt == n) && t_store != 0xFFFFFFFFu) {  // model.py:242-245
+                    const uint32_t i0 = t_store - 1;
+                    t_part = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
+                    go = 0;
+#pragma unroll
+                    for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] >= t_part) ? (1u << q) : 0u;
+                }
+            }
+            const uint32_t cnt_a = __popc(go);
+            if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
+                // stable partition + purity of both sides
+                uint32_t oa = 0, ob = cnt_a, la = 0xFFFFu, lb = 0xFFFFu;
+                bool pa = true, pb = true;
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) {
+                    if (q >= (int)n) break;
+                    if ((go >> q) & 1u) {
+                        Pn[oa++] = (PosT)p[q];
+                        if (la == 0xFFFFu) la = l[q];
+                        pa = pa && (l[q] == la);
+                    } else {
+                        Pn[ob++] = (PosT)p[q];
+                        if (lb == 0xFFFFu) lb = l[q];
+                        pb = pb && (l[q] == lb);
+                    }
+                }
+                nd.feat = (int32_t)f;
+                nd.thr = t_store;
+                nd.flags = fl_flags;
+                nd.sval = (cat || (fl_flags & RFMC_FLAG_TWO_ROW)) ? 0.0 : sv;
+                na_out = cnt_a;
+                fin_out = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
+                item->off = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
+                break;
+            }
+        }
+    }
+    c.nodes[node] = nd;
+    c.resna[w.lpos] = na_out;
+    c.resfin[w.lpos] = (uint16_t)fin_out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small (5..32 rows, one row per lane) and large (> 32 rows) nodes: one WARP per node
+// ---------------------------------------------------------------------------------------------
+template <typename CodeT, typename PosT>
+__device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint32_t* hist, int lane) {
+    const GrowArgs<CodeT, PosT>& a = *c.a;
+    const WorkItem w = *item;
+    const uint32_t n = w.hi - w.lo;
+    PosT* P = c.pos + w.lo;
+    PosT* Pn = (n <= SMALL_MAX) ? P : (c.tmp + w.lo);  // small: in place (rows are in registers)
     const int C = a.n_classes;
     const uint32_t lt = lanemask_lt();
+    const uint32_t node = c.base + w.lpos;
+    const bool small = n <= SMALL_MAX;
 
     // ---- class histogram of the node (np.unique(target_vals), model.py:267-268) ----
     for (int i = lane; i < RFMC_MAX_CLASSES; i += 32) hist[i] = 0;
     __syncwarp();
-    for (uint32_t base = 0; base < n; base += 32) {
-        uint32_t i = base + lane;
-        bool act = i < n;
-        uint32_t l = act ? (uint32_t)c.lab[P[i]] : 0u;
-        hist_add(hist, l, act, lane);
+    uint32_t my_p = 0, my_l = 0xFFFFu;  // small nodes keep their row and label in registers
+    if (small) {
+        const bool act = lane < (int)n;
+        my_p = act ? (uint32_t)P[lane] : 0u;
+        my_l = act ? (uint32_t)c.lab[my_p] : 0xFFFFu;
+        hist_add(hist, my_l, act, lane);
+    } else {
+        for (uint32_t base = 0; base < n; base += 128) {
+            uint32_t l[4];
+            bool act[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * 32 + lane;
+                act[u] = i < n;
+                l[u] = act[u] ? (uint32_t)P[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) l[u] = act[u] ? (uint32_t)c.lab[l[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base + u * 32 >= n) break;
+                hist_add(hist, l[u], act[u], lane);
+            }
+        }
     }
     __syncwarp();
     const uint32_t cls0 = hist[lane];
     const uint32_t cls1 = hist[lane + 32];
     __syncwarp();
     const int present = __popc(__ballot_sync(FULL, cls0 > 0)) + __popc(__ballot_sync(FULL, cls1 > 0));
-    const int depth = level + 1;
-    bool leaf = (depth >= a.max_depth) || (present == 1);
+    const int depth = c.level + 1;
+    const bool leaf = (depth >= a.max_depth) || (present == 1);
 
-    // outputs shared by leaf and split: class counts and the leaf vote (first max, sorted labels)
-    if (lane < C) c.counts[(size_t)w.node * C + lane] = (int32_t)cls0;
-    if (lane + 32 < C) c.counts[(size_t)w.node * C + lane + 32] = (int32_t)cls1;
+    if (lane < C) c.counts[(size_t)node * C + lane] = (int32_t)cls0;
+    if (lane + 32 < C) c.counts[(size_t)node * C + lane + 32] = (int32_t)cls1;
     {
         unsigned long long k0 = ((unsigned long long)cls0 << 8) | (unsigned long long)(255 - lane);
         unsigned long long k1 = ((unsigned long long)cls1 << 8) | (unsigned long long)(255 - (lane + 32));
         if (lane >= C) k0 = 0;
         if (lane + 32 >= C) k1 = 0;
         unsigned long long k = warp_max_u64(k0 > k1 ? k0 : k1);
-        if (lane == 0) c.votes[w.node] = (uint8_t)(255 - (int)(k & 255));
+        if (lane == 0) c.votes[node] = (uint8_t)(255 - (int)(k & 255));
     }
 
     bool accepted = false;
-    uint32_t thr_store = 0, thr_part = 0, na = 0, flags = 0, f_acc = 0, off_next = 0;
-    bool cat_acc = false;
+    uint32_t thr_store = 0, na = 0, flags = 0, f_acc = 0, off_next = 0, fin = NOT_FINAL | (NOT_FINAL << 8);
     double sv_acc = 0.0;
 
     if (!leaf) {
@@ -266,25 +490,13 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
             const uint32_t f = c.flist[fl];
             const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
             const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
-            uint32_t t_store = 0, t_part = 0, cnt_a = 0, fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
+            uint32_t t_store = 0, t_part = 0, cnt_a = 0;
+            const uint32_t fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
 
-            if (n == 2) {  // model.py:258-262
-                uint32_t c0 = col[P[0]], c1 = col[P[1]];
-                t_store = t_part = c0 > c1 ? c0 : c1;
-                fl_flags |= RFMC_FLAG_TWO_ROW;
-                cnt_a = 1;
-                if (a.mss <= 1) {
-                    accepted = true;
-                    if (lane == 0) {
-                        bool second_hi = c0 <= c1;
-                        Pn[0] = second_hi ? P[1] : P[0];
-                        Pn[1] = second_hi ? P[0] : P[1];
-                    }
-                }
-            } else if (n <= 32) {
+            if (small) {
                 const bool act = lane < (int)n;
-                const uint32_t my = act ? (uint32_t)col[P[lane]] : 0xFFFFFFFFu;
+                const uint32_t my = act ? (uint32_t)col[my_p] : 0xFFFFFFFFu;
                 if (cat) {  // mode, ties -> lowest code (model.py:249-250)
                     uint32_t grp = __match_any_sync(FULL, my);
                     unsigned long long key =
@@ -306,16 +518,7 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
                     const uint32_t K = (uint32_t)a.col_nuniq[f];
                     double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                     sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                    if (sv != sv) {
-                        t_store = t_part = 0xFFFFFFFFu;  // every comparison with NaN is False
-                    } else {
-                        uint32_t less;
-                        if (sv == va) less = ca - 1;
-                        else if (sv == vb) less = cb - 1;
-                        else if (va < sv && sv < vb) less = count_less(tab, ca, cb - 1, sv, lane);
-                        else less = count_less(tab, 0, K, sv, lane);
-                        t_store = t_part = less + 1;
-                    }
+                    t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
                 }
                 uint32_t ma = __ballot_sync(FULL, act && (cat ? my == t_part : my >= t_part));
                 cnt_a = __popc(ma);
@@ -329,12 +532,20 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
                 }
                 if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
                     accepted = true;
+                    const uint32_t all = (n == 32) ? FULL : ((1u << n) - 1u);
+                    const uint32_t mb = ~ma & all;
+                    __syncwarp();
                     if (act) {
                         bool go = (ma >> lane) & 1u;
-                        uint32_t mb = ~ma & ((n == 32) ? FULL : ((1u << n) - 1u));
                         uint32_t dst = go ? __popc(ma & lt) : cnt_a + __popc(mb & lt);
-                        Pn[dst] = P[lane];
+                        Pn[dst] = (PosT)my_p;
                     }
+                    // a side whose rows all carry one label is a finished leaf (model.py:268)
+                    const uint32_t la = __shfl_sync(FULL, my_l, __ffs(ma) - 1);
+                    const uint32_t lb = __shfl_sync(FULL, my_l, __ffs(mb) - 1);
+                    const bool pa = __ballot_sync(FULL, ((ma >> lane) & 1u) && my_l == la) == ma;
+                    const bool pb = __ballot_sync(FULL, ((mb >> lane) & 1u) && my_l == lb) == mb;
+                    fin = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
                 }
             } else {
                 const uint32_t K = (uint32_t)a.col_nuniq[f];
@@ -342,11 +553,22 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
                     if (K + 1 <= (uint32_t)HIST_WORDS) {
                         for (uint32_t i = lane; i <= K; i += 32) hist[i] = 0;
                         __syncwarp();
-                        for (uint32_t base = 0; base < n; base += 32) {
-                            uint32_t i = base + lane;
-                            bool act = i < n;
-                            uint32_t cv = act ? (uint32_t)col[P[i]] : 0u;
-                            hist_add(hist, cv, act, lane);
+                        for (uint32_t base = 0; base < n; base += 128) {
+                            uint32_t cv[4];
+                            bool act[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint32_t i = base + u * 32 + lane;
+                                act[u] = i < n;
+                                cv[u] = act[u] ? (uint32_t)P[i] : 0u;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[cv[u]] : 0u;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (base + u * 32 >= n) break;
+                                hist_add(hist, cv[u], act[u], lane);
+                            }
                         }
                         __syncwarp();
                         unsigned long long key = 0;
@@ -378,30 +600,31 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
                 } else {
                     int npass = (K < 0x100u) ? 1 : ((K < 0x10000u) ? 2 : ((K < 0x1000000u) ? 3 : 4));
                     uint32_t ca, cb;
-                    select_two<CodeT>(col, P, n, npass, (n - 1) >> 1, hist, lane, ca, cb);
+                    select_two<CodeT, PosT>(col, P, n, npass, (n - 1) >> 1, hist, lane, ca, cb);
                     const double* tab = a.tables + a.tab_off[f];
                     double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                     sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                    if (sv != sv) {
-                        t_store = t_part = 0xFFFFFFFFu;
-                    } else {
-                        uint32_t less;
-                        if (sv == va) less = ca - 1;
-                        else if (sv == vb) less = cb - 1;
-                        else if (va < sv && sv < vb) less = count_less(tab, ca, cb - 1, sv, lane);
-                        else less = count_less(tab, 0, K, sv, lane);
-                        t_store = t_part = less + 1;
-                    }
+                    t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
                 }
                 // side sizes
                 for (int attempt = 0; attempt < 2; ++attempt) {
                     cnt_a = 0;
-                    for (uint32_t base = 0; base < n; base += 32) {
-                        uint32_t i = base + lane;
-                        bool act = i < n;
-                        uint32_t cv = act ? (uint32_t)col[P[i]] : 0u;
-                        bool go = act && (cat ? cv == t_part : cv >= t_part);
-                        cnt_a += __popc(__ballot_sync(FULL, go));
+                    for (uint32_t base = 0; base < n; base += 128) {
+                        uint32_t cv[4];
+                        bool act[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t i = base + u * 32 + lane;
+                            act[u] = i < n;
+                            cv[u] = act[u] ? (uint32_t)P[i] : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[cv[u]] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool go = act[u] && (cat ? cv[u] == t_part : cv[u] >= t_part);
+                            cnt_a += __popc(__ballot_sync(FULL, go));
+                        }
                     }
                     if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu) break;
                     const double* tab = a.tables + a.tab_off[f];
@@ -416,145 +639,217 @@ __device__ void process_node(const CandCtx<CodeT>& c, WorkItem* cur, uint32_t j,
                     for (uint32_t base = 0; base < n; base += 32) {  // stable partition
                         uint32_t i = base + lane;
                         bool act = i < n;
-                        uint32_t pi = act ? P[i] : 0u;
+                        uint32_t pi = act ? (uint32_t)P[i] : 0u;
                         uint32_t cv = act ? (uint32_t)col[pi] : 0u;
                         bool go = act && (cat ? cv == t_part : cv >= t_part);
                         uint32_t ma = __ballot_sync(FULL, go);
                         uint32_t mb = __ballot_sync(FULL, act && !go);
-                        if (act) Pn[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = pi;
+                        if (act) Pn[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi;
                         oa += __popc(ma);
                         ob += __popc(mb);
                     }
+                    __syncwarp();
+                    for (uint32_t i = lane; i < n; i += 32) P[i] = Pn[i];
                 }
             }
             if (accepted) {
                 thr_store = t_store;
-                thr_part = t_part;
                 na = cnt_a;
                 flags = fl_flags;
                 f_acc = f;
-                cat_acc = cat;
-                sv_acc = (cat || (fl_flags & RFMC_FLAG_TWO_ROW)) ? 0.0 : sv;
+                sv_acc = cat ? 0.0 : sv;
                 off_next = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
                 break;
             }
         }
     }
-    (void)thr_part;
-    (void)cat_acc;
     if (lane == 0) {
         rfmc_node nd;
+        write_leaf(&nd);
         if (accepted) {
             nd.feat = (int32_t)f_acc;
             nd.thr = thr_store;
-            nd.child = -1;  // assigned by the level scan
             nd.flags = flags;
             nd.sval = sv_acc;
-            c.resna[j] = na;
-            cur[j].off = off_next;
-        } else {
-            nd.feat = -1;
-            nd.thr = 0;
-            nd.child = -1;
-            nd.flags = 0;
-            nd.sval = 0.0;
-            c.resna[j] = 0;
+            item->off = off_next;
         }
-        c.nodes[w.node] = nd;
+        c.nodes[node] = nd;
+        c.resna[w.lpos] = accepted ? na : 0u;
+        c.resfin[w.lpos] = (uint16_t)fin;
     }
 }
 
-template <typename CodeT>
-__global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT> a) {
+template <typename CodeT, typename PosT>
+__global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT, PosT> a) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ uint32_t s_hist[GROW_WARPS][HIST_WORDS];
     __shared__ uint32_t s_wtot[GROW_WARPS];
-    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_ticket[3];
+    __shared__ uint32_t s_cnt[2][3];  // items per size class, this level / next level
+    __shared__ uint32_t s_total;
     __shared__ int s_correct;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
+    const int nt = a.n_train;
+    // list regions inside one work buffer: tiny items hold >= 2 rows, small >= 5, large >= 33
+    const uint32_t cap_t = (uint32_t)nt / 2 + 1, cap_s = (uint32_t)nt / 5 + 1, cap_l = (uint32_t)nt / 33 + 1;
+    const uint32_t reg0[3] = {0u, cap_t, cap_t + cap_s};
+    const uint32_t cap_all = cap_t + cap_s + cap_l;
+
+    uint8_t* lab;
+    PosT* pos;
+    if (a.use_smem) {
+        lab = s_dyn;
+        pos = reinterpret_cast<PosT*>(s_dyn + (((size_t)a.nt_pad + 15) / 16) * 16);
+    } else {
+        lab = a.lab_g + (size_t)blockIdx.x * a.nt_pad;
+        pos = a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad;
+    }
+    PosT* tmp = a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad + a.nt_pad;
 
     for (int cand = blockIdx.x; cand < a.n_cand; cand += gridDim.x) {
-        CandCtx<CodeT> c;
+        CandCtx<CodeT, PosT> c;
         c.a = &a;
         c.cc = a.cc + (size_t)blockIdx.x * a.fmax * a.nt_pad;
-        c.lab = a.lab + (size_t)blockIdx.x * a.nt_pad;
-        c.pos = a.pos + (size_t)blockIdx.x * 2 * a.nt_pad;
-        c.resna = a.resna + (size_t)blockIdx.x * a.nt_pad;
+        c.lab = lab;
+        c.pos = pos;
+        c.tmp = tmp;
+        c.resfin = a.resfin + (size_t)blockIdx.x * a.nt_pad;
         c.nodes = a.nodes + (size_t)cand * a.max_nodes;
         c.counts = a.counts + (size_t)cand * a.max_nodes * a.n_classes;
         c.votes = a.votes + (size_t)cand * a.max_nodes;
         const int fo = a.feat_off[cand];
         c.flist = a.feat_list + fo;
         c.nf = a.feat_off[cand + 1] - fo;
-        WorkItem* work = a.work + (size_t)blockIdx.x * 2 * a.nt_pad;
+        WorkItem* work = a.work + (size_t)blockIdx.x * 2 * cap_all;
+        uint32_t* resna = a.resna + (size_t)blockIdx.x * 2 * a.nt_pad;
+        uint32_t* rank = a.rank + (size_t)blockIdx.x * a.nt_pad;
         const int slot = a.cand_slot[cand];
         const int32_t* idxT = a.idx_train + (size_t)slot * a.n_train;
         const int32_t* idxV = a.idx_val + (size_t)slot * a.n_val;
+        const int C = a.n_classes;
 
         // ---- gather the bootstrap rows once: coalesced row read -> compact [feature][row] ----
-        for (int i = warp; i < a.n_train; i += GROW_WARPS) {
+        for (int i = warp; i < nt; i += GROW_WARPS) {
             const int64_t row = idxT[i];
             const CodeT* src = a.codes + row * a.stride;
             for (int fl = lane; fl < c.nf; fl += 32) c.cc[(size_t)fl * a.nt_pad + i] = __ldg(&src[c.flist[fl]]);
             if (lane == 0) {
-                c.lab[i] = __ldg(&a.labels[row]);
-                c.pos[i] = (uint32_t)i;
+                lab[i] = __ldg(&a.labels[row]);
+                pos[i] = (PosT)i;
             }
         }
         if (tid == 0) {
-            work[0] = WorkItem{0u, (uint32_t)a.n_train, 0u, 0u};
+            const int cls = nt <= TINY_MAX ? 0 : (nt <= SMALL_MAX ? 1 : 2);
+            s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = 0;
+            s_cnt[0][cls] = 1;
+            work[reg0[cls]] = WorkItem{0u, (uint32_t)nt, 0u, 0u};
+            resna[0] = 0;
             s_correct = 0;
         }
-        uint32_t count = 1, n_nodes = 1;
+        uint32_t width = 1, base = 0;
         int level = 0;
         __syncthreads();
 
-        while (count > 0) {
-            WorkItem* cur = work + (size_t)(level & 1) * a.nt_pad;
-            WorkItem* nxt = work + (size_t)((level + 1) & 1) * a.nt_pad;
-            if (tid == 0) s_ticket = 0;
+        while (width > 0) {
+            const int cb = level & 1, nb = cb ^ 1;
+            WorkItem* cur = work + (size_t)cb * cap_all;
+            WorkItem* nxt = work + (size_t)nb * cap_all;
+            uint32_t* resna_cur = resna + (size_t)cb * a.nt_pad;
+            uint32_t* resna_nxt = resna + (size_t)nb * a.nt_pad;
+            c.resna = resna_cur;
+            c.base = base;
+            c.level = level;
+            const uint32_t n_tiny = s_cnt[cb][0], n_small = s_cnt[cb][1], n_large = s_cnt[cb][2];
+            if (tid < 3) {
+                s_ticket[tid] = 0;
+                s_cnt[nb][tid] = 0;
+            }
             __syncthreads();
-            // ---- phase 1: one warp per node ----
+            // ---- phase 1: large and small nodes by warps, tiny nodes by threads ----
             while (true) {
                 uint32_t j = 0;
-                if (lane == 0) j = atomicAdd(&s_ticket, 1u);
+                if (lane == 0) j = atomicAdd(&s_ticket[2], 1u);
                 j = __shfl_sync(FULL, j, 0);
-                if (j >= count) break;
-                process_node<CodeT>(c, cur, j, level, s_hist[warp], lane);
+                if (j >= n_large) break;
+                process_warp<CodeT, PosT>(c, cur + reg0[2] + j, s_hist[warp], lane);
+            }
+            while (true) {
+                uint32_t j = 0;
+                if (lane == 0) j = atomicAdd(&s_ticket[1], 1u);
+                j = __shfl_sync(FULL, j, 0);
+                if (j >= n_small) break;
+                process_warp<CodeT, PosT>(c, cur + reg0[1] + j, s_hist[warp], lane);
+            }
+            while (true) {
+                uint32_t j = 0;
+                if (lane == 0) j = atomicAdd(&s_ticket[0], 32u);
+                j = __shfl_sync(FULL, j, 0);
+                if (j >= n_tiny) break;
+                if (j + lane < n_tiny) process_tiny<CodeT, PosT>(c, cur + reg0[0] + j + lane);
             }
             __syncthreads();
-            // ---- phase 2: deterministic child numbering (block-wide scan over split flags) ----
-            uint32_t running = 0;
-            for (uint32_t tile = 0; tile < count; tile += GROW_THREADS) {
-                uint32_t j = tile + tid;
-                uint32_t na = (j < count) ? c.resna[j] : 0u;
-                bool split = na > 0;
-                uint32_t bal = __ballot_sync(FULL, split);
-                if (lane == 0) s_wtot[warp] = __popc(bal);
-                __syncthreads();
-                uint32_t woff = 0, tot = 0;
+            // ---- phase 2a: split rank of every level position (block-wide exclusive scan) ----
+            const uint32_t per = (width + GROW_THREADS - 1) / GROW_THREADS;
+            const uint32_t p0 = (uint32_t)tid * per, p1 = (p0 + per < width) ? p0 + per : width;
+            uint32_t mine = 0;
+            for (uint32_t p = p0; p < p1; ++p) mine += resna_cur[p] > 0;
+            uint32_t inc = mine;
 #pragma unroll
-                for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
-                    uint32_t t = s_wtot[w8];
-                    if (w8 < warp) woff += t;
-                    tot += t;
-                }
-                if (split) {
-                    uint32_t s = running + woff + __popc(bal & lt);
-                    WorkItem w = cur[j];
-                    uint32_t child = n_nodes + 2 * s;
-                    c.nodes[w.node].child = (int32_t)child;
-                    nxt[2 * s] = WorkItem{w.lo, w.lo + na, child, w.off};
-                    nxt[2 * s + 1] = WorkItem{w.lo + na, w.hi, child + 1, w.off};
-                }
-                running += tot;
-                __syncthreads();
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += t;
             }
-            n_nodes += 2 * running;
-            count = 2 * running;
+            if (lane == 31) s_wtot[warp] = inc;
+            __syncthreads();
+            uint32_t woff = 0, splits = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
+                const uint32_t t = s_wtot[w8];
+                if (w8 < warp) woff += t;
+                splits += t;
+            }
+            uint32_t run = woff + inc - mine;
+            for (uint32_t p = p0; p < p1; ++p) {
+                rank[p] = run;
+                run += resna_cur[p] > 0;
+            }
+            __syncthreads();
+            // ---- phase 2b: child ids, finished leaves, next level's work lists ----
+            const uint32_t base_next = base + width;
+            const uint32_t n_items = n_tiny + n_small + n_large;
+            for (uint32_t q = tid; q < n_items; q += GROW_THREADS) {
+                const WorkItem w = q < n_tiny ? cur[reg0[0] + q]
+                                              : (q < n_tiny + n_small ? cur[reg0[1] + q - n_tiny] : cur[reg0[2] + q - n_tiny - n_small]);
+                const uint32_t na = resna_cur[w.lpos];
+                if (na == 0) continue;
+                const uint32_t s = rank[w.lpos];
+                const uint32_t fin = c.resfin[w.lpos];
+                c.nodes[base + w.lpos].child = (int32_t)(base_next + 2 * s);
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const uint32_t lo = side ? w.lo + na : w.lo, hi = side ? w.hi : w.lo + na;
+                    const uint32_t sz = hi - lo, cpos = 2 * s + side, f8 = (fin >> (8 * side)) & 0xFFu;
+                    resna_nxt[cpos] = 0;
+                    if (f8 != NOT_FINAL) {  // finished leaf: all rows of one class
+                        const uint32_t cn = base_next + cpos;
+                        write_leaf(&c.nodes[cn]);
+                        for (int k = 0; k < C; ++k) c.counts[(size_t)cn * C + k] = (k == (int)f8) ? (int32_t)sz : 0;
+                        c.votes[cn] = (uint8_t)f8;
+                    } else {
+                        const int cls = sz <= TINY_MAX ? 0 : (sz <= SMALL_MAX ? 1 : 2);
+                        const uint32_t at = atomicAdd(&s_cnt[nb][cls], 1u);
+                        nxt[reg0[cls] + at] = WorkItem{lo, hi, cpos, w.off};
+                    }
+                }
+            }
+            base = base_next;
+            width = 2 * splits;
             ++level;
+            __syncthreads();
         }
+        const uint32_t n_nodes = base;
 
         // ---- validationTree (model.py:296-314): hold-out rows through the finished tree ----
         int good = 0;
@@ -581,12 +876,19 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT> a) {
         }
         __syncthreads();
     }
+    (void)lt;
 }
 
-template <typename CodeT>
+template <typename CodeT, typename PosT>
+static size_t smem_bytes(int nt_pad) {
+    return (((size_t)nt_pad + 15) / 16) * 16 + (size_t)nt_pad * sizeof(PosT);
+}
+constexpr size_t SMEM_BUDGET = 100 * 1024;  // per CTA, keeps >= 2 CTAs per SM
+
+template <typename CodeT, typename PosT>
 static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     rfmc_dataset* ds = b->ds;
-    GrowArgs<CodeT> a;
+    GrowArgs<CodeT, PosT> a;
     a.codes = (const CodeT*)ds->d_codes;
     a.stride = ds->stride;
     a.labels = ds->d_labels;
@@ -610,40 +912,59 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     a.feat_off = b->d_feat_off;
     a.feat_list = b->d_feat_list;
     a.cc = (CodeT*)b->d_cc;
-    a.lab = b->d_lab;
-    a.pos = b->d_pos;
+    a.lab_g = b->d_lab;
+    a.pos_g = (PosT*)b->d_pos;
     a.work = b->d_work;
     a.resna = b->d_resna;
+    a.rank = b->d_rank;
+    a.resfin = b->d_resfin;
+    const size_t dyn = smem_bytes<CodeT, PosT>(b->nt_pad);
+    a.use_smem = dyn <= SMEM_BUDGET;
     a.nodes = b->d_nodes;
     a.counts = b->d_counts;
     a.votes = b->d_votes;
     a.nnodes = b->d_nnodes;
     a.correct = b->d_correct;
-    grow_kernel<CodeT><<<b->grid, GROW_THREADS, 0, stream>>>(a);
+    auto k = grow_kernel<CodeT, PosT>;
+    const size_t smem = a.use_smem ? dyn : 0;
+    if (smem > 0) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    k<<<b->grid, GROW_THREADS, smem, stream>>>(a);
     RFMC_CUDA(cudaGetLastError());
     b->launches = 1;
     return 0;
 }
 
 int launch_grow(rfmc_batch* b, cudaStream_t stream) {
+    const bool p16 = b->n_train <= 65535;
     switch (b->ds->code_width) {
-        case 1: return launch_grow_t<uint8_t>(b, stream);
-        case 2: return launch_grow_t<uint16_t>(b, stream);
-        case 4: return launch_grow_t<uint32_t>(b, stream);
+        case 1: return p16 ? launch_grow_t<uint8_t, uint16_t>(b, stream) : launch_grow_t<uint8_t, uint32_t>(b, stream);
+        case 2: return p16 ? launch_grow_t<uint16_t, uint16_t>(b, stream) : launch_grow_t<uint16_t, uint32_t>(b, stream);
+        case 4: return p16 ? launch_grow_t<uint32_t, uint16_t>(b, stream) : launch_grow_t<uint32_t, uint32_t>(b, stream);
     }
     set_error("unsupported code width");
     return 1;
 }
 
-int grow_grid_size(const rfmc_dataset* ds, int n_cand) {
+template <typename CodeT, typename PosT>
+static int occupancy_t(int nt_pad) {
     int per_sm = 0;
-    cudaError_t e;
+    const size_t dyn = smem_bytes<CodeT, PosT>(nt_pad);
+    const size_t smem = dyn <= SMEM_BUDGET ? dyn : 0;
+    auto k = grow_kernel<CodeT, PosT>;
+    if (smem > 0) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, GROW_THREADS, smem) != cudaSuccess) per_sm = 1;
+    return per_sm < 1 ? 1 : per_sm;
+}
+
+int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train) {
+    const int nt_pad = (n_train + 15) / 16 * 16;
+    const bool p16 = n_train <= 65535;
+    int per_sm = 1;
     switch (ds->code_width) {
-        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel<uint8_t>, GROW_THREADS, 0); break;
-        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel<uint16_t>, GROW_THREADS, 0); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel<uint32_t>, GROW_THREADS, 0); break;
+        case 1: per_sm = p16 ? occupancy_t<uint8_t, uint16_t>(nt_pad) : occupancy_t<uint8_t, uint32_t>(nt_pad); break;
+        case 2: per_sm = p16 ? occupancy_t<uint16_t, uint16_t>(nt_pad) : occupancy_t<uint16_t, uint32_t>(nt_pad); break;
+        default: per_sm = p16 ? occupancy_t<uint32_t, uint16_t>(nt_pad) : occupancy_t<uint32_t, uint32_t>(nt_pad); break;
     }
-    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     long long g = (long long)ds->sm_count * per_sm;
     if (g > n_cand) g = n_cand;
     if (g < 1) g = 1;
