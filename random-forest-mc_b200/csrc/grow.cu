@@ -731,13 +731,31 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT, PosT
         const int C = a.n_classes;
 
         // ---- gather the bootstrap rows once: coalesced row read -> compact [feature][row] ----
-        for (int i = warp; i < nt; i += GROW_WARPS) {
-            const int64_t row = idxT[i];
+        // One lane per row: the row ids of 32 rows are one coalesced load, each lane then walks
+        // its own 132-byte row (L1-resident after the first touch; the loads of the unrolled
+        // feature loop are independent), and every store is 32 consecutive codes of one feature.
+        for (int i0 = warp * 32; i0 < nt; i0 += GROW_WARPS * 32) {
+            const int i = i0 + lane;
+            const bool act = i < nt;
+            const int64_t row = act ? (int64_t)__ldg(&idxT[i]) : 0;
             const CodeT* src = a.codes + row * a.stride;
-            for (int fl = lane; fl < c.nf; fl += 32) c.cc[(size_t)fl * a.nt_pad + i] = __ldg(&src[c.flist[fl]]);
-            if (lane == 0) {
+            if (act) {
                 lab[i] = __ldg(&a.labels[row]);
                 pos[i] = (PosT)i;
+            }
+            int fl = 0;
+            for (; fl + 8 <= c.nf; fl += 8) {
+                CodeT v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(&src[c.flist[fl + u]]);
+                if (act) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) c.cc[(size_t)(fl + u) * a.nt_pad + i] = v[u];
+                }
+            }
+            for (; fl < c.nf; ++fl) {
+                const CodeT v = __ldg(&src[c.flist[fl]]);
+                if (act) c.cc[(size_t)fl * a.nt_pad + i] = v;
             }
         }
         if (tid == 0) {
@@ -791,29 +809,27 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT, PosT
             }
             __syncthreads();
             // ---- phase 2a: split rank of every level position (block-wide exclusive scan) ----
-            const uint32_t per = (width + GROW_THREADS - 1) / GROW_THREADS;
-            const uint32_t p0 = (uint32_t)tid * per, p1 = (p0 + per < width) ? p0 + per : width;
+            // each warp owns a contiguous range of positions and walks it 32 at a time (coalesced);
+            // pass 1 counts, pass 2 re-reads the flags and writes the exclusive ranks
+            const uint32_t per = ((width + GROW_WARPS * 32 - 1) / (GROW_WARPS * 32)) * 32;
+            const uint32_t p0 = (uint32_t)warp * per, p1 = (p0 + per < width) ? p0 + per : width;
             uint32_t mine = 0;
-            for (uint32_t p = p0; p < p1; ++p) mine += resna_cur[p] > 0;
-            uint32_t inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_up_sync(FULL, inc, d);
-                if (lane >= d) inc += t;
-            }
-            if (lane == 31) s_wtot[warp] = inc;
+            for (uint32_t p = p0; p < p1; p += 32)
+                mine += __popc(__ballot_sync(FULL, (p + lane < p1) && resna_cur[p + lane] > 0));
+            if (lane == 0) s_wtot[warp] = mine;
             __syncthreads();
-            uint32_t woff = 0, splits = 0;
+            uint32_t run = 0, splits = 0;
 #pragma unroll
             for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
                 const uint32_t t = s_wtot[w8];
-                if (w8 < warp) woff += t;
+                if (w8 < warp) run += t;
                 splits += t;
             }
-            uint32_t run = woff + inc - mine;
-            for (uint32_t p = p0; p < p1; ++p) {
-                rank[p] = run;
-                run += resna_cur[p] > 0;
+            for (uint32_t p = p0; p < p1; p += 32) {
+                const bool in = p + lane < p1;
+                const uint32_t bal = __ballot_sync(FULL, in && resna_cur[p + lane] > 0);
+                if (in) rank[p + lane] = run + __popc(bal & lt);
+                run += __popc(bal);
             }
             __syncthreads();
             // ---- phase 2b: child ids, finished leaves, next level's work lists ----
