@@ -1,0 +1,79 @@
+"""Turn the ncu artefacts of profiles/prof_final.sh (read from gpurun_out/) into the tracked
+summary files: profiles/<tag>_launches.csv, profiles/<tag>_ncu_summary.md, profiles/ncu_traffic.json."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum",
+]
+
+
+def raw(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    return {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+
+
+def num(x):
+    return float(x.replace(",", ""))
+
+
+def to_bytes(val, unit):
+    return num(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+lines = [f"# ncu summary ({tag})", "", "Commands: `profiles/prof_final.sh` (default bench configuration, `--clock-control none`).", ""]
+src = os.path.join(OUT, "launchesF.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(list)
+    for r in rows[1:]:
+        try:
+            agg[r[ki][:70]].append(float(r[vi].replace(",", "")))
+        except ValueError:
+            pass
+    tot = sum(sum(v) for v in agg.values())
+    with open(os.path.join(ROOT, "profiles", f"{tag}_launches.csv"), "w") as f:
+        f.write(open(src).read())
+    lines += ["## Launch list (gpu__time_duration.sum; cold-cache, serialised: shares only)", "", "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {sum(v)/tot*100:.1f}% |")
+    lines.append("")
+traffic = {}
+for rep, name in (("prof_growF", "grow_kernel"), ("prof_predictF", "predict_kernel")):
+    path = os.path.join(OUT, rep + ".ncu-rep")
+    if not os.path.exists(path):
+        continue
+    d = raw(path)
+    lines += [f"## `rfmc::{name}` (one launch, `--set full`)", "", "| metric | value |", "|---|---|"]
+    for k in KEYS:
+        if k in d:
+            lines.append(f"| {k} | {d[k][0]} {d[k][1]} |")
+    lines.append("")
+    traffic[name] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
+    f.write("\n".join(lines) + "\n")
+with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
+    json.dump(traffic, f)
+print("\n".join(lines))
