@@ -127,6 +127,32 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
                         int32_t n_features, const uint8_t* absent, int soft, int weighted, double* probs_out,
                         int32_t* labels_out, int on_device, void* stream);
 
+/* ---- voting straight from a raw frame: the encode of predict-time values fused in front ---------
+ * rfmc_forest_set_codebook: per feature the sorted distinct numeric split values of the forest
+ * (thr_off [n_features+1] into thresholds); code(x) = #{t <= x}, NaN -> 0, so that the test
+ * `x >= split_val` of tree.py:177-180 becomes `code >= k+1`.
+ * rfmc_forest_predict_frame: n_cols host columns of n_rows elements each; col_feat[c] = feature
+ * index it feeds, col_dtype[c] = RFMC_DT_* (RFMC_DT_CODE: int32 codes already final, used for
+ * categorical columns whose values the host mapped to ids).  Columns are staged through pinned
+ * memory chunk by chunk, encoded on the GPU into the row-major code tile and voted; the frame is
+ * never materialised as a code matrix on the host. */
+#define RFMC_DT_F64 0
+#define RFMC_DT_F32 1
+#define RFMC_DT_I64 2
+#define RFMC_DT_I32 3
+#define RFMC_DT_I16 4
+#define RFMC_DT_I8 5
+#define RFMC_DT_U8 6
+#define RFMC_DT_U16 7
+#define RFMC_DT_U32 8
+#define RFMC_DT_U64 9
+#define RFMC_DT_CODE 10
+int rfmc_forest_set_codebook(rfmc_forest* f, int32_t n_features, const int64_t* thr_off, const double* thresholds);
+int rfmc_forest_predict_frame(rfmc_forest* f, int64_t n_rows, int32_t n_features, int64_t row_stride, int code_width,
+                              int32_t n_cols, const void* const* col_ptr, const int32_t* col_feat,
+                              const int32_t* col_dtype, const uint8_t* absent, int soft, int weighted,
+                              double* probs_out, int32_t* labels_out);
+
 /* Per-(row, tree) leaf export for DecisionTreeMC.__call__ (tree.py:112-113) and per-tree votes
  * (sampleClass2trees, model.py:406-407): leaves_out [n_rows][n_trees] = payload index, bit 31
  * set when the walk crossed an absent column.  Host buffers, synchronous. */

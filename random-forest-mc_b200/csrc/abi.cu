@@ -124,7 +124,9 @@ struct PredictPipe {
     double* d_probs[2] = {nullptr, nullptr};
     int32_t* pin_labels[2] = {nullptr, nullptr};
     int32_t* d_labels[2] = {nullptr, nullptr};
-    size_t cap_in = 0, cap_probs = 0, cap_labels = 0;
+    uint8_t* pin_raw[2] = {nullptr, nullptr};
+    uint8_t* d_raw[2] = {nullptr, nullptr};
+    size_t cap_in = 0, cap_probs = 0, cap_labels = 0, cap_raw = 0;
     long launches = 0;
 };
 
@@ -163,9 +165,24 @@ static int pipe_reserve(PredictPipe* p, size_t in_bytes, size_t probs_bytes, siz
     return 0;
 }
 
+static int pipe_reserve_raw(PredictPipe* p, size_t raw_bytes) {
+    if (raw_bytes > p->cap_raw) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->pin_raw[i]) cudaFreeHost(p->pin_raw[i]);
+            release(p->d_raw[i]);
+            RFMC_CUDA(cudaHostAlloc((void**)&p->pin_raw[i], raw_bytes, cudaHostAllocDefault));
+            RFMC_CUDA(cudaMalloc((void**)&p->d_raw[i], raw_bytes));
+        }
+        p->cap_raw = raw_bytes;
+    }
+    return 0;
+}
+
 static void pipe_destroy(PredictPipe* p) {
     if (!p) return;
     for (int i = 0; i < 2; ++i) {
+        if (p->pin_raw[i]) cudaFreeHost(p->pin_raw[i]);
+        release(p->d_raw[i]);
         if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
         if (p->pin_probs[i]) cudaFreeHost(p->pin_probs[i]);
         if (p->pin_labels[i]) cudaFreeHost(p->pin_labels[i]);
@@ -474,6 +491,8 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     release(f->d_probs_absent);
     release(f->d_scores);
     pipe_destroy(f->pipe);
+    release(f->d_thresholds);
+    release(f->d_thr_off);
     delete f;
     return 0;
 }
@@ -561,6 +580,135 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
         set_error("predict failed");
     }
     release(d_absent);
+    return rc;
+}
+
+int rfmc_forest_set_codebook(rfmc_forest* f, int32_t n_features, const int64_t* thr_off, const double* thresholds) {
+    RFMC_REQUIRE(f != nullptr && thr_off != nullptr, "forest or offsets are NULL");
+    RFMC_REQUIRE(n_features > 0, "bad feature count");
+    RFMC_CUDA(cudaSetDevice(f->device));
+    release(f->d_thresholds);
+    release(f->d_thr_off);
+    f->d_thresholds = nullptr;
+    f->d_thr_off = nullptr;
+    int rc = 0;
+    const size_t nt = (size_t)thr_off[n_features];
+    rc |= upload(&f->d_thr_off, thr_off, (size_t)n_features + 1, 0);
+    if (nt)
+        rc |= upload(&f->d_thresholds, thresholds, nt, 0);
+    else
+        rc |= reserve(&f->d_thresholds, 1);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("codebook upload failed");
+        rc = 1;
+    }
+    f->n_features_book = n_features;
+    return rc;
+}
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case RFMC_DT_F64: case RFMC_DT_I64: case RFMC_DT_U64: return 8;
+        case RFMC_DT_F32: case RFMC_DT_I32: case RFMC_DT_U32: case RFMC_DT_CODE: return 4;
+        case RFMC_DT_I16: case RFMC_DT_U16: return 2;
+        case RFMC_DT_I8: case RFMC_DT_U8: return 1;
+    }
+    return 0;
+}
+
+int rfmc_forest_predict_frame(rfmc_forest* f, int64_t n_rows, int32_t n_features, int64_t row_stride, int code_width,
+                              int32_t n_cols, const void* const* col_ptr, const int32_t* col_feat,
+                              const int32_t* col_dtype, const uint8_t* absent, int soft, int weighted,
+                              double* probs_out, int32_t* labels_out) {
+    RFMC_REQUIRE(f != nullptr, "forest is NULL");
+    RFMC_REQUIRE(f->d_thr_off != nullptr && f->n_features_book == n_features, "no code book set for this forest");
+    RFMC_REQUIRE(code_width == 1 || code_width == 2 || code_width == 4, "code_width must be 1, 2 or 4");
+    RFMC_REQUIRE(n_rows >= 0 && n_features > 0 && row_stride >= n_features && n_cols >= 0, "bad frame shape");
+    RFMC_REQUIRE((row_stride * code_width) % 4 == 0, "row pitch must be a multiple of 4 bytes");
+    if (n_rows == 0) return 0;
+    RFMC_CUDA(cudaSetDevice(f->device));
+    const int64_t chunk_rows = 32768;
+    std::vector<int64_t> col_off((size_t)n_cols > 0 ? n_cols : 1, 0);
+    size_t raw_bytes = 0;
+    for (int c = 0; c < n_cols; ++c) {
+        const size_t es = dtype_size(col_dtype[c]);
+        RFMC_REQUIRE(es != 0, "unknown column dtype");
+        RFMC_REQUIRE(col_feat[c] >= 0 && col_feat[c] < n_features, "column feature index out of range");
+        col_off[c] = (int64_t)raw_bytes;
+        raw_bytes += ((size_t)chunk_rows * es + 15) / 16 * 16;
+    }
+    if (raw_bytes == 0) raw_bytes = 16;
+    bool has_absent = false;
+    if (absent)
+        for (int i = 0; i < n_features; ++i) has_absent |= absent[i] != 0;
+    const size_t C = (size_t)f->n_classes;
+    const size_t row_bytes = (size_t)row_stride * code_width;
+    PredictPipe* pp = f->pipe;
+    if (!pp) pp = f->pipe = new PredictPipe();
+    if (pipe_reserve(pp, chunk_rows * row_bytes, probs_out ? chunk_rows * C * sizeof(double) : 0,
+                     labels_out ? chunk_rows * sizeof(int32_t) : 0) ||
+        pipe_reserve_raw(pp, raw_bytes))
+        return 1;
+    uint8_t* d_absent = nullptr;
+    int64_t* d_col_off = nullptr;
+    int32_t* d_col_feat = nullptr;
+    int32_t* d_col_dtype = nullptr;
+    int rc = 0;
+    if (has_absent) rc |= upload(&d_absent, absent, (size_t)n_features, 0);
+    rc |= upload(&d_col_off, col_off.data(), col_off.size(), 0);
+    if (n_cols) {
+        rc |= upload(&d_col_feat, col_feat, (size_t)n_cols, 0);
+        rc |= upload(&d_col_dtype, col_dtype, (size_t)n_cols, 0);
+    }
+    cudaStreamSynchronize(0);
+    const int64_t n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
+    auto drain = [&](int64_t c) {
+        const int sl = (int)(c & 1);
+        const int64_t r0 = c * chunk_rows, nr = (n_rows - r0) < chunk_rows ? (n_rows - r0) : chunk_rows;
+        if (cudaEventSynchronize(pp->done[sl]) != cudaSuccess) rc = 1;
+        if (probs_out) memcpy(probs_out + r0 * C, pp->pin_probs[sl], (size_t)nr * C * sizeof(double));
+        if (labels_out) memcpy(labels_out + r0, pp->pin_labels[sl], (size_t)nr * sizeof(int32_t));
+    };
+    for (int64_t c = 0; c < n_chunks && !rc; ++c) {
+        const int sl = (int)(c & 1);
+        if (c >= 2) drain(c - 2);
+        const int64_t r0 = c * chunk_rows, nr = (n_rows - r0) < chunk_rows ? (n_rows - r0) : chunk_rows;
+        for (int k = 0; k < n_cols; ++k) {
+            const size_t es = dtype_size(col_dtype[k]);
+            memcpy(pp->pin_raw[sl] + col_off[k], (const uint8_t*)col_ptr[k] + (size_t)r0 * es, (size_t)nr * es);
+        }
+        cudaStream_t cs = pp->st[sl];
+        if (cudaMemcpyAsync(pp->d_raw[sl], pp->pin_raw[sl], raw_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = 1;
+        if (!rc)
+            rc = launch_encode(pp->d_raw[sl], d_col_off, d_col_feat, d_col_dtype, n_cols, nr, row_stride, code_width,
+                               f->d_thresholds, f->d_thr_off, pp->d_in[sl], cs);
+        if (!rc)
+            rc = launch_predict(f, pp->d_in[sl], code_width, nr, row_stride, n_features, d_absent, has_absent, soft, weighted,
+                                probs_out ? pp->d_probs[sl] : nullptr, labels_out ? pp->d_labels[sl] : nullptr, cs);
+        if (!rc && probs_out &&
+            cudaMemcpyAsync(pp->pin_probs[sl], pp->d_probs[sl], (size_t)nr * C * sizeof(double), cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = 1;
+        if (!rc && labels_out &&
+            cudaMemcpyAsync(pp->pin_labels[sl], pp->d_labels[sl], (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = 1;
+        if (!rc && cudaEventRecord(pp->done[sl], cs) != cudaSuccess) rc = 1;
+        pp->launches += 2;
+    }
+    if (!rc) {
+        if (n_chunks >= 2) drain(n_chunks - 2);
+        drain(n_chunks - 1);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(pp->st[0]), e1 = cudaStreamSynchronize(pp->st[1]);
+    if (e0 != cudaSuccess || e1 != cudaSuccess) {
+        set_error(std::string("predict_frame failed: ") + cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+        rc = 1;
+    } else if (rc && g_error.empty()) {
+        set_error("predict_frame failed");
+    }
+    release(d_absent);
+    release(d_col_off);
+    release(d_col_feat);
+    release(d_col_dtype);
     return rc;
 }
 

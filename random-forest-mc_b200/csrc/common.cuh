@@ -102,6 +102,9 @@ struct rfmc_forest {
     double* d_scores = nullptr;
     int sm_count = 0;
     PredictPipe* pipe = nullptr;  // pinned staging + streams of the host-buffer voting path
+    double* d_thresholds = nullptr;  // code book of the frame encoder (rfmc_forest_set_codebook)
+    int64_t* d_thr_off = nullptr;
+    int32_t n_features_book = 0;
 };
 
 namespace rfmc {
@@ -114,4 +117,7 @@ int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t 
                    int32_t* d_labels, cudaStream_t stream);
 int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,
                   int32_t n_features, const uint8_t* d_absent, int32_t* d_out, cudaStream_t stream);
+int launch_encode(const void* d_raw, const int64_t* d_col_off, const int32_t* d_col_feat, const int32_t* d_col_dtype,
+                  int32_t n_cols, int64_t n_rows, int64_t row_stride, int code_width, const double* d_thresholds,
+                  const int64_t* d_thr_off, void* d_codes, cudaStream_t stream);
 }  // namespace rfmc

@@ -302,4 +302,124 @@ int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t 
     return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame encoding: raw column values -> the forest's code space (flat.encode_frame on the GPU).
+// The comparisons of tree.py:177-180 only need code(x) = #{split values t of that feature with
+// t <= x} (numeric; NaN -> 0) or the id of the category (categorical, mapped on the host).  One
+// thread per row walks the frame's columns (each column read is coalesced across the CTA's rows),
+// fills its row of a shared-memory tile and the tile leaves as whole coalesced rows.  This is the
+// one HBM-streaming kernel of the path: 8 bytes in, 2 bytes out per numeric cell.
+// ---------------------------------------------------------------------------------------------
+struct EncodeArgs {
+    const uint8_t* raw;        // staged chunk: column c starts at raw + col_off[c], chunk_rows elements
+    const int64_t* col_off;    // [n_cols]
+    const int32_t* col_feat;   // [n_cols] destination feature index
+    const int32_t* col_dtype;  // [n_cols] RFMC_DT_*
+    int32_t n_cols;
+    int64_t n_rows;            // rows in this chunk
+    int64_t stride;            // elements per output row
+    const double* thresholds;  // concatenated per-feature sorted split values
+    const int64_t* thr_off;    // [n_features+1]
+    void* codes;               // [n_rows][stride]
+};
+
+__device__ __forceinline__ double load_as_double(const uint8_t* p, int dtype, int64_t i) {
+    switch (dtype) {
+        case RFMC_DT_F64: return reinterpret_cast<const double*>(p)[i];
+        case RFMC_DT_F32: return (double)reinterpret_cast<const float*>(p)[i];
+        case RFMC_DT_I64: return (double)reinterpret_cast<const long long*>(p)[i];
+        case RFMC_DT_I32: return (double)reinterpret_cast<const int*>(p)[i];
+        case RFMC_DT_I16: return (double)reinterpret_cast<const short*>(p)[i];
+        case RFMC_DT_I8: return (double)reinterpret_cast<const signed char*>(p)[i];
+        case RFMC_DT_U8: return (double)p[i];
+        case RFMC_DT_U16: return (double)reinterpret_cast<const unsigned short*>(p)[i];
+        case RFMC_DT_U32: return (double)reinterpret_cast<const unsigned int*>(p)[i];
+        case RFMC_DT_U64: return (double)reinterpret_cast<const unsigned long long*>(p)[i];
+    }
+    return 0.0;
+}
+
+template <typename CodeT>
+__global__ void __launch_bounds__(PRED_THREADS) encode_kernel(EncodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * PRED_THREADS;
+    const int rows = (int)((a.n_rows - row0) < PRED_THREADS ? (a.n_rows - row0) : PRED_THREADS);
+    const int words = (int)((size_t)PRED_THREADS * a.stride * sizeof(CodeT) / 4);
+    for (int i = tid; i < words; i += PRED_THREADS) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+    __syncthreads();
+    if (tid < rows) {
+        CodeT* myrow = tile + (size_t)tid * a.stride;
+        const int64_t r = row0 + tid;
+        for (int c = 0; c < a.n_cols; ++c) {
+            const int dt = a.col_dtype[c];
+            const int f = a.col_feat[c];
+            const uint8_t* base = a.raw + a.col_off[c];
+            uint32_t code;
+            if (dt == RFMC_DT_CODE) {
+                code = (uint32_t)reinterpret_cast<const int*>(base)[r];
+            } else {
+                const double x = load_as_double(base, dt, r);
+                const double* t = a.thresholds + a.thr_off[f];
+                uint32_t lo = 0, hi = (uint32_t)(a.thr_off[f + 1] - a.thr_off[f]);
+                if (x != x) hi = 0;  // NaN fails every comparison -> code 0
+                while (hi > lo) {  // upper_bound: number of split values <= x
+                    const uint32_t mid = lo + ((hi - lo) >> 1);
+                    if (__ldg(&t[mid]) <= x)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                code = lo;
+            }
+            myrow[f] = (CodeT)code;
+        }
+    }
+    __syncthreads();
+    const int out_words = (int)((size_t)rows * a.stride * sizeof(CodeT) / 4);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<CodeT*>(a.codes) + row0 * a.stride);
+    for (int i = tid; i < out_words; i += PRED_THREADS) dst[i] = reinterpret_cast<const uint32_t*>(tile)[i];
+}
+
+int launch_encode(const void* d_raw, const int64_t* d_col_off, const int32_t* d_col_feat, const int32_t* d_col_dtype,
+                  int32_t n_cols, int64_t n_rows, int64_t row_stride, int code_width, const double* d_thresholds,
+                  const int64_t* d_thr_off, void* d_codes, cudaStream_t stream) {
+    EncodeArgs a;
+    a.raw = (const uint8_t*)d_raw;
+    a.col_off = d_col_off;
+    a.col_feat = d_col_feat;
+    a.col_dtype = d_col_dtype;
+    a.n_cols = n_cols;
+    a.n_rows = n_rows;
+    a.stride = row_stride;
+    a.thresholds = d_thresholds;
+    a.thr_off = d_thr_off;
+    a.codes = d_codes;
+    const unsigned blocks = (unsigned)((n_rows + PRED_THREADS - 1) / PRED_THREADS);
+    if (blocks == 0) return 0;
+    const size_t smem = (size_t)PRED_THREADS * row_stride * code_width;
+    if (smem > 200 * 1024) {
+        set_error("frame encode: too many feature columns for the shared-memory tile");
+        return 1;
+    }
+    switch (code_width) {
+        case 1:
+            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            encode_kernel<uint8_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            break;
+        case 2:
+            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            encode_kernel<uint16_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            break;
+        case 4:
+            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            encode_kernel<uint32_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            break;
+        default: set_error("unsupported code width"); return 1;
+    }
+    RFMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace rfmc

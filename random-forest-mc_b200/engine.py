@@ -52,6 +52,9 @@ _SIGNATURES = {
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
     "rfmc_forest_leaves": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p]),
     "rfmc_legacy_permutation_prefix": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, _p]),
+    "rfmc_forest_set_codebook": (C.c_int, [_p, C.c_int32, _p, _p]),
+    "rfmc_forest_predict_frame": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, C.c_int, C.c_int32, _p, _p, _p, _p,
+                                            C.c_int, C.c_int, _p, _p]),
     "rfmc_legacy_draw_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p, C.c_int64, C.c_int64,
                                         C.c_int32, C.c_int64, C.c_int64, _p, _p, _p, _p, _p, C.c_int32]),
 }
@@ -294,6 +297,69 @@ class DeviceForest:
             )
         )
         self._h = h
+        nf = tables.n_features
+        books = [t if t is not None else np.zeros(0) for t in tables.thresholds]
+        off = np.zeros(nf + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in books])
+        flat = np.ascontiguousarray(np.concatenate(books) if books else np.zeros(0), dtype=np.float64)
+        if len(flat) == 0:
+            flat = np.zeros(1, dtype=np.float64)
+        _check(load_library().rfmc_forest_set_codebook(self._h, nf, _ptr(off), _ptr(flat)))
+
+    _DT = {"float64": 0, "float32": 1, "int64": 2, "int32": 3, "int16": 4, "int8": 5, "uint8": 6, "uint16": 7,
+           "uint32": 8, "uint64": 9}
+
+    def predict_frame(self, frame, soft: bool, weighted: bool, want_probs: bool = True, want_labels: bool = True):
+        """Vote a raw pandas frame: numeric columns go to the GPU as they are and are encoded there
+        against the forest's split values; categorical columns are mapped to ids on the host.
+        Mirrors flat.encode_frame + predict (tree.py:166-181 semantics for absent / NaN cells)."""
+        import pandas as pd
+
+        t = self.tables
+        n = len(frame)
+        absent = np.zeros(t.n_features, dtype=np.uint8)
+        have = set(frame.columns)
+        keep, ptrs, feats, dts = [], [], [], []
+        for j, name in enumerate(t.feature_cols):
+            thr, cats = t.thresholds[j], t.categories[j]
+            if thr is None and cats is None:
+                continue
+            if name not in have:
+                absent[j] = 1
+                continue
+            col = frame[name]
+            if thr is not None:
+                arr = col.to_numpy()
+                if arr.dtype.name not in self._DT:
+                    arr = pd.to_numeric(col, errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+                arr = np.ascontiguousarray(arr)
+                dts.append(self._DT[arr.dtype.name])
+            else:
+                ids, uniques = pd.factorize(col.to_numpy(), use_na_sentinel=True)
+                lut = np.zeros(len(uniques) + 1, dtype=np.int32)
+                for k, u in enumerate(uniques):
+                    try:
+                        lut[k] = cats.get(u, 0)
+                    except TypeError:
+                        lut[k] = 0
+                arr = np.ascontiguousarray(lut[ids], dtype=np.int32)
+                dts.append(10)
+            keep.append(arr)
+            ptrs.append(arr.ctypes.data)
+            feats.append(j)
+        probs = np.empty((n, self.n_classes), dtype=np.float64) if want_probs else None
+        labels = np.empty(n, dtype=np.int32) if want_labels else None
+        ncol = len(keep)
+        ptr_arr = (C.c_void_p * max(ncol, 1))(*ptrs)
+        feat_arr = np.asarray(feats if feats else [0], dtype=np.int32)
+        dt_arr = np.asarray(dts if dts else [0], dtype=np.int32)
+        _check(
+            load_library().rfmc_forest_predict_frame(
+                self._h, n, t.n_features, t.stride, t.width, ncol, C.cast(ptr_arr, _p), _ptr(feat_arr), _ptr(dt_arr),
+                _ptr(absent), int(bool(soft)), int(bool(weighted)), _ptr(probs), _ptr(labels),
+            )
+        )
+        return probs, labels
 
     def predict(self, codes: np.ndarray, absent: Optional[np.ndarray], soft: bool, weighted: bool,
                 want_probs: bool = True, want_labels: bool = True, stream=None):

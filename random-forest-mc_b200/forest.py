@@ -190,8 +190,7 @@ class BaseRandomForestMC(UserList):
 
     def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool):
         dev = self._device_forest()
-        codes, absent = encode_frame(self._forest_tables, frame)
-        return dev.predict(codes, absent, self.soft_voting, self.weighted_tree, want_probs, want_labels)
+        return dev.predict_frame(frame, self.soft_voting, self.weighted_tree, want_probs, want_labels)
 
     # -- inference API (forest.py:100-112, 204-274) ----------------------------------------------
     def useForest(self, row) -> dict:

@@ -66,6 +66,12 @@ class FakeForest:
         p, l = cm.vote_tables(self.tables, codes, absent, soft, weighted)
         return (p if want_probs else None), (l if want_labels else None)
 
+    def predict_frame(self, frame, soft, weighted, want_probs=True, want_labels=True):
+        from random_forest_mc_b200.flat import encode_frame
+
+        codes, absent = encode_frame(self.tables, frame)
+        return self.predict(codes, absent, soft, weighted, want_probs, want_labels)
+
     def leaves(self, codes, absent, stream=None):
         t = self.tables
         LEAF, CAT = 0x80000000, 0x40000000
