@@ -173,7 +173,8 @@ int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos, int64_t n, int64
  * min(per_class, n_train_pclass)] (class-major, draw order), idx_val [n_slots][the rest],
  * feat_counts [n_slots][n_cands]; key_snap [n_slots][624] / pos_snap [n_slots] = the stream state
  * BEFORE each slot (for the exact rewind of a mis-speculated plan; NULL to skip).  The permutation
- * resolves run on n_threads worker threads while the calling thread walks the stream. */
+ * resolves run on (n_threads & 0xFF) worker threads while the calling thread walks the stream;
+ * n_threads | 0x100 additionally generates the MT19937 blocks on a producer thread. */
 int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos, int32_t n_slots, int32_t n_classes, const int64_t* class_rows,
                           const int64_t* class_off, int64_t per_class, int64_t n_train_pclass, int32_t n_cands,
                           int64_t randint_low, int64_t randint_high, int32_t* idx_train, int32_t* idx_val,

@@ -38,7 +38,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
+#include <memory>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -86,18 +88,75 @@ RFMC_CLONES void mt_temper(const uint32_t* k, uint32_t* out) {
     }
 }
 
+// A ring of MT19937 blocks filled by a producer thread: block b+1 = regen(block b), tempered.  The
+// stream itself does not depend on how it is consumed, so generation runs ahead of the rejection
+// walk; the consumer's end state is simply (untempered key of its current block, position).
+struct BlockRing {
+    static constexpr int K = 64;
+    uint32_t key[K][MT_N];
+    uint32_t tw[K][MT_N];
+    std::atomic<int64_t> produced{1};  // blocks 0 .. produced-1 are ready
+    std::atomic<int64_t> current{0};   // block the consumer is reading
+    std::atomic<bool> stop{false};
+    std::thread worker;
+    void start(const uint32_t* key0) {
+        memcpy(key[0], key0, sizeof(key[0]));
+        mt_temper(key[0], tw[0]);
+        worker = std::thread([this] {
+            for (int64_t b = 1; !stop.load(std::memory_order_relaxed); ++b) {
+                while (b - current.load(std::memory_order_acquire) >= K) {
+                    if (stop.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                uint32_t* k = key[b % K];
+                memcpy(k, key[(b - 1) % K], sizeof(key[0]));
+                mt_regen(k);
+                mt_temper(k, tw[b % K]);
+                produced.store(b + 1, std::memory_order_release);
+            }
+        });
+    }
+    void finish() {
+        stop.store(true);
+        if (worker.joinable()) worker.join();
+    }
+};
+
 struct Stream {  // numpy's MT19937 state + the tempered copy of the current block
     uint32_t* key;
+    const uint32_t* tw;
     int pos;
-    uint32_t tw[MT_N];
+    BlockRing* ring = nullptr;
+    int64_t block = 0;
+    uint32_t own_tw[MT_N];
     void attach(uint32_t* k, int p) {
         key = k;
         pos = p;
-        if (pos < MT_N) mt_temper(key, tw);
+        tw = own_tw;
+        if (pos < MT_N) mt_temper(key, own_tw);
+    }
+    void attach_ring(BlockRing* r, int p) {
+        ring = r;
+        block = 0;
+        key = r->key[0];
+        tw = r->tw[0];
+        pos = p;
     }
     void refill() {
-        mt_regen(key);
-        mt_temper(key, tw);
+        if (ring) {
+            ++block;
+            ring->current.store(block, std::memory_order_release);
+            while (ring->produced.load(std::memory_order_acquire) <= block) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            key = ring->key[block % BlockRing::K];
+            tw = ring->tw[block % BlockRing::K];
+        } else {
+            mt_regen(key);
+            mt_temper(key, own_tw);
+        }
         pos = 0;
     }
     uint32_t next() {
@@ -406,7 +465,8 @@ extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_s
     const uint64_t rng = (uint64_t)(randint_high - 1 - randint_low);
     if (rng > 0xFFFFFFFEull) return 1;
     const uint32_t rmask = all_ones_at_least((uint32_t)rng);
-    if (n_threads < 0) n_threads = 0;
+    const bool use_ring = n_threads >= 0x100;  // bit 8: MT19937 blocks from a producer thread
+    n_threads &= 0xFF;
     if (n_threads > 32) n_threads = 32;
 
     Pool pool;
@@ -419,9 +479,16 @@ extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_s
     for (int t = 0; t < n_threads; ++t) workers.emplace_back([&pool] { pool.worker(); });
 
     Stream st;
-    st.attach(key, *pos_io);
+    std::unique_ptr<BlockRing> ring;
+    if (use_ring) {  // MT19937 blocks are generated ahead of the walk by a producer thread
+        ring.reset(new BlockRing());
+        ring->start(key);
+        st.attach_ring(ring.get(), *pos_io);
+    } else {
+        st.attach(key, *pos_io);
+    }
     for (int32_t s = 0; s < n_slots; ++s) {
-        if (key_snap) memcpy(key_snap + (size_t)s * MT_N, key, MT_N * sizeof(uint32_t));
+        if (key_snap) memcpy(key_snap + (size_t)s * MT_N, st.key, MT_N * sizeof(uint32_t));
         if (pos_snap) pos_snap[s] = st.pos;
         for (int c = 0; c < n_classes; ++c) {
             Task t;
@@ -466,6 +533,10 @@ extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_s
     }
     pool.cv_task.notify_all();
     for (auto& w : workers) w.join();
+    if (ring) {
+        ring->finish();
+        memcpy(key, st.key, MT_N * sizeof(uint32_t));
+    }
     *pos_io = st.pos;
     return 0;
 }

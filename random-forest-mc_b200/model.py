@@ -144,6 +144,7 @@ class RandomForestMC(BaseRandomForestMC):
         self.max_candidates_per_launch = 4096
         self.max_batch_bytes = 24 << 30
         self.rng_threads = max(0, min(6, (os.cpu_count() or 1) - 1))
+        self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"  # MT19937 blocks from a producer thread
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -228,7 +229,7 @@ class RandomForestMC(BaseRandomForestMC):
         key = st[1].copy()
         T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
             key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,
-            int(self.min_feature), int(self.max_feature) + 1, self.rng_threads,
+            int(self.min_feature), int(self.max_feature) + 1, self.rng_threads | (0x100 if self.rng_producer else 0),
         )
         np.random.set_state((st[0], key, pos, st[3], st[4]))
         cols = self.feature_cols

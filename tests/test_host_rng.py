@@ -38,7 +38,7 @@ def test_stream_continues_exactly():
         assert np.array_equal(g, w)
 
 
-@pytest.mark.parametrize("threads", [0, 3])
+@pytest.mark.parametrize("threads", [0, 3, 0x103])
 @pytest.mark.parametrize("per_class,n_train,lo,hi", [(20, 10, 2, 65), (7, 10, 2, 3), (300, 250, 3, 9), (5, 5, 4, 5)])
 def test_draw_plan_matches_numpy_call_sequence(threads, per_class, n_train, lo, hi):
     """choice x classes then randint x candidates per slot, exactly numpy's values and end state."""
