@@ -58,7 +58,7 @@ constexpr int MT_N = 624, MT_M = 397;
 constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER_MASK = 0x80000000u, LOWER_MASK = 0x7fffffffu;
 
 #if defined(__x86_64__) && defined(__GNUC__)
-#define RFMC_CLONES __attribute__((target_clones("avx2", "default")))
+#define RFMC_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
 #else
 #define RFMC_CLONES
 #endif
@@ -272,6 +272,44 @@ __attribute__((target("avx2"))) void reject_avx2(Stream& st, uint32_t mask, int6
     }
 }
 
+// AVX-512: 64 words per loop-carried update of i; accepted lanes leave through vpcompressd.
+// Levels whose mask is too small for a 64-word window (a neighbour-dependent lane would be common)
+// and the tail of each level go through the AVX2 path.
+__attribute__((target("avx512f,avx2"))) void reject_avx512(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uint32_t* A,
+                                                            int64_t& k) {
+    const __m512i vmask = _mm512_set1_epi32((int)mask);
+    while (i > lo) {
+        if (st.pos == MT_N) st.refill();
+        if (!(MT_N - st.pos >= 64 && i - 64 >= lo)) break;
+        const uint32_t* w = st.tw + st.pos;
+        const __m512i vi = _mm512_set1_epi32((int)i), vs = _mm512_set1_epi32((int)(i - 63));
+        const __m512i u0 = _mm512_and_si512(_mm512_loadu_si512(w), vmask);
+        const __m512i u1 = _mm512_and_si512(_mm512_loadu_si512(w + 16), vmask);
+        const __m512i u2 = _mm512_and_si512(_mm512_loadu_si512(w + 32), vmask);
+        const __m512i u3 = _mm512_and_si512(_mm512_loadu_si512(w + 48), vmask);
+        const __mmask16 g0 = _mm512_cmpgt_epi32_mask(u0, vi), g1 = _mm512_cmpgt_epi32_mask(u1, vi);
+        const __mmask16 g2 = _mm512_cmpgt_epi32_mask(u2, vi), g3 = _mm512_cmpgt_epi32_mask(u3, vi);
+        const unsigned amb = (unsigned)(g0 ^ _mm512_cmpgt_epi32_mask(u0, vs)) | (unsigned)(g1 ^ _mm512_cmpgt_epi32_mask(u1, vs)) |
+                             (unsigned)(g2 ^ _mm512_cmpgt_epi32_mask(u2, vs)) | (unsigned)(g3 ^ _mm512_cmpgt_epi32_mask(u3, vs));
+        if (amb) {
+            reject_scalar(st, mask, lo, i, A, k, 64);
+            continue;
+        }
+        const __mmask16 m0 = (__mmask16)~g0, m1 = (__mmask16)~g1, m2 = (__mmask16)~g2, m3 = (__mmask16)~g3;
+        const int c0 = __builtin_popcount((unsigned)m0), c1 = __builtin_popcount((unsigned)m1);
+        const int c2 = __builtin_popcount((unsigned)m2), c3 = __builtin_popcount((unsigned)m3);
+        uint32_t* dst = A + k;
+        _mm512_storeu_si512(dst, _mm512_maskz_compress_epi32(m0, u0));
+        _mm512_storeu_si512(dst + c0, _mm512_maskz_compress_epi32(m1, u1));
+        _mm512_storeu_si512(dst + c0 + c1, _mm512_maskz_compress_epi32(m2, u2));
+        _mm512_storeu_si512(dst + c0 + c1 + c2, _mm512_maskz_compress_epi32(m3, u3));
+        const int c = c0 + c1 + c2 + c3;
+        k += c;
+        i -= c;
+        st.pos += 64;
+    }
+}
+
 // Ascending scan over steps q >= size (descending k): 8 membership tests per gather.
 __attribute__((target("avx2"))) void resolve_avx2(const uint32_t* A, int64_t n, int64_t size, uint32_t* live,
                                                     int32_t* owner, int32_t* head) {
@@ -331,11 +369,15 @@ bool have_avx2() {
 void draw_accepted(Stream& st, int64_t n, uint32_t* A) {
     if (n < 2) return;
     const bool avx2 = have_avx2();
+#ifdef RFMC_HAVE_AVX2
+    static const bool avx512 = __builtin_cpu_supports("avx512f") && avx2;
+#endif
     uint32_t mask = all_ones_at_least((uint32_t)(n - 1));
     int64_t i = n - 1, k = 0;
     while (i >= 1) {
         const int64_t lo = (int64_t)(mask >> 1);  // this mask serves i in (lo, mask]
 #ifdef RFMC_HAVE_AVX2
+        if (avx512 && mask >= 131071) reject_avx512(st, mask, lo, i, A, k);  // leaves a tail for the paths below
         if (avx2 && mask >= 1023)
             reject_avx2(st, mask, lo, i, A, k);
         else
@@ -436,7 +478,7 @@ extern "C" int rfmc_legacy_permutation_prefix(uint32_t* key, int32_t* pos_io, in
         return 1;
     if (n == 0) return 0;
     Scratch& s = g_s;
-    if ((int64_t)s.A.size() < n + 64) s.A.resize((size_t)n + 64);
+    if ((int64_t)s.A.size() < n + 128) s.A.resize((size_t)n + 128);
     Stream st;
     st.attach(key, *pos_io);
     draw_accepted(st, n, s.A.data());
@@ -472,7 +514,7 @@ extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_s
     Pool pool;
     std::vector<std::vector<uint32_t>> bufs((size_t)(n_threads ? 2 * n_threads + 2 : 1));
     for (auto& b : bufs) {
-        b.resize((size_t)max_n + 64);
+        b.resize((size_t)max_n + 128);
         pool.free_bufs.push_back(b.data());
     }
     std::vector<std::thread> workers;

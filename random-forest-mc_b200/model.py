@@ -144,7 +144,7 @@ class RandomForestMC(BaseRandomForestMC):
         self.max_candidates_per_launch = 4096
         self.max_batch_bytes = 24 << 30
         self.rng_threads = max(0, min(6, (os.cpu_count() or 1) - 1))
-        self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"  # MT19937 blocks from a producer thread
+        self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "1" if (os.cpu_count() or 1) >= 12 else "0") == "1"  # MT19937 blocks from a producer thread
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
