@@ -235,8 +235,9 @@ class RandomForestMC(BaseRandomForestMC):
         cols = self.feature_cols
         where = {name: j for j, name in enumerate(cols)}
         plan = []
+        py_state0 = _pyrandom.getstate()
         for s in range(n_plan):
-            py_state = _pyrandom.getstate()
+            py_state = ("replay", py_state0, K, spec, s)
             feats = []
             for k in range(spec):
                 out = _pyrandom.sample(cols, min(len(cols), int(K[s, k])))
@@ -300,10 +301,20 @@ class RandomForestMC(BaseRandomForestMC):
     def _snapshot(self):
         return np.random.get_state(), _pyrandom.getstate()
 
-    @staticmethod
-    def _restore(snap):
+    def _restore(self, snap):
         np.random.set_state(snap[0])
-        _pyrandom.setstate(snap[1])
+        py = snap[1]
+        if isinstance(py, tuple) and len(py) == 5 and py[0] == "replay":
+            # CPython's stream is snapshotted once per plan; a slot's state is recovered by replaying
+            # the plan's random.sample calls up to that slot (they are pure functions of the stream)
+            _, state0, counts, spec, upto = py
+            _pyrandom.setstate(state0)
+            cols = self.feature_cols
+            for t in range(upto):
+                for k in range(spec):
+                    _pyrandom.sample(cols, min(len(cols), int(counts[t, k])))
+        else:
+            _pyrandom.setstate(py)
 
     def _draw_slot(self, n_cands: int, idx=None):
         """One slot's draws: rows once (unless continuing a slot), then ``n_cands`` feature lists.
