@@ -591,6 +591,28 @@ class RandomForestMC(BaseRandomForestMC):
             matrix[a][b], matrix[b][a] = count, count
         return pd.DataFrame(matrix, index=self.feature_cols, columns=self.feature_cols)
 
+    # missing-value exploration (model.py:495-568): pandas reshaping around one predict_proba call
+    @staticmethod
+    def _fill_row_missing(row, dict_values):
+        from .missing import fill_row
+
+        return fill_row(row, dict_values)
+
+    def _validationMissingValues(self, dict_values) -> None:
+        from .missing import check_dict_values
+
+        check_dict_values(self, dict_values)
+
+    def _genFilledDataMissing(self, row_or_matrix, dict_values):
+        from .missing import expand
+
+        return expand(row_or_matrix, dict_values)
+
+    def predictMissingValues(self, row_or_matrix, dict_values):
+        from .missing import predict_missing_values
+
+        return predict_missing_values(self, row_or_matrix, dict_values)
+
     def sampleClassFeatCount(self, row, Class):
         return self.featCount(self.sampleClass2trees(row=row, Class=Class))
 

@@ -91,3 +91,33 @@ def check_persistence_and_merge(g, m):
     m3.mergeForest(m, N=3, by="score")
     assert len(m3.data) == 3
     assert m3.survived_scores == sorted(m3.survived_scores, reverse=True)
+
+
+def check_predict_missing_values():
+    """predictMissingValues == the frame recorded from the reference (same seed, same inputs)."""
+    import gzip
+    import os
+    import pickle
+
+    import pandas as pd
+
+    from tests.helpers import GOLDEN_DIR
+
+    with gzip.open(os.path.join(GOLDEN_DIR, "..", "golden_missing", "missing_titanic.pkl.gz"), "rb") as f:
+        g = pickle.load(f)
+    m = RandomForestMC(**g["kwargs"])
+    np.random.seed(g["seed"])
+    random.seed(g["seed"])
+    m.fit(g["frame"].copy(), disable_progress_bar=True)
+    assert [float(s) for s in m.survived_scores] == [float(s) for s in g["survived_scores"]]
+    got_row = m.predictMissingValues(g["row"], g["dict_values"])
+    got_frame = m.predictMissingValues(g["holes"], g["dict_values"])
+    pd.testing.assert_frame_equal(got_row, g["by_row"], check_exact=True, check_dtype=False)
+    pd.testing.assert_frame_equal(got_frame, g["by_frame"], check_exact=True, check_dtype=False)
+    from random_forest_mc_b200.model import DictValuesAllFeaturesMissing, MissingValuesNotFound
+    import pytest
+
+    with pytest.raises(MissingValuesNotFound):
+        m.predictMissingValues(g["frame"].loc[0], g["dict_values"])
+    with pytest.raises(DictValuesAllFeaturesMissing):
+        m.predictMissingValues(g["holes"], {"Not Feature": [1, 2], "Not Feature 2": [3]})

@@ -56,3 +56,7 @@ def test_single_tree_call_matches_oracle():
         got = tree(row)
         assert list(got.keys()) == list(want.keys())
         assert all(float(got[k]) == float(want[k]) for k in want)
+
+
+def test_predict_missing_values_matches_reference():
+    model_checks.check_predict_missing_values()

@@ -80,3 +80,7 @@ def test_depths_and_plant_validate_single_calls():
 
     assert tree_diff(t.data, ref["tree"]) is None
     assert float(m.validationTree(t, ref["idx_V"])) == float(ref["th_val"])
+
+
+def test_predict_missing_values_matches_reference():
+    model_checks.check_predict_missing_values()
