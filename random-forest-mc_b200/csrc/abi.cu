@@ -195,6 +195,63 @@ static void pipe_destroy(PredictPipe* p) {
     delete p;
 }
 
+// Blocked layout for the vote kernel: every block = 4 records of 8 bytes {lo = feat | cat<<14 |
+// leaf<<15 | thr<<16, hi = next}: slot 0 a node, slots 1/2 its '>=' / '<' children; a split child's
+// `next` is the block of ITS '>=' child (the '<' child is the next block).  Returns false when the
+// forest is not eligible (codes or feature ids too wide), in which case the 16-byte nodes are used.
+static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t* roots, int32_t n_trees,
+                         std::vector<uint32_t>& out, std::vector<uint32_t>& root_b) {
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        const rfmc_pnode& n = nodes[i];
+        if (n.feat_flags & RFMC_PNODE_LEAF) continue;
+        if ((n.feat_flags & 0xFFFFu) >= 0x4000u) return false;
+        if (n.thr != 0xFFFFFFFFu && n.thr > 65534u) return false;
+    }
+    auto rec_lo = [](const rfmc_pnode& n) -> uint32_t {
+        if (n.feat_flags & RFMC_PNODE_LEAF) return 0x8000u;
+        const uint32_t thr = n.thr == 0xFFFFFFFFu ? 0xFFFFu : n.thr;
+        return (n.feat_flags & 0x3FFFu) | ((n.feat_flags & RFMC_PNODE_CATEGORICAL) ? 0x4000u : 0u) | (thr << 16);
+    };
+    out.clear();
+    out.reserve((size_t)n_nodes * 4);
+    root_b.assign((size_t)n_trees, 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> queue;  // (node, block)
+    auto new_blocks = [&](int count) -> uint32_t {
+        const uint32_t first = (uint32_t)(out.size() / 8);
+        out.resize(out.size() + (size_t)count * 8, 0u);
+        return first;
+    };
+    for (int32_t t = 0; t < n_trees; ++t) {
+        queue.clear();
+        root_b[t] = new_blocks(1);
+        queue.emplace_back((uint32_t)roots[t], root_b[t]);
+        for (size_t q = 0; q < queue.size(); ++q) {
+            const uint32_t ni = queue[q].first, bi = queue[q].second;
+            const rfmc_pnode& p = nodes[ni];
+            out[(size_t)bi * 8 + 0] = rec_lo(p);
+            if (p.feat_flags & RFMC_PNODE_LEAF) {
+                out[(size_t)bi * 8 + 1] = p.thr;  // payload
+                continue;
+            }
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t ci = p.child + (uint32_t)side;
+                const rfmc_pnode& x = nodes[ci];
+                const size_t at = (size_t)bi * 8 + 2 + 2 * (size_t)side;
+                out[at] = rec_lo(x);
+                if (x.feat_flags & RFMC_PNODE_LEAF) {
+                    out[at + 1] = x.thr;
+                } else {
+                    const uint32_t nb = new_blocks(2);
+                    out[at + 1] = nb;
+                    queue.emplace_back(x.child, nb);
+                    queue.emplace_back(x.child + 1, nb + 1);
+                }
+            }
+        }
+    }
+    return true;
+}
+
 extern "C" {
 
 int rfmc_abi_version(void) { return RFMC_ABI_VERSION; }
@@ -468,6 +525,12 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
     rc |= upload(&f->d_probs, probs, (size_t)n_payloads * n_classes, 0);
     rc |= upload(&f->d_probs_absent, probs_absent, (size_t)n_payloads * n_classes, 0);
     rc |= upload(&f->d_scores, scores, (size_t)n_trees, 0);
+    std::vector<uint32_t> blocks, root_b;  // must outlive the asynchronous uploads below
+    if (!rc && build_blocks(nodes, n_nodes, tree_root, n_trees, blocks, root_b)) {
+        f->n_blocks = (int64_t)(blocks.size() / 8);
+        rc |= upload((uint32_t**)&f->d_blocks, blocks.data(), blocks.size(), 0);
+        rc |= upload(&f->d_root_b, root_b.data(), root_b.size(), 0);
+    }
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) {
         set_error("forest upload failed");
         rc = 1;
@@ -491,6 +554,8 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     release(f->d_probs_absent);
     release(f->d_scores);
     pipe_destroy(f->pipe);
+    release(f->d_blocks);
+    release(f->d_root_b);
     release(f->d_thresholds);
     release(f->d_thr_off);
     delete f;

@@ -102,6 +102,9 @@ struct rfmc_forest {
     double* d_scores = nullptr;
     int sm_count = 0;
     PredictPipe* pipe = nullptr;  // pinned staging + streams of the host-buffer voting path
+    uint4* d_blocks = nullptr;       // blocked 8-byte-node layout for the vote kernel (nullptr: not eligible)
+    uint32_t* d_root_b = nullptr;
+    int64_t n_blocks = 0;
     double* d_thresholds = nullptr;  // code book of the frame encoder (rfmc_forest_set_codebook)
     int64_t* d_thr_off = nullptr;
     int32_t n_features_book = 0;
