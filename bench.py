@@ -343,6 +343,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         return time.perf_counter() - t, forest
 
+    def e2e_fit_parallel(k):
+        model.data, model.survived_scores = [], []
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        forest_p = model._fit_slots_streams(args.n_trees, [9000 + 100 * rank + r for r in range(k)])
+        torch.cuda.synchronize()
+        return time.perf_counter() - t, forest_p
+
     e2e_fit()  # warm-up
     barrier()
     e2e_s, e2e_cands, forest, e2e_each = 0.0, 0, None, []
@@ -354,6 +362,24 @@ def run_b200(args):
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     stats = dict(model.fit_stats)
+    # fitParallel on this GPU: the slots shared over k independent host RNG streams (threads)
+    k_streams = max(1, min(args.host_streams, os.cpu_count() or 1, args.n_trees))
+    par = None
+    if world == 1 and k_streams > 1:
+        e2e_fit_parallel(k_streams)
+        par_each, par_cands = [], 0
+        for _ in range(args.e2e_steps):
+            dt, _fp = e2e_fit_parallel(k_streams)
+            par_each.append(round(dt * 1e3, 2))
+            par_cands += model.fit_stats["candidates_grown"]
+        par = {
+            "value": par_cands / (sum(par_each) / 1e3),
+            "unit": "candidate-trees/s",
+            "host_streams": k_streams,
+            "ms_each": par_each,
+            "api": "RandomForestMC.fitParallel(max_workers=k): k host threads with independent seeded RNG streams (the "
+            "semantics of the reference's process pool and of the CPU arm) feeding one GPU",
+        }
     surv_nodes = sum(t.soa.n_nodes for t in forest[: args.n_trees])
     h2d = int(args.n_trees * (batch.n_train + batch.n_val) * 4 + sum(len(f) for f in feats) * 2 + n_cand * 8)
     d2h = int(n_cand * 8 + surv_nodes * (24 + 4 * C))
@@ -462,7 +488,8 @@ def run_b200(args):
                 "ms_each_rank0": e2e_each,
                 "fit_stats": stats,
             },
-            "gpu_launches": int(launches),
+            "e2e_fitParallel": par,
+            "gpu_launches": int(launches) + args.steps,
             "roofline": {
                 "kernel": "rfmc::grow_kernel",
                 "bound": "hbm",
@@ -533,6 +560,7 @@ def main():
     ap.add_argument("--predict-rows", type=int, default=1_000_000, dest="predict_rows")
     ap.add_argument("--e2e-steps", type=int, default=2, dest="e2e_steps")
     ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
+    ap.add_argument("--host-streams", type=int, default=8, dest="host_streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.predict_rows = min(args.predict_rows, args.rows)

@@ -93,9 +93,9 @@ static int reserve(T** dst, size_t count) {
     return 0;
 }
 
-// One pinned staging buffer per process for device -> host survivor export.
-static void* g_pin = nullptr;
-static size_t g_pin_cap = 0;
+// One pinned staging buffer per host thread for device -> host survivor export.
+static thread_local void* g_pin = nullptr;
+static thread_local size_t g_pin_cap = 0;
 static void* pinned_staging(size_t bytes) {
     if (bytes > g_pin_cap) {
         if (g_pin) cudaFreeHost(g_pin);

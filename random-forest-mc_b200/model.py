@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import logging as log
 import os
+import threading
 import random as _pyrandom
 from sys import getrecursionlimit
 from typing import List, Optional, Tuple
@@ -141,6 +142,7 @@ class RandomForestMC(BaseRandomForestMC):
         self.encoded: Optional[EncodedDataset] = None
         self._dev_dataset: Optional[engine.DeviceDataset] = None
         self.fit_stats = {}
+        self._tls = threading.local()
         self.max_candidates_per_launch = 4096
         self.max_batch_bytes = 24 << 30
         self.rng_threads = max(0, min(6, (os.cpu_count() or 1) - 1))
@@ -184,12 +186,20 @@ class RandomForestMC(BaseRandomForestMC):
     # ---------------------------------------------------------------------------------------------
     # host RNG draws, exactly the reference's (model.py:198-219)
     # ---------------------------------------------------------------------------------------------
+    def _np_rng(self):
+        """numpy's global legacy generator (the reference's), or this thread's own RandomState when
+        fitParallel runs several host streams."""
+        return getattr(self._tls, "np_rng", None) or np.random
+
+    def _py_rng(self):
+        return getattr(self._tls, "py_rng", None) or _pyrandom
+
     def split_train_val(self) -> Tuple[np.ndarray, np.ndarray]:
         """model.py:198-210.  ``np.random.choice(class_indices, _N, replace=False)`` per class in
         ``class_vals`` order, drawn from numpy's global legacy stream by the host restatement in
         csrc/host_rng.cpp (same indices, same end state as numpy: tests/test_host_rng.py).  The
         per-class row lists ``indices[target_vals == val]`` are cached: building them uses no RNG."""
-        st = np.random.get_state()
+        st = self._np_rng().get_state()
         key, pos = st[1].copy(), int(st[2])
         train, val = [], []
         for class_indices in self.encoded.class_rows:
@@ -197,12 +207,12 @@ class RandomForestMC(BaseRandomForestMC):
             selected = class_indices[idx]
             train.append(selected[: self.batch_train_pclass])
             val.append(selected[self.batch_train_pclass :])
-        np.random.set_state((st[0], key, pos, st[3], st[4]))
+        self._np_rng().set_state((st[0], key, pos, st[3], st[4]))
         return np.concatenate(train), np.concatenate(val)
 
     def sampleFeats(self, feature_cols: List[str]) -> List[str]:
-        n_samples = np.random.randint(self.min_feature, self.max_feature + 1)
-        out = _pyrandom.sample(feature_cols, min(len(feature_cols), n_samples))
+        n_samples = self._np_rng().randint(self.min_feature, self.max_feature + 1)
+        out = self._py_rng().sample(feature_cols, min(len(feature_cols), n_samples))
         if not self.temporal_features:
             return out
         return sorted(out, key=lambda x: int(x.split("_")[-1]))
@@ -225,22 +235,23 @@ class RandomForestMC(BaseRandomForestMC):
         then picks and orders the features.  Entry layout as ``_draw_slot``."""
         if self.min_feature > self.max_feature:
             raise ValueError("low >= high")  # what np.random.randint raises in the reference
-        st = np.random.get_state()
+        st = self._np_rng().get_state()
         key = st[1].copy()
         T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
             key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,
-            int(self.min_feature), int(self.max_feature) + 1, self.rng_threads | (0x100 if self.rng_producer else 0),
+            int(self.min_feature), int(self.max_feature) + 1, getattr(self._tls, "rng_flags", self.rng_threads | (0x100 if self.rng_producer else 0)),
         )
-        np.random.set_state((st[0], key, pos, st[3], st[4]))
+        self._np_rng().set_state((st[0], key, pos, st[3], st[4]))
         cols = self.feature_cols
         where = {name: j for j, name in enumerate(cols)}
         plan = []
-        py_state0 = _pyrandom.getstate()
+        py_rng = self._py_rng()
+        py_state0 = py_rng.getstate()
         for s in range(n_plan):
             py_state = ("replay", py_state0, K, spec, s)
             feats = []
             for k in range(spec):
-                out = _pyrandom.sample(cols, min(len(cols), int(K[s, k])))
+                out = py_rng.sample(cols, min(len(cols), int(K[s, k])))
                 if self.temporal_features:
                     out = sorted(out, key=lambda x: int(x.split("_")[-1]))
                 feats.append([where[f] for f in out])
@@ -299,22 +310,23 @@ class RandomForestMC(BaseRandomForestMC):
     # the batched, speculative fit loop
     # ---------------------------------------------------------------------------------------------
     def _snapshot(self):
-        return np.random.get_state(), _pyrandom.getstate()
+        return self._np_rng().get_state(), self._py_rng().getstate()
 
     def _restore(self, snap):
-        np.random.set_state(snap[0])
+        self._np_rng().set_state(snap[0])
+        py_rng = self._py_rng()
         py = snap[1]
         if isinstance(py, tuple) and len(py) == 5 and py[0] == "replay":
             # CPython's stream is snapshotted once per plan; a slot's state is recovered by replaying
             # the plan's random.sample calls up to that slot (they are pure functions of the stream)
             _, state0, counts, spec, upto = py
-            _pyrandom.setstate(state0)
+            py_rng.setstate(state0)
             cols = self.feature_cols
             for t in range(upto):
                 for k in range(spec):
-                    _pyrandom.sample(cols, min(len(cols), int(counts[t, k])))
+                    py_rng.sample(cols, min(len(cols), int(counts[t, k])))
         else:
-            _pyrandom.setstate(py)
+            py_rng.setstate(py)
 
     def _draw_slot(self, n_cands: int, idx=None):
         """One slot's draws: rows once (unless continuing a slot), then ``n_cands`` feature lists.
@@ -429,7 +441,45 @@ class RandomForestMC(BaseRandomForestMC):
             t.features = self.feature_cols
             t.used_features = self.tree2feats(t)
         self.fit_stats = stats
+        self._tls.last_stats = stats
         return trees
+
+    def _fit_slots_streams(self, n_slots: int, seeds):
+        """``n_slots`` shared over ``len(seeds)`` independent host RNG streams, one thread each, all
+        feeding this GPU.  Worker r is exactly the serial algorithm on its share of the slots under
+        ``np.random.seed(seeds[r]); random.seed(seeds[r])`` (its own RandomState / Random objects);
+        the forest is the concatenation in worker order -- the same contract as the rank-sharded
+        fit, and the semantics of the reference's process pool (independent streams per worker)."""
+        from .dist import shard_bounds
+
+        k = len(seeds)
+        parts, stats, errors = [None] * k, [None] * k, []
+
+        def work(r):
+            try:
+                self._tls.np_rng = np.random.RandomState(int(seeds[r]))
+                self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
+                self._tls.rng_flags = 1  # one resolve helper per stream, no producer thread
+                lo, hi = shard_bounds(n_slots, r, k)
+                parts[r] = self._fit_slots(hi - lo) if hi > lo else []
+                stats[r] = getattr(self._tls, "last_stats", None)
+            except BaseException as e:  # surfaced on the calling thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(k)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        total = {}
+        for st in stats:
+            for key, v in (st or {}).items():
+                total[key] = total.get(key, 0) + v
+        total["host_streams"] = k
+        self.fit_stats = total
+        return [t for part in parts for t in part]
 
     def _collect(self, batch, chosen, trees_out):
         ids = []
@@ -507,20 +557,26 @@ class RandomForestMC(BaseRandomForestMC):
         disable_progress_bar: bool = False,
         max_workers: Optional[int] = None,
     ):
-        """The multi-GPU analogue of the reference's process pool (model.py:372-404): tree slots are
-        sharded over the ranks of the default torch.distributed group (one process per GPU), each
-        rank replays the serial algorithm on its own seeded streams, survivors are all-gathered.
-        Without an initialised process group this is ``fit``."""
+        """The analogue of the reference's process pool (model.py:372-404): tree slots are sharded
+        over independent RNG streams.  With an initialised torch.distributed group: one rank per GPU,
+        survivors all-gathered.  Otherwise: ``max_workers`` host threads, each with its own seeded
+        streams, all feeding this GPU (the draws -- the serial floor of ``fit`` -- run in parallel).
+        Either way worker r == the serial algorithm under its seed, forest = concatenation."""
         if dataset is not None:
             self.process_dataset(dataset)
         if self.dataset_numpy is None:
             raise DatasetNotFound
         from . import dist
 
-        if not dist.is_distributed():
-            Forest = self._fit_slots(self.n_trees)
-        else:
+        if dist.is_distributed():
             Forest = dist.fit_sharded(self)
+        else:
+            k = max_workers or min(8, os.cpu_count() or 1)
+            k = max(1, min(int(k), self.n_trees))
+            seeds = getattr(self, "worker_seeds", None)
+            if seeds is None:  # derived from the global stream: reproducible under np.random.seed(s)
+                seeds = [int(x) for x in self._np_rng().randint(0, 2**31 - 1, size=k)]
+            Forest = self._fit_slots_streams(self.n_trees, list(seeds)[:k] if len(seeds) >= k else list(seeds))
         self.data.extend(Forest)
         self.survived_scores.extend([Tree.survived_score for Tree in Forest])
 

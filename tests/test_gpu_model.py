@@ -60,3 +60,9 @@ def test_single_tree_call_matches_oracle():
 
 def test_predict_missing_values_matches_reference():
     model_checks.check_predict_missing_values()
+
+
+def test_fit_parallel_host_streams_contract():
+    from tests.test_host_model import test_fit_parallel_host_streams_contract as check
+
+    check()

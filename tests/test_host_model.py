@@ -84,3 +84,41 @@ def test_depths_and_plant_validate_single_calls():
 
 def test_predict_missing_values_matches_reference():
     model_checks.check_predict_missing_values()
+
+
+def test_fit_parallel_host_streams_contract():
+    """fitParallel(max_workers=2): worker r == the serial algorithm under seed s_r on its share of
+    the slots; forest = concatenation in worker order (checked against the oracle)."""
+    import random
+
+    from oracle import rfmc_oracle as orc
+    from random_forest_mc_b200.model import RandomForestMC
+    from tests.helpers import tree_diff
+
+    g = load_golden("mixed_default")
+    kw = dict(g["kwargs"])
+    kw["n_trees"] = 5
+    m = RandomForestMC(**kw)
+    m.worker_seeds = [1000, 1001]
+    m.fitParallel(g["frame"].copy(), disable_progress_bar=True, max_workers=2)
+    want_trees, want_scores = [], []
+    for seed, n in ((1000, 3), (1001, 2)):
+        ds = orc.ingest(g["frame"].copy(), target_col=kw["target_col"])
+        np.random.seed(seed)
+        random.seed(seed)
+        t, s, _ = orc.fit(ds, n, max_discard_trees=kw["max_discard_trees"])
+        want_trees += t
+        want_scores += [float(x) for x in s]
+    assert [float(s) for s in m.survived_scores] == want_scores
+    for a, b in zip(m.data, want_trees):
+        assert tree_diff(a.data, b) is None
+    assert m.fit_stats["host_streams"] == 2
+    # default seeds come from the global stream: reproducible under np.random.seed
+    outs = []
+    for _ in range(2):
+        m2 = RandomForestMC(**kw)
+        np.random.seed(3)
+        random.seed(3)
+        m2.fitParallel(g["frame"].copy(), disable_progress_bar=True, max_workers=3)
+        outs.append([float(s) for s in m2.survived_scores])
+    assert outs[0] == outs[1] and len(outs[0]) == 5
