@@ -358,6 +358,7 @@ def run_b200(args):
         dt, forest = e2e_fit()
         e2e_s += dt
         e2e_each.append(round(dt * 1e3, 2))
+        print("e2e step", round(dt * 1e3, 1), "ms", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in model.fit_stats.items()}, file=sys.stderr)
         e2e_cands += model.fit_stats["candidates_grown"]
     barrier()
     e2e_s = max_over_ranks(e2e_s)
