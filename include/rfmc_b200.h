@@ -127,6 +127,12 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
                         int32_t n_features, const uint8_t* absent, int soft, int weighted, double* probs_out,
                         int32_t* labels_out, int on_device, void* stream);
 
+/* CPython's random.sample(population, k) for n_calls candidates in a row (model.py:216): the
+ * population INDICES it picks, on CPython's own MT19937 stream (key[624] / *pos from
+ * random.getstate()[1], advanced in place).  out holds sum(ks) indices back to back. */
+int rfmc_pyrandom_sample_plan(uint32_t* key, int32_t* pos, int32_t n_pop, int32_t n_calls, const int32_t* ks,
+                              int32_t* out);
+
 /* ---- voting straight from a raw frame: the encode of predict-time values fused in front ---------
  * rfmc_forest_set_codebook: per feature the sorted distinct numeric split values of the forest
  * (thr_off [n_features+1] into thresholds); code(x) = #{t <= x}, NaN -> 0, so that the test

@@ -582,3 +582,62 @@ extern "C" int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos_io, int32_t n_s
     *pos_io = st.pos;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// CPython's random.sample(population, k) (model.py:216, `random_sample(feature_cols, ...)`) for a
+// whole plan of candidates: the INDICES it would pick, on CPython's own MT19937 stream
+// (random.getstate()[1] = 624 state words + index; same generator and tempering as numpy's).
+// Restates CPython 3.12 Lib/random.py:
+//   _randbelow_with_getrandbits(n): k = n.bit_length(); r = getrandbits(k) until r < n
+//   getrandbits(k <= 32)          : genrand_uint32() >> (32 - k)      (Modules/_randommodule.c)
+//   sample(): setsize = 21 (+ 4 ** ceil(log(3k, 4)) when k > 5);
+//             n <= setsize: pool selection  (j = randbelow(n - i); take pool[j]; pool[j] = pool[n-i-1])
+//             else        : rejection on a set of already selected indices
+// Parity: tests/test_host_rng.py compares with random.sample itself, end state included.
+// ---------------------------------------------------------------------------------------------
+#include <math.h>
+
+namespace {
+inline uint32_t py_randbelow(Stream& st, uint32_t n) {
+    const int k = 32 - __builtin_clz(n);  // n.bit_length(), n >= 1
+    uint32_t r;
+    do {
+        r = st.next() >> (32 - k);
+    } while (r >= n);
+    return r;
+}
+}  // namespace
+
+extern "C" int rfmc_pyrandom_sample_plan(uint32_t* key, int32_t* pos_io, int32_t n_pop, int32_t n_calls, const int32_t* ks,
+                                         int32_t* out) {
+    if (!key || !pos_io || !ks || !out || n_pop < 1 || n_calls < 0 || *pos_io < 0 || *pos_io > MT_N) return 1;
+    Stream st;
+    st.attach(key, *pos_io);
+    std::vector<int32_t> pool((size_t)n_pop);
+    std::vector<uint8_t> taken((size_t)n_pop);
+    int64_t at = 0;
+    for (int32_t c = 0; c < n_calls; ++c) {
+        const int32_t k = ks[c];
+        if (k < 0 || k > n_pop) return 1;
+        long long setsize = 21;
+        if (k > 5) setsize += (long long)llround(pow(4.0, ceil(log((double)k * 3.0) / log(4.0))));
+        if ((long long)n_pop <= setsize) {
+            for (int32_t i = 0; i < n_pop; ++i) pool[i] = i;
+            for (int32_t i = 0; i < k; ++i) {
+                const uint32_t j = py_randbelow(st, (uint32_t)(n_pop - i));
+                out[at++] = pool[j];
+                pool[j] = pool[n_pop - i - 1];
+            }
+        } else {
+            memset(taken.data(), 0, taken.size());
+            for (int32_t i = 0; i < k; ++i) {
+                uint32_t j = py_randbelow(st, (uint32_t)n_pop);
+                while (taken[j]) j = py_randbelow(st, (uint32_t)n_pop);
+                taken[j] = 1;
+                out[at++] = (int32_t)j;
+            }
+        }
+    }
+    *pos_io = st.pos;
+    return 0;
+}

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
     "rfmc_forest_leaves": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p]),
     "rfmc_legacy_permutation_prefix": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, _p]),
+    "rfmc_pyrandom_sample_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p]),
     "rfmc_forest_set_codebook": (C.c_int, [_p, C.c_int32, _p, _p]),
     "rfmc_forest_predict_frame": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, C.c_int, C.c_int32, _p, _p, _p, _p,
                                             C.c_int, C.c_int, _p, _p]),
@@ -145,6 +146,22 @@ def legacy_draw_plan(key: np.ndarray, pos: int, n_slots: int, class_rows: Sequen
     if rc != 0:
         raise EngineError("rfmc_legacy_draw_plan: bad arguments")
     return idx_train, idx_val, counts, key_snap, pos_snap, p.value
+
+
+def pyrandom_sample_plan(rng, n_pop: int, ks: np.ndarray):
+    """``rng.sample(range(n_pop), k)`` for every k of ``ks`` in a row, on ``rng``'s own stream
+    (``rng`` = the ``random`` module or a ``random.Random``).  Returns the picked indices back to
+    back; the generator is left exactly where CPython would have left it."""
+    version, internal, gauss = rng.getstate()
+    key = np.array(internal[:624], dtype=np.uint32)
+    p = C.c_int32(int(internal[624]))
+    ks = np.ascontiguousarray(ks, dtype=np.int32).reshape(-1)
+    out = np.empty(int(ks.sum()), dtype=np.int32)
+    rc = load_library().rfmc_pyrandom_sample_plan(_ptr(key), C.byref(p), n_pop, len(ks), _ptr(ks), _ptr(out))
+    if rc != 0:
+        raise EngineError("rfmc_pyrandom_sample_plan: bad arguments")
+    rng.setstate((version, tuple(key.tolist()) + (p.value,), gauss))
+    return out
 
 
 class DeviceDataset:

@@ -243,20 +243,24 @@ class RandomForestMC(BaseRandomForestMC):
         )
         self._np_rng().set_state((st[0], key, pos, st[3], st[4]))
         cols = self.feature_cols
-        where = {name: j for j, name in enumerate(cols)}
-        plan = []
         py_rng = self._py_rng()
         py_state0 = py_rng.getstate()
+        ks = np.minimum(K, len(cols)).astype(np.int32)
+        if not self.temporal_features:
+            # CPython's stream walked in one host call as well (engine.pyrandom_sample_plan)
+            flat = engine.pyrandom_sample_plan(py_rng, len(cols), ks)
+            ends = np.cumsum(ks.reshape(-1))
+            per_cand = np.split(flat, ends[:-1])
+        else:
+            per_cand = []
+            where = {name: j for j, name in enumerate(cols)}
+            for k in ks.reshape(-1):
+                out = sorted(py_rng.sample(cols, int(k)), key=lambda x: int(x.split("_")[-1]))
+                per_cand.append(np.array([where[f] for f in out], dtype=np.int32))
+        plan = []
         for s in range(n_plan):
-            py_state = ("replay", py_state0, K, spec, s)
-            feats = []
-            for k in range(spec):
-                out = py_rng.sample(cols, min(len(cols), int(K[s, k])))
-                if self.temporal_features:
-                    out = sorted(out, key=lambda x: int(x.split("_")[-1]))
-                feats.append([where[f] for f in out])
-            start = ((st[0], ksnap[s], int(psnap[s]), st[3], st[4]), py_state)
-            plan.append((T[s], V[s], feats, (start, True)))
+            start = ((st[0], ksnap[s], int(psnap[s]), st[3], st[4]), ("replay", py_state0, K, spec, s))
+            plan.append((T[s], V[s], per_cand[s * spec : (s + 1) * spec], (start, True)))
         return plan
 
     def _wrap(self, soa, score=None) -> DecisionTreeMC:
@@ -438,8 +442,7 @@ class RandomForestMC(BaseRandomForestMC):
                 tail = recent_used[-16:]
                 assume_pass = K > 1 and (sum(1 for u in tail if u == 1) * 2 > len(tail))
         for t in trees:
-            t.features = self.feature_cols
-            t.used_features = self.tree2feats(t)
+            t.features = self.feature_cols  # used_features is derived from the node table on first access
         self.fit_stats = stats
         self._tls.last_stats = stats
         return trees

@@ -44,6 +44,7 @@ class DecisionTreeMC(UserDict):
         # UserDict.__init__ is bypassed on purpose, as in the reference (tree.py:86)
         self._data = data
         self._soa: Optional[TreeSoA] = None
+        self._used_features = None
         self._enc = None
         self._type_of_cols = None
         self.class_vals = class_vals
@@ -74,6 +75,21 @@ class DecisionTreeMC(UserDict):
     @property
     def soa(self) -> Optional[TreeSoA]:
         return self._soa
+
+    @property
+    def used_features(self):
+        """Features the tree splits on (model.py:413-417).  For a tree that came from the grower the
+        list is read off the node table on first access."""
+        if self._used_features is None and self._soa is not None and self._enc is not None:
+            from .flat import used_feature_ids
+
+            names = self._enc.feature_cols
+            self._used_features = [names[j] for j in used_feature_ids(self._soa)]
+        return self._used_features
+
+    @used_features.setter
+    def used_features(self, value) -> None:
+        self._used_features = value
 
     def _check_format(self, other):
         if not isinstance(other, DecisionTreeMC):

@@ -68,3 +68,29 @@ def test_draw_plan_matches_numpy_call_sequence(threads, per_class, n_train, lo, 
     assert np.array_equal(key, after[1]) and pos == after[2]
     for s in range(n_slots):
         assert np.array_equal(ksnap[s], want_state[s][1]) and psnap[s] == want_state[s][2]
+
+
+@pytest.mark.parametrize("n_pop", [1, 2, 6, 21, 22, 64, 85, 86, 128, 1000])
+def test_pyrandom_sample_matches_cpython(n_pop):
+    """Indices and end state of random.sample, for the module-level stream and a Random instance,
+    across the pool / set branches (setsize = 21 + 4**ceil(log(3k, 4)))."""
+    import random
+
+    g = np.random.default_rng(n_pop)
+    ks = np.minimum(g.integers(0, max(2, n_pop + 1), size=40), n_pop).astype(np.int32)
+    ks[:6] = [0, min(1, n_pop), min(5, n_pop), min(6, n_pop), n_pop, min(7, n_pop)]
+    pop = list(range(n_pop))
+    for make in (lambda: random, lambda: random.Random(77)):
+        rng = make()
+        rng.seed(1234 + n_pop)
+        rng.random()
+        want = [rng.sample(pop, int(k)) for k in ks]
+        after = rng.getstate()
+        rng.seed(1234 + n_pop)
+        rng.random()
+        got = engine.pyrandom_sample_plan(rng, n_pop, ks)
+        assert rng.getstate() == after
+        at = 0
+        for k, w in zip(ks, want):
+            assert got[at : at + k].tolist() == w
+            at += int(k)
