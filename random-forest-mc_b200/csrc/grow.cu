@@ -35,6 +35,9 @@
 namespace rfmc {
 
 constexpr int GROW_THREADS = 256;
+#ifndef RFMC_GROW_MIN_CTAS
+#define RFMC_GROW_MIN_CTAS 4  // 64 registers per thread; the kernel is latency-bound, see profiles/
+#endif
 constexpr int GROW_WARPS = GROW_THREADS / 32;
 constexpr int HIST_WORDS = 512;  // per warp
 constexpr uint32_t NOT_FINAL = 0xFFu;
@@ -680,7 +683,7 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
 }
 
 template <typename CodeT, typename PosT>
-__global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs<CodeT, PosT> a) {
+__global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(GrowArgs<CodeT, PosT> a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ uint32_t s_hist[GROW_WARPS][HIST_WORDS];
     __shared__ uint32_t s_wtot[GROW_WARPS];
