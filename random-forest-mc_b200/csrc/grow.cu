@@ -30,6 +30,8 @@
 // table.  Nodes of <= 32 rows hold their rows in registers and partition their segment in place;
 // larger nodes partition into a global scratch segment and copy back.  On-chip: per-warp shared-memory histograms with warp-aggregated atomics (match.any),
 // ballots and shuffles for rank counting, prefix sums and arg-max.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rfmc {
@@ -983,6 +985,10 @@ int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train) {
         case 1: per_sm = p16 ? occupancy_t<uint8_t, uint16_t>(nt_pad) : occupancy_t<uint8_t, uint32_t>(nt_pad); break;
         case 2: per_sm = p16 ? occupancy_t<uint16_t, uint16_t>(nt_pad) : occupancy_t<uint16_t, uint32_t>(nt_pad); break;
         default: per_sm = p16 ? occupancy_t<uint32_t, uint16_t>(nt_pad) : occupancy_t<uint32_t, uint32_t>(nt_pad); break;
+    }
+    if (const char* e = getenv("RFMC_GROW_CTAS_PER_SM")) {  // experiment knob: fewer resident candidates
+        const int want = atoi(e);
+        if (want >= 1 && want < per_sm) per_sm = want;
     }
     long long g = (long long)ds->sm_count * per_sm;
     if (g > n_cand) g = n_cand;
