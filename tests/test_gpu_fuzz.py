@@ -13,9 +13,6 @@ import pytest
 from oracle import rfmc_oracle as orc
 from tests.helpers import probs_equal, tree_diff
 
-pytestmark = pytest.mark.gpu
-
-
 def random_frame(g, n):
     cols = {}
     n_cols = int(g.integers(2, 9))
@@ -44,14 +41,14 @@ def random_frame(g, n):
     n_classes = int(g.integers(2, 6))
     labels = [str(x) for x in g.permutation(["10", "9", "b", "A", "c", "zz"])[:n_classes]]
     first = df.iloc[:, 0]
-    base = pd.factorize(first)[0] if first.dtype == object or first.dtype == bool else first.to_numpy(dtype=float)
+    is_num = pd.api.types.is_numeric_dtype(first) and not pd.api.types.is_bool_dtype(first)
+    base = first.to_numpy(dtype=float) if is_num else pd.factorize(first)[0]
     s = np.asarray(base, dtype=float) + g.normal(size=n) * (np.std(base) + 1.0)
     df["target"] = np.array(labels)[np.argsort(np.argsort(s)) * n_classes // n]
     return df
 
 
-@pytest.mark.parametrize("seed", range(24))
-def test_random_config_matches_oracle(seed):
+def run_case(seed):
     import logging
 
     from random_forest_mc_b200.model import RandomForestMC
@@ -114,3 +111,9 @@ def test_random_config_matches_oracle(seed):
                 want_l = orc.forest_labels(want_trees, want_scores, ds.class_vals, fr, soft, weighted)
                 assert probs_equal(m.testForestProbs(fr), want_p), (soft, weighted)
                 assert m.testForest(fr) == want_l, (soft, weighted)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_random_config_matches_oracle(seed):
+    run_case(seed)
