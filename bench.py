@@ -231,11 +231,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, workload):
+    """dram bytes per launch from the committed ncu capture -- only for the workload it was taken on."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get(kernel)
+            d = json.load(f)
+        if d.get("workload") == workload:
+            return d.get("bytes_per_launch", {}).get(kernel)
     return None
 
 
@@ -498,7 +501,7 @@ def run_b200(args):
                 "peak": hbm_peak,
                 "unit": "GB/s",
                 "frac": grow_gbs / hbm_peak,
-                "traffic": ncu_traffic("grow_kernel"),
+                "traffic": ncu_traffic("grow_kernel", workload_name(args)),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
             },
@@ -532,7 +535,7 @@ def run_b200(args):
                     "peak": hbm_peak,
                     "unit": "GB/s",
                     "frac": pred_gbs / hbm_peak,
-                    "traffic": ncu_traffic("predict_kernel"),
+                    "traffic": ncu_traffic("predict_kernel", workload_name(args)),
                     "algorithmic_bytes_per_launch": pred_algo,
                 },
             },

@@ -74,6 +74,10 @@ for rep, name in (("prof_growF", "grow_kernel"), ("prof_predictF", "predict_kern
     traffic[name] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
+workload = None
+plain = os.path.join(OUT, "plainF.json")
+if os.path.exists(plain):
+    workload = json.load(open(plain))["config"]["workload"]
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
-    json.dump(traffic, f)
+    json.dump({"workload": workload, "bytes_per_launch": traffic}, f)
 print("\n".join(lines))
