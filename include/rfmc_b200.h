@@ -67,6 +67,10 @@ typedef struct rfmc_batch rfmc_batch;
 typedef struct rfmc_forest rfmc_forest;
 
 int rfmc_abi_version(void);
+/* A non-blocking CUDA stream on `device` as an opaque pointer for the `stream` arguments below
+ * (so that several host threads can keep independent batches in flight). */
+int rfmc_stream_create(int device, void** out);
+int rfmc_stream_destroy(int device, void* stream);
 const char* rfmc_last_error(void);
 int rfmc_device_count(int* count);
 

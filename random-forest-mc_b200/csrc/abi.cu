@@ -258,6 +258,23 @@ int rfmc_abi_version(void) { return RFMC_ABI_VERSION; }
 
 const char* rfmc_last_error(void) { return g_error.c_str(); }
 
+int rfmc_stream_create(int device, void** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_CUDA(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    RFMC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *out = (void*)st;
+    return 0;
+}
+
+int rfmc_stream_destroy(int device, void* stream) {
+    if (!stream) return 0;
+    RFMC_CUDA(cudaSetDevice(device));
+    RFMC_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return 0;
+}
+
 int rfmc_device_count(int* count) {
     RFMC_REQUIRE(count != nullptr, "count is NULL");
     *count = 0;

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "rfmc_abi_version": (C.c_int, []),
     "rfmc_last_error": (C.c_char_p, []),
     "rfmc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "rfmc_stream_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "rfmc_stream_destroy": (C.c_int, [C.c_int, _p]),
     "rfmc_dataset_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int32, C.c_int64, _p, C.c_int32, _p, _p, _p, _p, _p, C.POINTER(_p)]),
     "rfmc_dataset_destroy": (C.c_int, [_p]),
     "rfmc_batch_create": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
@@ -111,6 +113,17 @@ def _stream_ptr(stream) -> Optional[int]:
     if isinstance(stream, int):
         return stream or None
     return getattr(stream, "cuda_stream", None) or None
+
+
+def stream_create(device: int = 0) -> int:
+    h = _p()
+    _check(load_library().rfmc_stream_create(device, C.byref(h)))
+    return h.value
+
+
+def stream_destroy(device: int, stream: int) -> None:
+    if stream:
+        _check(load_library().rfmc_stream_destroy(device, _p(stream)))
 
 
 def legacy_choice_indices(key: np.ndarray, pos: int, n: int, size: int):

@@ -459,15 +459,22 @@ class RandomForestMC(BaseRandomForestMC):
         parts, stats, errors = [None] * k, [None] * k, []
 
         def work(r):
+            stream = 0
             try:
+                stream = engine.stream_create(self.device)  # each host stream keeps its own launches in flight
                 self._tls.np_rng = np.random.RandomState(int(seeds[r]))
                 self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
                 self._tls.rng_flags = 1  # one resolve helper per stream, no producer thread
                 lo, hi = shard_bounds(n_slots, r, k)
-                parts[r] = self._fit_slots(hi - lo) if hi > lo else []
+                parts[r] = self._fit_slots(hi - lo, stream) if hi > lo else []
                 stats[r] = getattr(self._tls, "last_stats", None)
             except BaseException as e:  # surfaced on the calling thread
                 errors.append(e)
+            finally:
+                try:
+                    engine.stream_destroy(self.device, stream)
+                except Exception:
+                    pass
 
         threads = [threading.Thread(target=work, args=(r,)) for r in range(k)]
         for t in threads:

@@ -99,6 +99,8 @@ class FakeForest:
 def install(monkeypatch):
     from random_forest_mc_b200 import engine
 
+    monkeypatch.setattr(engine, "stream_create", lambda device=0: 0)
+    monkeypatch.setattr(engine, "stream_destroy", lambda device, stream: None)
     monkeypatch.setattr(engine, "DeviceDataset", FakeDataset)
     monkeypatch.setattr(engine, "GrowBatch", FakeBatch)
     monkeypatch.setattr(engine, "DeviceForest", FakeForest)
@@ -108,3 +110,5 @@ def install_plain():
     from random_forest_mc_b200 import engine
 
     engine.DeviceDataset, engine.GrowBatch, engine.DeviceForest = FakeDataset, FakeBatch, FakeForest
+    engine.stream_create = lambda device=0: 0
+    engine.stream_destroy = lambda device, stream: None
