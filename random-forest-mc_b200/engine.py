@@ -349,7 +349,18 @@ class DeviceForest:
         n = len(frame)
         absent = np.zeros(t.n_features, dtype=np.uint8)
         have = set(frame.columns)
-        keep, ptrs, feats, dts = [], [], [], []
+        def categorical_ids(col, cats):
+            # Series.factorize keeps Arrow-backed strings in Arrow (dictionary encode, GIL released)
+            ids, uniques = col.factorize(use_na_sentinel=True)
+            lut = np.zeros(len(uniques) + 1, dtype=np.int32)  # last slot: NaN sentinel (-1) -> 0
+            for k, u in enumerate(uniques):
+                try:
+                    lut[k] = cats.get(u, 0)
+                except TypeError:
+                    lut[k] = 0
+            return np.ascontiguousarray(lut[ids], dtype=np.int32)
+
+        jobs = []  # (feature index, dtype code or None, array or column)
         for j, name in enumerate(t.feature_cols):
             thr, cats = t.thresholds[j], t.categories[j]
             if thr is None and cats is None:
@@ -363,20 +374,23 @@ class DeviceForest:
                 if arr.dtype.name not in self._DT:
                     arr = pd.to_numeric(col, errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
                 arr = np.ascontiguousarray(arr)
-                dts.append(self._DT[arr.dtype.name])
+                jobs.append((j, self._DT[arr.dtype.name], arr))
             else:
-                ids, uniques = pd.factorize(col.to_numpy(), use_na_sentinel=True)
-                lut = np.zeros(len(uniques) + 1, dtype=np.int32)
-                for k, u in enumerate(uniques):
-                    try:
-                        lut[k] = cats.get(u, 0)
-                    except TypeError:
-                        lut[k] = 0
-                arr = np.ascontiguousarray(lut[ids], dtype=np.int32)
-                dts.append(10)
-            keep.append(arr)
-            ptrs.append(arr.ctypes.data)
-            feats.append(j)
+                jobs.append((j, None, (col, cats)))
+        todo = [k for k, job in enumerate(jobs) if job[1] is None]
+        if len(todo) > 1 and n >= 100_000:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(8, len(todo))) as pool:
+                done = list(pool.map(lambda k: categorical_ids(*jobs[k][2]), todo))
+        else:
+            done = [categorical_ids(*jobs[k][2]) for k in todo]
+        for k, arr in zip(todo, done):
+            jobs[k] = (jobs[k][0], 10, arr)
+        keep = [job[2] for job in jobs]
+        ptrs = [a.ctypes.data for a in keep]
+        feats = [job[0] for job in jobs]
+        dts = [job[1] for job in jobs]
         probs = np.empty((n, self.n_classes), dtype=np.float64) if want_probs else None
         labels = np.empty(n, dtype=np.int32) if want_labels else None
         ncol = len(keep)

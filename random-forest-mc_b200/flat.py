@@ -282,7 +282,7 @@ def encode_frame(tables: ForestTables, frame):
             code[np.isnan(x)] = 0
             codes[:, j] = code
         else:
-            ids, uniques = pd.factorize(col.to_numpy(), use_na_sentinel=True)
+            ids, uniques = col.factorize(use_na_sentinel=True)
             lut = np.zeros(len(uniques) + 1, dtype=np.int64)  # last slot: NaN sentinel (-1) -> 0
             for k, u in enumerate(uniques):
                 try:

@@ -204,8 +204,7 @@ class BaseRandomForestMC(UserList):
         if len(ds) == 0:
             return []
         _, labels = self._vote_frame(ds, False, True)
-        cv = self.class_vals
-        return [cv[k] for k in labels]
+        return np.array(self.class_vals, dtype=object)[labels].tolist()
 
     def testForestProbs(self, ds: pd.DataFrame) -> List[dict]:
         if len(ds) == 0:
