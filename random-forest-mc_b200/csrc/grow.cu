@@ -43,7 +43,7 @@ constexpr int GROW_THREADS = 256;
 constexpr int GROW_WARPS = GROW_THREADS / 32;
 constexpr int HIST_WORDS = 512;  // per warp
 constexpr uint32_t NOT_FINAL = 0xFFu;
-constexpr int TINY_MAX = 4, SMALL_MAX = 32;
+constexpr int TINY_MAX = 4, SMALL_MAX = 32, HUGE_MIN = 1024;
 
 template <typename CodeT, typename PosT>
 struct GrowArgs {
@@ -684,13 +684,295 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// huge nodes (> HUGE_MIN rows): the whole CTA works on ONE node.  The top levels of a tree hold one
+// to a few such nodes; giving each to a single warp leaves seven warps of the CTA waiting at the
+// level barrier.  Every warp takes a contiguous slice of the node's rows, accumulates into its own
+// shared-memory histogram, the 8 histograms are summed into s_comb, and every warp then derives the
+// same digits / mode / counts from s_comb, so all control flow stays CTA-uniform.  The stable
+// partition uses per-warp side counts (slices are contiguous, so slice order = row order).
+// ---------------------------------------------------------------------------------------------
+template <typename CodeT, typename PosT>
+__device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint32_t (*s_hist)[HIST_WORDS], uint32_t* s_comb,
+                            uint32_t* s_part, int tid) {
+    const GrowArgs<CodeT, PosT>& a = *c.a;
+    const int lane = tid & 31, warp = tid >> 5;
+    const WorkItem w = *item;
+    const uint32_t n = w.hi - w.lo;
+    PosT* P = c.pos + w.lo;
+    PosT* T = c.tmp + w.lo;
+    const int C = a.n_classes;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t node = c.base + w.lpos;
+    uint32_t* hist = s_hist[warp];
+    const uint32_t per = ((n + GROW_WARPS * 32 - 1) / (GROW_WARPS * 32)) * 32;
+    const uint32_t r0 = (uint32_t)warp * per < n ? (uint32_t)warp * per : n;
+    const uint32_t r1 = r0 + per < n ? r0 + per : n;
+
+    // ---- class histogram ----
+    for (int i = lane; i < RFMC_MAX_CLASSES; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (uint32_t base = r0; base < r1; base += 128) {
+        uint32_t l[4];
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            act[u] = i < r1;
+            l[u] = act[u] ? (uint32_t)P[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) l[u] = act[u] ? (uint32_t)c.lab[l[u]] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hist_add(hist, l[u], act[u], lane);
+    }
+    __syncthreads();
+    if (tid < RFMC_MAX_CLASSES) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < GROW_WARPS; ++w8) sum += s_hist[w8][tid];
+        s_comb[tid] = sum;
+    }
+    __syncthreads();
+    const uint32_t cls0 = s_comb[lane];
+    const uint32_t cls1 = s_comb[lane + 32];
+    const int present = __popc(__ballot_sync(FULL, cls0 > 0)) + __popc(__ballot_sync(FULL, cls1 > 0));
+    const int depth = c.level + 1;
+    const bool leaf = (depth >= a.max_depth) || (present == 1);
+    if (warp == 0) {
+        if (lane < C) c.counts[(size_t)node * C + lane] = (int32_t)cls0;
+        if (lane + 32 < C) c.counts[(size_t)node * C + lane + 32] = (int32_t)cls1;
+        unsigned long long k0 = ((unsigned long long)cls0 << 8) | (unsigned long long)(255 - lane);
+        unsigned long long k1 = ((unsigned long long)cls1 << 8) | (unsigned long long)(255 - (lane + 32));
+        if (lane >= C) k0 = 0;
+        if (lane + 32 >= C) k1 = 0;
+        unsigned long long k = warp_max_u64(k0 > k1 ? k0 : k1);
+        if (lane == 0) c.votes[node] = (uint8_t)(255 - (int)(k & 255));
+    }
+    __syncthreads();  // s_comb is reused below
+
+    bool accepted = false;
+    uint32_t thr_store = 0, na = 0, flags = 0, f_acc = 0, off_next = 0;
+    double sv_acc = 0.0;
+    if (!leaf) {
+        for (int k = 0; k < c.nf; ++k) {
+            int fl = (int)w.off + k;
+            if (fl >= c.nf) fl -= c.nf;
+            const uint32_t f = c.flist[fl];
+            const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
+            const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
+            const uint32_t K = (uint32_t)a.col_nuniq[f];
+            uint32_t t_store = 0, t_part = 0, cnt_a = 0;
+            const uint32_t fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
+            double sv = 0.0;
+            if (cat) {
+                if (K + 1 <= (uint32_t)HIST_WORDS) {
+                    for (uint32_t i = lane; i <= K; i += 32) hist[i] = 0;
+                    __syncwarp();
+                    for (uint32_t base = r0; base < r1; base += 128) {
+                        uint32_t cv[4];
+                        bool act[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t i = base + u * 32 + lane;
+                            act[u] = i < r1;
+                            cv[u] = act[u] ? (uint32_t)P[i] : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[cv[u]] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hist_add(hist, cv[u], act[u], lane);
+                    }
+                    __syncthreads();
+                    for (uint32_t b = tid; b <= K; b += GROW_THREADS) {
+                        uint32_t sum = 0;
+#pragma unroll
+                        for (int w8 = 0; w8 < GROW_WARPS; ++w8) sum += s_hist[w8][b];
+                        s_comb[b] = sum;
+                    }
+                    __syncthreads();
+                    unsigned long long key = 0;
+                    for (uint32_t i = lane; i <= K; i += 32) {
+                        unsigned long long kk = ((unsigned long long)s_comb[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+                        key = kk > key ? kk : key;
+                    }
+                    key = warp_max_u64(key);
+                    t_store = t_part = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+                } else {  // high-cardinality categorical: warp 0 counts all pairs (rare path)
+                    if (warp == 0) {
+                        unsigned long long key = 0;
+                        for (uint32_t base = 0; base < n; base += 32) {
+                            bool act = base + lane < n;
+                            uint32_t my = act ? (uint32_t)col[P[base + lane]] : 0xFFFFFFFFu;
+                            uint32_t cnt = 0;
+                            for (uint32_t b2 = 0; b2 < n; b2 += 32) {
+                                uint32_t other = (b2 + lane < n) ? (uint32_t)col[P[b2 + lane]] : 0xFFFFFFFEu;
+#pragma unroll 8
+                                for (int s = 0; s < 32; ++s) cnt += (__shfl_sync(FULL, other, s) == my);
+                            }
+                            unsigned long long kk =
+                                act ? (((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - my)) : 0ull;
+                            key = kk > key ? kk : key;
+                        }
+                        key = warp_max_u64(key);
+                        if (lane == 0) s_comb[0] = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+                    }
+                    __syncthreads();
+                    t_store = t_part = s_comb[0];
+                }
+            } else {
+                const int npass = (K < 0x100u) ? 1 : ((K < 0x10000u) ? 2 : ((K < 0x1000000u) ? 3 : 4));
+                uint32_t prefA = 0, prefB = 0, rA = (n - 1) >> 1, rB = ((n - 1) >> 1) + 1;
+                bool same = true;
+                for (int pass = npass - 1; pass >= 0; --pass) {
+                    const int shift = pass * 8;
+                    const uint32_t himask = (pass == npass - 1) ? 0u : (0xFFFFFFFFu << (shift + 8));
+                    for (int i = lane; i < (same ? 256 : 512); i += 32) hist[i] = 0;
+                    __syncwarp();
+                    for (uint32_t base = r0; base < r1; base += 128) {
+                        uint32_t cv[4];
+                        bool act[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t i = base + u * 32 + lane;
+                            act[u] = i < r1;
+                            cv[u] = act[u] ? (uint32_t)P[i] : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[cv[u]] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t d = (cv[u] >> shift) & 255u;
+                            hist_add(hist, d, act[u] && ((cv[u] & himask) == (prefA & himask)), lane);
+                            if (!same) hist_add(hist + 256, d, act[u] && ((cv[u] & himask) == (prefB & himask)), lane);
+                        }
+                    }
+                    __syncthreads();
+                    {
+                        uint32_t sa = 0, sb = 0;
+#pragma unroll
+                        for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
+                            sa += s_hist[w8][tid];
+                            if (!same) sb += s_hist[w8][256 + tid];
+                        }
+                        s_comb[tid] = sa;
+                        if (!same) s_comb[256 + tid] = sb;
+                    }
+                    __syncthreads();
+                    const uint32_t dA = find_bin256(s_comb, rA, lane);
+                    uint32_t dB;
+                    if (same) {
+                        dB = find_bin256(s_comb, rB, lane);
+                        if (dB != dA) same = false;
+                    } else {
+                        dB = find_bin256(s_comb + 256, rB, lane);
+                    }
+                    prefA |= dA << shift;
+                    prefB |= dB << shift;
+                }
+                const uint32_t ca = prefA, cb = prefB;
+                const double* tab = a.tables + a.tab_off[f];
+                const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
+                sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
+                t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
+            }
+            // ---- side sizes (per-warp slices, summed through shared memory) ----
+            uint32_t mine_a = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                mine_a = 0;
+                for (uint32_t base = r0; base < r1; base += 128) {
+                    uint32_t cv[4];
+                    bool act[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t i = base + u * 32 + lane;
+                        act[u] = i < r1;
+                        cv[u] = act[u] ? (uint32_t)P[i] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[cv[u]] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool go = act[u] && (cat ? cv[u] == t_part : cv[u] >= t_part);
+                        mine_a += __popc(__ballot_sync(FULL, go));
+                    }
+                }
+                __syncthreads();  // previous readers of s_part are done
+                if (lane == 0) s_part[warp] = mine_a;
+                __syncthreads();
+                cnt_a = 0;
+#pragma unroll
+                for (int w8 = 0; w8 < GROW_WARPS; ++w8) cnt_a += s_part[w8];
+                if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu) break;
+                const double* tab = a.tables + a.tab_off[f];
+                const uint32_t i0 = t_store - 1;
+                const uint32_t t2 = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
+                if (t2 == t_part) break;
+                t_part = t2;
+            }
+            if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
+                accepted = true;
+                uint32_t oa = 0, ob = cnt_a;  // slices are contiguous: slice order is row order
+#pragma unroll
+                for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
+                    if (w8 < warp) {
+                        const uint32_t s0 = (uint32_t)w8 * per < n ? (uint32_t)w8 * per : n;
+                        const uint32_t s1 = s0 + per < n ? s0 + per : n;
+                        oa += s_part[w8];
+                        ob += (s1 - s0) - s_part[w8];
+                    }
+                }
+                for (uint32_t base = r0; base < r1; base += 32) {
+                    const uint32_t i = base + lane;
+                    const bool act = i < r1;
+                    const uint32_t pi = act ? (uint32_t)P[i] : 0u;
+                    const uint32_t cv = act ? (uint32_t)col[pi] : 0u;
+                    const bool go = act && (cat ? cv == t_part : cv >= t_part);
+                    const uint32_t ma = __ballot_sync(FULL, go);
+                    const uint32_t mb = __ballot_sync(FULL, act && !go);
+                    if (act) T[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi;
+                    oa += __popc(ma);
+                    ob += __popc(mb);
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < n; i += GROW_THREADS) P[i] = T[i];
+                __syncthreads();
+                thr_store = t_store;
+                na = cnt_a;
+                flags = fl_flags;
+                f_acc = f;
+                sv_acc = cat ? 0.0 : sv;
+                off_next = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
+                break;
+            }
+        }
+    }
+    if (tid == 0) {
+        rfmc_node nd;
+        write_leaf(&nd);
+        if (accepted) {
+            nd.feat = (int32_t)f_acc;
+            nd.thr = thr_store;
+            nd.flags = flags;
+            nd.sval = sv_acc;
+            item->off = off_next;
+        }
+        c.nodes[node] = nd;
+        c.resna[w.lpos] = accepted ? na : 0u;
+        c.resfin[w.lpos] = (uint16_t)(NOT_FINAL | (NOT_FINAL << 8));
+    }
+    __syncthreads();
+}
+
 template <typename CodeT, typename PosT>
 __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(GrowArgs<CodeT, PosT> a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ uint32_t s_hist[GROW_WARPS][HIST_WORDS];
     __shared__ uint32_t s_wtot[GROW_WARPS];
     __shared__ uint32_t s_ticket[3];
-    __shared__ uint32_t s_cnt[2][3];  // items per size class, this level / next level
+    __shared__ uint32_t s_cnt[2][4];  // items per size class (tiny, small, large, huge), this level / next level
+    __shared__ uint32_t s_comb[HIST_WORDS];
+    __shared__ uint32_t s_part[GROW_WARPS];
     __shared__ uint32_t s_total;
     __shared__ int s_correct;
 
@@ -699,8 +981,9 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
     const int nt = a.n_train;
     // list regions inside one work buffer: tiny items hold >= 2 rows, small >= 5, large >= 33
     const uint32_t cap_t = (uint32_t)nt / 2 + 1, cap_s = (uint32_t)nt / 5 + 1, cap_l = (uint32_t)nt / 33 + 1;
-    const uint32_t reg0[3] = {0u, cap_t, cap_t + cap_s};
-    const uint32_t cap_all = cap_t + cap_s + cap_l;
+    const uint32_t cap_h = (uint32_t)nt / (HUGE_MIN + 1) + 1;
+    const uint32_t reg0[4] = {0u, cap_t, cap_t + cap_s, cap_t + cap_s + cap_l};
+    const uint32_t cap_all = cap_t + cap_s + cap_l + cap_h;
 
     uint8_t* lab;
     PosT* pos;
@@ -764,8 +1047,8 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             }
         }
         if (tid == 0) {
-            const int cls = nt <= TINY_MAX ? 0 : (nt <= SMALL_MAX ? 1 : 2);
-            s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = 0;
+            const int cls = nt <= TINY_MAX ? 0 : (nt <= SMALL_MAX ? 1 : (nt <= HUGE_MIN ? 2 : 3));
+            s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = s_cnt[0][3] = 0;
             s_cnt[0][cls] = 1;
             work[reg0[cls]] = WorkItem{0u, (uint32_t)nt, 0u, 0u};
             resna[0] = 0;
@@ -784,13 +1067,15 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             c.resna = resna_cur;
             c.base = base;
             c.level = level;
-            const uint32_t n_tiny = s_cnt[cb][0], n_small = s_cnt[cb][1], n_large = s_cnt[cb][2];
-            if (tid < 3) {
-                s_ticket[tid] = 0;
+            const uint32_t n_tiny = s_cnt[cb][0], n_small = s_cnt[cb][1], n_large = s_cnt[cb][2], n_huge = s_cnt[cb][3];
+            if (tid < 4) {
+                if (tid < 3) s_ticket[tid] = 0;
                 s_cnt[nb][tid] = 0;
             }
             __syncthreads();
-            // ---- phase 1: large and small nodes by warps, tiny nodes by threads ----
+            // ---- phase 1: huge nodes by the whole CTA, large and small nodes by warps, tiny by threads ----
+            for (uint32_t j = 0; j < n_huge; ++j)
+                process_cta<CodeT, PosT>(c, cur + reg0[3] + j, s_hist, s_comb, s_part, tid);
             while (true) {
                 uint32_t j = 0;
                 if (lane == 0) j = atomicAdd(&s_ticket[2], 1u);
@@ -839,10 +1124,12 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             __syncthreads();
             // ---- phase 2b: child ids, finished leaves, next level's work lists ----
             const uint32_t base_next = base + width;
-            const uint32_t n_items = n_tiny + n_small + n_large;
+            const uint32_t n_items = n_tiny + n_small + n_large + n_huge;
             for (uint32_t q = tid; q < n_items; q += GROW_THREADS) {
                 const WorkItem w = q < n_tiny ? cur[reg0[0] + q]
-                                              : (q < n_tiny + n_small ? cur[reg0[1] + q - n_tiny] : cur[reg0[2] + q - n_tiny - n_small]);
+                                   : (q < n_tiny + n_small ? cur[reg0[1] + q - n_tiny]
+                                      : (q < n_tiny + n_small + n_large ? cur[reg0[2] + q - n_tiny - n_small]
+                                                                         : cur[reg0[3] + q - n_tiny - n_small - n_large]));
                 const uint32_t na = resna_cur[w.lpos];
                 if (na == 0) continue;
                 const uint32_t s = rank[w.lpos];
@@ -859,7 +1146,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                         for (int k = 0; k < C; ++k) c.counts[(size_t)cn * C + k] = (k == (int)f8) ? (int32_t)sz : 0;
                         c.votes[cn] = (uint8_t)f8;
                     } else {
-                        const int cls = sz <= TINY_MAX ? 0 : (sz <= SMALL_MAX ? 1 : 2);
+                        const int cls = sz <= TINY_MAX ? 0 : (sz <= SMALL_MAX ? 1 : (sz <= (uint32_t)HUGE_MIN ? 2 : 3));
                         const uint32_t at = atomicAdd(&s_cnt[nb][cls], 1u);
                         nxt[reg0[cls] + at] = WorkItem{lo, hi, cpos, w.off};
                     }
