@@ -275,6 +275,9 @@ int rfmc_stream_destroy(int device, void* stream) {
     return 0;
 }
 
+/* debug builds (-DRFMC_GROW_TIMING) only: per-level cycle counters of the grower; not part of the ABI header */
+int rfmc_debug_read(unsigned long long* out, int n) { return debug_read(out, n); }
+
 int rfmc_device_count(int* count) {
     RFMC_REQUIRE(count != nullptr, "count is NULL");
     *count = 0;

@@ -113,6 +113,7 @@ struct rfmc_forest {
 namespace rfmc {
 int launch_grow(rfmc_batch* b, cudaStream_t stream);
 int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train);
+int debug_read(unsigned long long* out, int n);
 int launch_pack(rfmc_batch* b, const int32_t* d_cand_ids, const int64_t* d_dst_off, int32_t n_sel, rfmc_node* nodes_out,
                 int32_t* counts_out, cudaStream_t stream);
 int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t n_rows, int64_t row_stride,

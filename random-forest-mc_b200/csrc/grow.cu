@@ -41,6 +41,13 @@ constexpr int GROW_THREADS = 256;
 #define RFMC_GROW_MIN_CTAS 4  // 64 registers per thread; the kernel is latency-bound, see profiles/
 #endif
 constexpr int GROW_WARPS = GROW_THREADS / 32;
+#ifdef RFMC_GROW_TIMING
+// debug build only: per-level cycle counts of CTA 0's first candidate (see profiles/grow_levels.py)
+__device__ unsigned long long g_dbg[8192];
+#define RFMC_TICK(slot) if (blockIdx.x == 0 && cand == 0 && threadIdx.x == 0 && (slot) < 8192) g_dbg[(slot)] = clock64()
+#else
+#define RFMC_TICK(slot)
+#endif
 constexpr int HIST_WORDS = 512;  // per warp
 constexpr uint32_t NOT_FINAL = 0xFFu;
 constexpr int TINY_MAX = 4, SMALL_MAX = 32, HUGE_MIN = 1024;
@@ -1019,6 +1026,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         const int C = a.n_classes;
 
         // ---- gather the bootstrap rows once: coalesced row read -> compact [feature][row] ----
+        RFMC_TICK(0);
         // One lane per row: the row ids of 32 rows are one coalesced load, each lane then walks
         // its own 132-byte row (L1-resident after the first touch; the loads of the unrolled
         // feature loop are independent), and every store is 32 consecutive codes of one feature.
@@ -1057,6 +1065,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         uint32_t width = 1, base = 0;
         int level = 0;
         __syncthreads();
+        RFMC_TICK(1);
 
         while (width > 0) {
             const int cb = level & 1, nb = cb ^ 1;
@@ -1073,6 +1082,15 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                 s_cnt[nb][tid] = 0;
             }
             __syncthreads();
+#ifdef RFMC_GROW_TIMING
+            if (blockIdx.x == 0 && cand == 0 && tid == 0 && 16 + 8 * level + 7 < 8192) {
+                g_dbg[16 + 8 * level + 0] = clock64();
+                g_dbg[16 + 8 * level + 4] = n_tiny;
+                g_dbg[16 + 8 * level + 5] = n_small;
+                g_dbg[16 + 8 * level + 6] = n_large;
+                g_dbg[16 + 8 * level + 7] = n_huge;
+            }
+#endif
             // ---- phase 1: huge nodes by the whole CTA, large and small nodes by warps, tiny by threads ----
             for (uint32_t j = 0; j < n_huge; ++j)
                 process_cta<CodeT, PosT>(c, cur + reg0[3] + j, s_hist, s_comb, s_part, tid);
@@ -1098,6 +1116,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                 if (j + lane < n_tiny) process_tiny<CodeT, PosT>(c, cur + reg0[0] + j + lane);
             }
             __syncthreads();
+            RFMC_TICK(16 + 8 * level + 1);
             // ---- phase 2a: split rank of every level position (block-wide exclusive scan) ----
             // each warp owns a contiguous range of positions and walks it 32 at a time (coalesced);
             // pass 1 counts, pass 2 re-reads the flags and writes the exclusive ranks
@@ -1122,6 +1141,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                 run += __popc(bal);
             }
             __syncthreads();
+            RFMC_TICK(16 + 8 * level + 2);
             // ---- phase 2b: child ids, finished leaves, next level's work lists ----
             const uint32_t base_next = base + width;
             const uint32_t n_items = n_tiny + n_small + n_large + n_huge;
@@ -1154,9 +1174,11 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             }
             base = base_next;
             width = 2 * splits;
-            ++level;
             __syncthreads();
+            RFMC_TICK(16 + 8 * level + 3);
+            ++level;
         }
+        RFMC_TICK(2);
         const uint32_t n_nodes = base;
 
         // ---- validationTree (model.py:296-314): hold-out rows through the finished tree ----
@@ -1178,6 +1200,10 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         for (int d = 16; d > 0; d >>= 1) good += __shfl_xor_sync(FULL, good, d);
         if (lane == 0 && good) atomicAdd(&s_correct, good);
         __syncthreads();
+        RFMC_TICK(3);
+#ifdef RFMC_GROW_TIMING
+        if (blockIdx.x == 0 && cand == 0 && tid == 0) g_dbg[4] = (unsigned long long)level;
+#endif
         if (tid == 0) {
             a.nnodes[cand] = (int32_t)n_nodes;
             a.correct[cand] = s_correct;
@@ -1262,6 +1288,17 @@ static int occupancy_t(int nt_pad) {
     if (smem > 0) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, GROW_THREADS, smem) != cudaSuccess) per_sm = 1;
     return per_sm < 1 ? 1 : per_sm;
+}
+
+int debug_read(unsigned long long* out, int n) {
+#ifdef RFMC_GROW_TIMING
+    if (n > 8192) n = 8192;
+    return cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : 1;
+#else
+    (void)out;
+    (void)n;
+    return 1;
+#endif
 }
 
 int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train) {
