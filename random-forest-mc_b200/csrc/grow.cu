@@ -12,8 +12,8 @@
 // A tree grown to purity on 8,000 rows has ~14,000 nodes; 59 % of its split nodes hold 2-4 rows,
 // 93 % hold <= 32, and every leaf is pure (88 % are single rows).  So the level's work list is kept
 // in three size classes, each with its own execution shape:
-//   tiny  (<= 4 rows)  one THREAD per node (32 nodes in flight per warp, scalar sorting network);
-//   small (5..32 rows) one WARP per node, one row per lane (ballots, shuffles, match.any);
+//   tiny  (<= 8 rows)  one THREAD per node (32 nodes in flight per warp, 19-comparator sorting network);
+//   small (9..32 rows) one WARP per node, one row per lane (ballots, shuffles, match.any);
 //   large (> 32 rows)  one WARP per node, 128 rows per iteration (4 independent gathers in flight
 //                      per lane), MSD radix select over per-warp shared-memory histograms.
 // A split's child that is provably a leaf already (a single row, or all rows of one class) is
@@ -50,7 +50,7 @@ __device__ unsigned long long g_dbg[8192];
 #endif
 constexpr int HIST_WORDS = 512;  // per warp
 constexpr uint32_t NOT_FINAL = 0xFFu;
-constexpr int TINY_MAX = 4, SMALL_MAX = 32, HUGE_MIN = 1024;
+constexpr int TINY_MAX = 8, SMALL_MAX = 32, HUGE_MIN = 1024;  // the sorting network in process_tiny is for 8
 
 template <typename CodeT, typename PosT>
 struct GrowArgs {
@@ -302,15 +302,14 @@ __device__ __forceinline__ void write_leaf(rfmc_node* nd) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// tiny nodes: one THREAD per node, n in 1..4
+// tiny nodes: one THREAD per node, n in 1..8
 // ---------------------------------------------------------------------------------------------
 template <typename CodeT, typename PosT>
 __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
     const GrowArgs<CodeT, PosT>& a = *c.a;
     const WorkItem w = *item;
-    const uint32_t n = w.hi - w.lo;
-    PosT* P = c.pos + w.lo;
-    PosT* Pn = P;  // rows are in registers: the partition goes back in place
+    const int n = (int)(w.hi - w.lo);
+    PosT* P = c.pos + w.lo;  // rows are in registers: the partition goes back in place
     const int C = a.n_classes;
     const uint32_t node = c.base + w.lpos;
 
@@ -318,8 +317,8 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
     uint32_t l[TINY_MAX];
 #pragma unroll
     for (int q = 0; q < TINY_MAX; ++q) {
-        p[q] = (q < (int)n) ? (uint32_t)P[q] : 0u;
-        l[q] = (q < (int)n) ? (uint32_t)c.lab[p[q]] : 0xFFFFu;
+        p[q] = (q < n) ? (uint32_t)P[q] : 0u;
+        l[q] = (q < n) ? (uint32_t)c.lab[p[q]] : 0xFFFFu;
     }
     // class counts + vote (first max in sorted-label order)
     int32_t* crow = c.counts + (size_t)node * C;
@@ -335,7 +334,7 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
         }
     }
     c.votes[node] = (uint8_t)best_c;
-    const bool pure = best_n == n;
+    const bool pure = (int)best_n == n;
     const int depth = c.level + 1;
     rfmc_node nd;
     write_leaf(&nd);
@@ -349,7 +348,7 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
             const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
             uint32_t cv[TINY_MAX];
 #pragma unroll
-            for (int q = 0; q < TINY_MAX; ++q) cv[q] = (q < (int)n) ? (uint32_t)col[p[q]] : 0u;
+            for (int q = 0; q < TINY_MAX; ++q) cv[q] = (q < n) ? (uint32_t)col[p[q]] : 0xFFFFFFFFu;
             uint32_t t_store, t_part, go = 0, fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
             if (n == 2) {  // model.py:258-262
@@ -360,64 +359,79 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
                 uint32_t bc = 0, bn = 0;
 #pragma unroll
                 for (int q = 0; q < TINY_MAX; ++q) {
-                    if (q >= (int)n) break;
-                    uint32_t cnt = 0;
+                    if (q < n) {
+                        uint32_t cnt = 0;
 #pragma unroll
-                    for (int r = 0; r < TINY_MAX; ++r) cnt += (r < (int)n) && (cv[r] == cv[q]);
-                    if (cnt > bn || (cnt == bn && cv[q] < bc)) {
-                        bn = cnt;
-                        bc = cv[q];
+                        for (int r = 0; r < TINY_MAX; ++r) cnt += (cv[r] == cv[q]);
+                        if (cnt > bn || (cnt == bn && cv[q] < bc)) {
+                            bn = cnt;
+                            bc = cv[q];
+                        }
                     }
                 }
                 t_store = t_part = bc;
 #pragma unroll
-                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] == bc) ? (1u << q) : 0u;
-            } else {  // median of 3 or 4 (ranks 1 and 2 of the sorted codes)
-                uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = (n == 4) ? cv[3] : 0xFFFFFFFFu;
+                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < n) && cv[q] == bc) ? (1u << q) : 0u;
+            } else {  // median: ranks (n-1)/2 and (n-1)/2 + 1 of the sorted codes (absent rows sort last)
+                uint32_t s[TINY_MAX];
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) s[q] = cv[q];
                 uint32_t t;
-#define RFMC_CSWAP(x, y) if (x > y) { t = x; x = y; y = t; }
-                RFMC_CSWAP(s0, s1) RFMC_CSWAP(s2, s3) RFMC_CSWAP(s0, s2) RFMC_CSWAP(s1, s3) RFMC_CSWAP(s1, s2)
+#define RFMC_CSWAP(i, j) if (s[i] > s[j]) { t = s[i]; s[i] = s[j]; s[j] = t; }
+                RFMC_CSWAP(0, 1) RFMC_CSWAP(2, 3) RFMC_CSWAP(4, 5) RFMC_CSWAP(6, 7)
+                RFMC_CSWAP(0, 2) RFMC_CSWAP(1, 3) RFMC_CSWAP(4, 6) RFMC_CSWAP(5, 7)
+                RFMC_CSWAP(1, 2) RFMC_CSWAP(5, 6)
+                RFMC_CSWAP(0, 4) RFMC_CSWAP(1, 5) RFMC_CSWAP(2, 6) RFMC_CSWAP(3, 7)
+                RFMC_CSWAP(2, 4) RFMC_CSWAP(3, 5)
+                RFMC_CSWAP(1, 2) RFMC_CSWAP(3, 4) RFMC_CSWAP(5, 6)
 #undef RFMC_CSWAP
-                const uint32_t ca = s1, cb = s2;
+                const int k0 = (n - 1) >> 1;
+                uint32_t ca = 0, cb = 0;
+#pragma unroll
+                for (int q = 0; q < TINY_MAX; ++q) {
+                    if (q == k0) ca = s[q];
+                    if (q == k0 + 1) cb = s[q];
+                }
                 const double* tab = a.tables + a.tab_off[f];
                 const uint32_t K = (uint32_t)a.col_nuniq[f];
                 const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                 sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
                 t_store = t_part = threshold_scalar(tab, K, sv, va, vb, ca, cb);
 #pragma unroll
-                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] >= t_part) ? (1u << q) : 0u;
-                uint32_t cnt = __popc(go);
+                for (int q = 0; q < TINY_MAX; ++q) go |= ((q < n) && cv[q] >= t_part) ? (1u << q) : 0u;
+                const int cnt = __popc(go);
                 if ((cnt == 0 || cnt == n) && t_store != 0xFFFFFFFFu) {  // model.py:242-245
                     const uint32_t i0 = t_store - 1;
                     t_part = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
                     go = 0;
 #pragma unroll
-                    for (int q = 0; q < TINY_MAX; ++q) go |= ((q < (int)n) && cv[q] >= t_part) ? (1u << q) : 0u;
+                    for (int q = 0; q < TINY_MAX; ++q) go |= ((q < n) && cv[q] >= t_part) ? (1u << q) : 0u;
                 }
             }
-            const uint32_t cnt_a = __popc(go);
-            if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
+            const int cnt_a = __popc(go);
+            if (cnt_a >= a.mss && n - cnt_a >= a.mss) {
                 // stable partition + purity of both sides
-                uint32_t oa = 0, ob = cnt_a, la = 0xFFFFu, lb = 0xFFFFu;
+                uint32_t oa = 0, ob = (uint32_t)cnt_a, la = 0xFFFFu, lb = 0xFFFFu;
                 bool pa = true, pb = true;
 #pragma unroll
                 for (int q = 0; q < TINY_MAX; ++q) {
-                    if (q >= (int)n) break;
-                    if ((go >> q) & 1u) {
-                        Pn[oa++] = (PosT)p[q];
-                        if (la == 0xFFFFu) la = l[q];
-                        pa = pa && (l[q] == la);
-                    } else {
-                        Pn[ob++] = (PosT)p[q];
-                        if (lb == 0xFFFFu) lb = l[q];
-                        pb = pb && (l[q] == lb);
+                    if (q < n) {
+                        if ((go >> q) & 1u) {
+                            P[oa++] = (PosT)p[q];
+                            if (la == 0xFFFFu) la = l[q];
+                            pa = pa && (l[q] == la);
+                        } else {
+                            P[ob++] = (PosT)p[q];
+                            if (lb == 0xFFFFu) lb = l[q];
+                            pb = pb && (l[q] == lb);
+                        }
                     }
                 }
                 nd.feat = (int32_t)f;
                 nd.thr = t_store;
                 nd.flags = fl_flags;
                 nd.sval = (cat || (fl_flags & RFMC_FLAG_TWO_ROW)) ? 0.0 : sv;
-                na_out = cnt_a;
+                na_out = (uint32_t)cnt_a;
                 fin_out = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
                 item->off = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
                 break;
@@ -430,7 +444,7 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// small (5..32 rows, one row per lane) and large (> 32 rows) nodes: one WARP per node
+// small (9..32 rows, one row per lane) and large (> 32 rows) nodes: one WARP per node
 // ---------------------------------------------------------------------------------------------
 template <typename CodeT, typename PosT>
 __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint32_t* hist, int lane) {
