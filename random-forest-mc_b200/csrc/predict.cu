@@ -47,6 +47,14 @@ struct PredictArgs {
     int32_t* labels_out;
 };
 
+// One 32-byte block in ONE request (LDG.E.256 on sm_100a): the vote kernel sits at the L1TEX
+// request-throughput limit (97 % in ncu), so a block fetched as two 16-byte loads costs twice.
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& lo, uint4& hi) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+        : "l"(p));
+}
+
 // MODE: 0 hard, 1 hard+weighted, 2 soft, 3 soft+weighted
 template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT, bool TILE>
 __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
@@ -109,10 +117,7 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
                 any = false;
 #pragma unroll
                 for (int k = 0; k < PRED_ILP; ++k) {
-                    if (!done[k]) {
-                        b0[k] = __ldg(a.blocks + 2 * (size_t)node[k]);
-                        b1[k] = __ldg(a.blocks + 2 * (size_t)node[k] + 1);
-                    }
+                    if (!done[k]) ldg256(a.blocks + 2 * (size_t)node[k], b0[k], b1[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < PRED_ILP; ++k) {
