@@ -214,7 +214,7 @@ static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t
     };
     out.clear();
     out.reserve((size_t)n_nodes * 4);
-    root_b.assign((size_t)n_trees + 1, 0u);  // + sentinel: block count of the last tree
+    root_b.assign((size_t)n_trees, 0u);
     std::vector<std::pair<uint32_t, uint32_t>> queue;  // (node, block)
     auto new_blocks = [&](int count) -> uint32_t {
         const uint32_t first = (uint32_t)(out.size() / 8);
@@ -249,7 +249,6 @@ static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t
             }
         }
     }
-    root_b[(size_t)n_trees] = (uint32_t)(out.size() / 8);
     return true;
 }
 

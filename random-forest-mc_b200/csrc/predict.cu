@@ -55,38 +55,6 @@ __device__ __forceinline__ void ldg256(const uint4* p, uint4& lo, uint4& hi) {
         : "l"(p));
 }
 
-// ---- TMA bulk-copy staging of every tree's top blocks (cp.async.bulk + mbarrier) ---------------
-// All 128 rows of a CTA cross the same few blocks at the top of a tree, so those blocks are read
-// from shared memory instead of through L1TEX.  One thread issues 1-D bulk copies for the NEXT
-// group of trees into the other half of a double buffer while the CTA walks the current group;
-// completion is tracked by an mbarrier (complete_tx), so no thread ever polls global memory.
-constexpr int TOP_BLOCKS = 21;  // 1 + 4 + 16 blocks = the top 6 levels of a tree (blocks are in BFS order)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(b))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
-    uint32_t ok = 0;
-    int spins = 0;
-    while (!ok) {
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok)
-            : "r"(smem_u32(b)), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1 << 22)) __trap();  // never hang the device on a programming error
-    }
-}
-
 // MODE: 0 hard, 1 hard+weighted, 2 soft, 3 soft+weighted
 template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT, bool TILE>
 __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
@@ -110,9 +78,9 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
         for (int i = tid; i < a.n_features; i += PRED_THREADS) s_absent[i] = a.absent[i];
     }
     __syncthreads();
-    const bool active = tid < rows;  // idle threads of a ragged last tile still take part in the barriers
+    if (tid >= rows) return;
 
-    const CodeT* myrow = TILE ? (tile + (size_t)tid * a.stride) : (gcodes + (size_t)(active ? tid : 0) * a.stride);
+    const CodeT* myrow = TILE ? (tile + (size_t)tid * a.stride) : (gcodes + (size_t)tid * a.stride);
     const int C = a.n_classes;
 
     double acc[CMAX];
@@ -131,77 +99,25 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
     // dependent 32-byte L2 sector serves two tree levels; a child's `next` is the block of its own
     // '>=' child ('<' child = next + 1).  The kernel is bound by those dependent sector fetches
     // (L1 hit rate ~3 %, L2 hit rate 99 %), so halving them is the lever.
-    __shared__ __align__(32) uint4 s_top[2][PRED_ILP][TOP_BLOCKS * 2];
-    __shared__ __align__(8) unsigned long long s_mbar[2];
-    const bool blocked = a.blocks != nullptr;
-    const int n_groups = (a.n_trees + PRED_ILP - 1) / PRED_ILP;
-    auto stage_group = [&](int g) {  // one thread: bulk-copy the top blocks of group g's trees
-        const int buf = g & 1;
-        uint32_t bytes = 0;
-#pragma unroll
-        for (int k = 0; k < PRED_ILP; ++k) {
-            const int t = g * PRED_ILP + k;
-            if (t < a.n_trees) {
-                uint32_t nb = __ldg(&a.root_b[t + 1]) - __ldg(&a.root_b[t]);
-                bytes += (nb < (uint32_t)TOP_BLOCKS ? nb : (uint32_t)TOP_BLOCKS) * 32u;
-            }
-        }
-        mbar_expect_tx(&s_mbar[buf], bytes);
-#pragma unroll
-        for (int k = 0; k < PRED_ILP; ++k) {
-            const int t = g * PRED_ILP + k;
-            if (t < a.n_trees) {
-                const uint32_t rb = __ldg(&a.root_b[t]);
-                uint32_t nb = __ldg(&a.root_b[t + 1]) - rb;
-                if (nb > (uint32_t)TOP_BLOCKS) nb = (uint32_t)TOP_BLOCKS;
-                bulk_g2s(&s_top[buf][k][0], a.blocks + 2 * (size_t)rb, nb * 32u, &s_mbar[buf]);
-            }
-        }
-    };
-    if (blocked) {
-        if (tid == 0) {
-            mbar_init(&s_mbar[0], 1);
-            mbar_init(&s_mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) stage_group(0);
-    }
-    for (int g = 0; g < n_groups; ++g) {
-        const int t0 = g * PRED_ILP;
-        if (blocked) {
-            __syncthreads();  // everyone is done with group g-1, whose buffer group g+1 will overwrite
-            if (tid == 0 && g + 1 < n_groups) stage_group(g + 1);
-            mbar_wait(&s_mbar[g & 1], (uint32_t)((g >> 1) & 1));
-        }
-        if (!active) continue;
-        uint32_t node[PRED_ILP], pay[PRED_ILP], rootb[PRED_ILP];
+    for (int t0 = 0; t0 < a.n_trees; t0 += PRED_ILP) {
+        uint32_t node[PRED_ILP], pay[PRED_ILP];
         bool done[PRED_ILP], seen[PRED_ILP];
 #pragma unroll
         for (int k = 0; k < PRED_ILP; ++k) {
             const bool valid = t0 + k < a.n_trees;
-            node[k] = valid ? (blocked ? __ldg(&a.root_b[t0 + k]) : (uint32_t)__ldg(&a.root[t0 + k])) : 0u;
-            rootb[k] = node[k];
+            node[k] = valid ? (a.blocks ? __ldg(&a.root_b[t0 + k]) : (uint32_t)__ldg(&a.root[t0 + k])) : 0u;
             done[k] = !valid;
             seen[k] = false;
             pay[k] = 0u;
         }
         bool any = true;
-        if (blocked) {
+        if (a.blocks != nullptr) {
             uint4 b0[PRED_ILP], b1[PRED_ILP];
             while (any) {
                 any = false;
 #pragma unroll
                 for (int k = 0; k < PRED_ILP; ++k) {
-                    if (!done[k]) {
-                        const uint32_t rel = node[k] - rootb[k];
-                        if (rel < (uint32_t)TOP_BLOCKS) {  // staged by TMA: shared memory, broadcast-friendly
-                            b0[k] = s_top[g & 1][k][2 * rel];
-                            b1[k] = s_top[g & 1][k][2 * rel + 1];
-                        } else {
-                            ldg256(a.blocks + 2 * (size_t)node[k], b0[k], b1[k]);
-                        }
-                    }
+                    if (!done[k]) ldg256(a.blocks + 2 * (size_t)node[k], b0[k], b1[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < PRED_ILP; ++k) {
@@ -297,7 +213,6 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
         }
     }
 
-    if (!active) return;
     const double denom = (MODE == 0 || MODE == 2) ? (double)a.n_trees : a.score_fsum;
     const int64_t row = row0 + tid;
     int best = 0;
