@@ -99,7 +99,40 @@ class LazyTreeSoA:
         return self._block.host()[self._rank][1][self._start : self._start + self._size]
 
 
-def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int, used_masks=None):
+class PackRecorder:
+    """NCCL path: the survivors of every launch are packed into a device tensor (by the engine's
+    pack kernel), copied to the host from there, and the device copy is kept as the all-gather
+    send buffer -- the node tables never make a host -> device trip."""
+
+    def __init__(self, n_classes: int):
+        self.n_classes = n_classes
+        self.nodes, self.counts, self.n_trees = [], [], 0
+
+    def __call__(self, batch, ids):
+        import torch
+
+        if batch.n_nodes is None:
+            batch.results()
+        sizes = batch.n_nodes[np.asarray(ids, dtype=np.int64)].astype(np.int64)
+        total, C = int(sizes.sum()), self.n_classes
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tn = torch.empty(total * NODE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        tc = torch.empty(total * C * 4, dtype=torch.uint8, device=dev)
+        batch.pack_to_device(ids, tn.data_ptr(), tc.data_ptr())
+        nodes = tn.cpu().numpy().view(NODE_DTYPE)
+        counts = tc.cpu().numpy().view(np.int32).reshape(total, C)
+        self.nodes.append(tn)
+        self.counts.append(tc)
+        self.n_trees += len(ids)
+        out, at = [], 0
+        for s_ in sizes:
+            s_ = int(s_)
+            out.append(TreeSoA(nodes[at : at + s_], counts[at : at + s_]))
+            at += s_
+        return out
+
+
+def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int, used_masks=None, dev_payload=None):
     """All-gather variable-length survivor tables (sizes first, then the padded payload).
     Returns [(soa, score, used_mask)] in rank order; this rank's own trees are returned as they
     are, the others as lazy views of the gathered (device-resident) block."""
@@ -109,11 +142,13 @@ def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classe
     world, rank = td.get_world_size(), td.get_rank()
     dev = _comm_device()
     sizes = np.array([t.n_nodes for t in trees], dtype=np.int64)
-    nodes = np.concatenate([t.nodes for t in trees]) if len(trees) else np.zeros(0, dtype=NODE_DTYPE)
-    counts = np.concatenate([t.counts for t in trees]) if len(trees) else np.zeros((0, n_classes), dtype=np.int32)
+    n_local_nodes = int(sizes.sum())
+    if dev_payload is None:
+        nodes = np.concatenate([t.nodes for t in trees]) if len(trees) else np.zeros(0, dtype=NODE_DTYPE)
+        counts = np.concatenate([t.counts for t in trees]) if len(trees) else np.zeros((0, n_classes), dtype=np.int32)
     sc = np.array([float(s) for s in scores], dtype=np.float64)
     nmask = 0 if used_masks is None else used_masks.shape[1]
-    meta = torch.tensor([len(trees), len(nodes)], dtype=torch.int64, device=dev)
+    meta = torch.tensor([len(trees), n_local_nodes], dtype=torch.int64, device=dev)
     metas_t = [torch.zeros_like(meta) for _ in range(world)]
     td.all_gather(metas_t, meta)
     metas = [tuple(int(x) for x in m.cpu().numpy()) for m in metas_t]
@@ -141,9 +176,20 @@ def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classe
         return buf
 
     packed = np.concatenate([field(sizes, 8), field(sc, 8)] + ([field(used_masks, nmask)] if nmask else [np.zeros(0, dtype=np.uint8)]))
+    def gather_dev(t, nbytes: int):
+        mine = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        mine[: t.numel()] = t
+        out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
+        td.all_gather_into_tensor(out, mine)
+        return out.view(world, mine.numel())
+
     g_small = gather(packed, len(packed)).cpu().numpy()
-    g_nodes = gather(nodes, max_nodes * NODE_DTYPE.itemsize)
-    g_counts = gather(counts, max_nodes * n_classes * 4)
+    if dev_payload is not None:
+        g_nodes = gather_dev(dev_payload[0], max_nodes * NODE_DTYPE.itemsize)
+        g_counts = gather_dev(dev_payload[1], max_nodes * n_classes * 4)
+    else:
+        g_nodes = gather(nodes, max_nodes * NODE_DTYPE.itemsize)
+        g_counts = gather(counts, max_nodes * n_classes * 4)
     block = GatheredBlock(g_nodes, g_counts, metas, n_classes)
     out = []
     for r in range(world):
@@ -161,14 +207,19 @@ def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classe
     return out
 
 
-def _gather_forest(model, local):
+def _gather_forest(model, local, recorder=None):
     nf = len(model.feature_cols)
     masks = np.zeros((len(local), nf), dtype=np.uint8)
     pos = {name: j for j, name in enumerate(model.feature_cols)}
     for i, t in enumerate(local):
         for f in t.used_features:
             masks[i, pos[f]] = 1
-    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks)
+    payload = None
+    if recorder is not None and recorder.n_trees == len(local) and recorder.nodes:
+        import torch
+
+        payload = (torch.cat(recorder.nodes), torch.cat(recorder.counts))
+    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks, payload)
     forest = []
     for soa, score, mask in gathered:
         t = model._wrap(soa, score)
@@ -176,6 +227,14 @@ def _gather_forest(model, local):
         t.used_features = [model.feature_cols[j] for j in np.flatnonzero(mask)]
         forest.append(t)
     return forest
+
+
+def _install_recorder(model):
+    if _td().get_backend() != "nccl":
+        return None
+    rec = PackRecorder(len(model.class_vals))
+    model._tls.pack_hook = rec
+    return rec
 
 
 def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
@@ -186,17 +245,25 @@ def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
     if seeds is not None:
         np.random.seed(seeds[rank])
         _pyrandom.seed(seeds[rank])
-    local = model._fit_slots(hi - lo) if hi > lo else []
-    return _gather_forest(model, local)
+    recorder = _install_recorder(model)
+    try:
+        local = model._fit_slots(hi - lo) if hi > lo else []
+    finally:
+        model._tls.pack_hook = None
+    return _gather_forest(model, local, recorder)
 
 
 def fit_sharded_local(model, n_local: int):
     """Weak-scaling variant used by bench.py: every rank grows ``n_local`` slots from its current
     RNG state, then the survivors are all-gathered (rank order)."""
-    local = model._fit_slots(n_local)
     if not is_distributed():
-        return local
-    return _gather_forest(model, local)
+        return model._fit_slots(n_local)
+    recorder = _install_recorder(model)
+    try:
+        local = model._fit_slots(n_local)
+    finally:
+        model._tls.pack_hook = None
+    return _gather_forest(model, local, recorder)
 
 
 def predict_sharded(model, frame, want_probs: bool):

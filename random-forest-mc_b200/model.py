@@ -497,7 +497,9 @@ class RandomForestMC(BaseRandomForestMC):
             if cid is None:
                 raise AttributeError("'NoneType' object has no attribute 'survived_score'")  # model.py:345
             ids.append(cid)
-        for soa, (_, score) in zip(batch.fetch(ids), chosen):
+        hook = getattr(self._tls, "pack_hook", None)  # rank-sharded fit: keep the packed tables on the device too
+        soas = hook(batch, ids) if (hook is not None and ids) else batch.fetch(ids)
+        for soa, (_, score) in zip(soas, chosen):
             trees_out.append(self._wrap(soa, score))
 
     def _extend_slot(self, p, judge, batch, stream, stats) -> DecisionTreeMC:
