@@ -106,7 +106,7 @@ class PackRecorder:
 
     def __init__(self, n_classes: int):
         self.n_classes = n_classes
-        self.nodes, self.counts, self.n_trees = [], [], 0
+        self.nodes, self.counts, self.sizes, self.n_trees = [], [], [], 0
 
     def __call__(self, batch, ids):
         import torch
@@ -119,17 +119,11 @@ class PackRecorder:
         tn = torch.empty(total * NODE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         tc = torch.empty(total * C * 4, dtype=torch.uint8, device=dev)
         batch.pack_to_device(ids, tn.data_ptr(), tc.data_ptr())
-        nodes = tn.cpu().numpy().view(NODE_DTYPE)
-        counts = tc.cpu().numpy().view(np.int32).reshape(total, C)
         self.nodes.append(tn)
         self.counts.append(tc)
+        self.sizes.append(sizes)
         self.n_trees += len(ids)
-        out, at = [], 0
-        for s_ in sizes:
-            s_ = int(s_)
-            out.append(TreeSoA(nodes[at : at + s_], counts[at : at + s_]))
-            at += s_
-        return out
+        return batch.fetch(ids)  # host copy through the engine's pinned staging
 
 
 def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int, used_masks=None, dev_payload=None):
@@ -209,16 +203,25 @@ def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classe
 
 def _gather_forest(model, local, recorder=None):
     nf = len(model.feature_cols)
-    masks = np.zeros((len(local), nf), dtype=np.uint8)
-    pos = {name: j for j, name in enumerate(model.feature_cols)}
-    for i, t in enumerate(local):
-        for f in t.used_features:
-            masks[i, pos[f]] = 1
     payload = None
     if recorder is not None and recorder.n_trees == len(local) and recorder.nodes:
         import torch
 
         payload = (torch.cat(recorder.nodes), torch.cat(recorder.counts))
+        # which features each tree splits on, read off the device copy of the node tables
+        feat = payload[0].view(torch.int32).view(-1, NODE_DTYPE.itemsize // 4)[:, 0].long()
+        sizes = torch.from_numpy(np.concatenate(recorder.sizes)).to(feat.device)
+        owner = torch.repeat_interleave(torch.arange(len(local), device=feat.device), sizes)
+        hit = torch.zeros(len(local) * nf, dtype=torch.uint8, device=feat.device)
+        sel = feat >= 0
+        hit[owner[sel] * nf + feat[sel]] = 1
+        masks = hit.view(len(local), nf).cpu().numpy()
+    else:
+        masks = np.zeros((len(local), nf), dtype=np.uint8)
+        pos = {name: j for j, name in enumerate(model.feature_cols)}
+        for i, t in enumerate(local):
+            for f in t.used_features:
+                masks[i, pos[f]] = 1
     gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks, payload)
     forest = []
     for soa, score, mask in gathered:

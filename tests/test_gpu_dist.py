@@ -31,11 +31,23 @@ m.device = local
 m.rank_seeds = [1000, 1001]
 m.fitParallel(g["frame"].copy(), disable_progress_bar=True)
 (lo, hi), labels = dist.predict_sharded(m, g["frames"]["nan"], want_probs=False)
-out = dict(trees=[t.data for t in m.data], scores=[float(s) for s in m.survived_scores], lo=lo, hi=hi, labels=labels)
+used = [sorted(t.used_features) for t in m.data]  # from the gathered masks, before any table is materialised
+out = dict(used=used, trees=[t.data for t in m.data], scores=[float(s) for s in m.survived_scores], lo=lo, hi=hi, labels=labels)
 with open(os.path.join({tmp!r}, "rank%d.pkl" % td.get_rank()), "wb") as f:
     pickle.dump(out, f)
 td.destroy_process_group()
 """
+
+
+def _split_features(tree):
+    seen, todo = set(), [tree]
+    while todo:
+        node = todo.pop()
+        name = next(iter(node))
+        if name != "leaf":
+            seen.add(name)
+            todo += [node[name]["split"]["<"], node[name]["split"][">="]]
+    return seen
 
 
 def test_sharded_fit_over_nccl_world2():
@@ -69,6 +81,8 @@ def test_sharded_fit_over_nccl_world2():
         assert out[r]["scores"] == want_scores
         for a, b in zip(out[r]["trees"], want_trees):
             assert tree_diff(a, b) is None
+        for u, b in zip(out[r]["used"], want_trees):
+            assert u == sorted(_split_features(b))
     fr = g["frames"]["nan"]
     want = orc.forest_labels(want_trees, want_scores, g["class_vals"], fr, False, False)
     assert out[0]["labels"] + out[1]["labels"] == want
