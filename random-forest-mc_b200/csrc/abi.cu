@@ -11,10 +11,11 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
 // Device memory comes from a small caching allocator: a fit makes one batch per plan with the
-// same gigabyte-sized scratch and output buffers, and cudaMalloc/cudaFree of those costs tens of
-// milliseconds per batch.  Blocks >= 1 MiB are kept per device on release and handed out again to
-// requests of similar size.  Every release in this file happens after the work that used the
-// block has been synchronised.
+// same scratch and output buffers, and cudaMalloc/cudaFree cost milliseconds each -- cudaFree also
+// synchronises the whole device, which serialises host threads that feed the GPU through their own
+// streams.  Every block is kept per device on release and handed out again to a request of similar
+// size (small requests are rounded to a power of two so they always find a match).  Every release
+// in this file happens after the work that used the block has been synchronised.
 struct DevCache {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
@@ -22,8 +23,15 @@ struct DevCache {
 };
 static std::mutex g_mem_mu;
 static std::map<int, DevCache> g_mem;
-constexpr size_t CACHE_MIN_BLOCK = 1u << 20;
+constexpr size_t CACHE_SMALL = 1u << 20;  // below this: power-of-two size classes
 constexpr size_t CACHE_CAP = 48ull << 30;
+
+static size_t size_class(size_t bytes) {
+    if (bytes >= CACHE_SMALL) return (bytes + 511) & ~(size_t)511;
+    size_t c = 512;
+    while (c < bytes) c <<= 1;
+    return c;
+}
 
 static void flush_cache_locked(DevCache& dc) {
     for (auto& kv : dc.free_blocks) cudaFree(kv.second);
@@ -34,9 +42,10 @@ static void flush_cache_locked(DevCache& dc) {
 static cudaError_t dev_alloc(void** p, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lk(g_mem_mu);
-    DevCache& dc = g_mem[dev];
-    if (bytes >= CACHE_MIN_BLOCK) {
+    bytes = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        DevCache& dc = g_mem[dev];
         auto it = dc.free_blocks.lower_bound(bytes);
         if (it != dc.free_blocks.end() && it->first <= bytes + bytes / 2) {
             *p = it->second;
@@ -46,7 +55,9 @@ static cudaError_t dev_alloc(void** p, size_t bytes) {
             return cudaSuccess;
         }
     }
-    cudaError_t e = cudaMalloc(p, bytes);
+    cudaError_t e = cudaMalloc(p, bytes);  // outside the lock: other host threads keep allocating from the cache
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    DevCache& dc = g_mem[dev];
     if (e != cudaSuccess) {
         cudaGetLastError();
         flush_cache_locked(dc);
@@ -60,21 +71,21 @@ static void release(void* p) {
     if (!p) return;
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lk(g_mem_mu);
-    DevCache& dc = g_mem[dev];
-    auto it = dc.live.find(p);
-    if (it == dc.live.end()) {
-        cudaFree(p);
-        return;
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        DevCache& dc = g_mem[dev];
+        auto it = dc.live.find(p);
+        if (it != dc.live.end()) {
+            const size_t bytes = it->second;
+            dc.live.erase(it);
+            if (dc.cached + bytes <= CACHE_CAP) {
+                dc.free_blocks.emplace(bytes, p);
+                dc.cached += bytes;
+                return;
+            }
+        }
     }
-    const size_t bytes = it->second;
-    dc.live.erase(it);
-    if (bytes >= CACHE_MIN_BLOCK && dc.cached + bytes <= CACHE_CAP) {
-        dc.free_blocks.emplace(bytes, p);
-        dc.cached += bytes;
-    } else {
-        cudaFree(p);
-    }
+    cudaFree(p);
 }
 
 template <typename T>
@@ -93,24 +104,52 @@ static int reserve(T** dst, size_t count) {
     return 0;
 }
 
-// One pinned staging buffer per host thread for device -> host survivor export.
-static thread_local void* g_pin = nullptr;
-static thread_local size_t g_pin_cap = 0;
-static void* pinned_staging(size_t bytes) {
-    if (bytes > g_pin_cap) {
-        if (g_pin) cudaFreeHost(g_pin);
-        g_pin = nullptr;
-        g_pin_cap = 0;
-        size_t want = bytes + bytes / 4;
-        if (cudaHostAlloc(&g_pin, want, cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            g_pin = nullptr;
-            return nullptr;
+// Pinned staging buffers for device -> host survivor export come from a process-wide pool: the host
+// threads of a multi-stream fit are short-lived, and page-locking tens of megabytes per thread per
+// fit costs more than the copy it speeds up.
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void*> g_pin_free;
+static size_t g_pin_cached = 0;
+constexpr size_t PIN_CAP = 8ull << 30;
+
+struct PinnedLease {
+    void* p = nullptr;
+    size_t cap = 0;
+    explicit PinnedLease(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(g_pin_mu);
+            auto it = g_pin_free.lower_bound(bytes);
+            if (it != g_pin_free.end() && it->first <= 2 * bytes + (1u << 20)) {
+                p = it->second;
+                cap = it->first;
+                g_pin_cached -= cap;
+                g_pin_free.erase(it);
+                return;
+            }
         }
-        g_pin_cap = want;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return;
+        }
+        cap = want;
     }
-    return g_pin;
-}
+    ~PinnedLease() {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> lk(g_pin_mu);
+            if (g_pin_cached + cap <= PIN_CAP) {
+                g_pin_free.emplace(cap, p);
+                g_pin_cached += cap;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+    PinnedLease(const PinnedLease&) = delete;
+    PinnedLease& operator=(const PinnedLease&) = delete;
+};
 }  // namespace rfmc
 
 using namespace rfmc;
@@ -463,7 +502,8 @@ int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_
     if (!rc && !dst_on_device) {
         // device -> pinned staging (full-rate DMA) -> caller's pageable buffers
         const size_t nb = total * sizeof(rfmc_node), cb = total * C * sizeof(int32_t);
-        uint8_t* pin = (uint8_t*)pinned_staging(nb + cb);
+        PinnedLease lease(nb + cb);
+        uint8_t* pin = (uint8_t*)lease.p;
         void* h_nodes = pin ? (void*)pin : (void*)nodes_out;
         void* h_counts = pin ? (void*)(pin + nb) : (void*)counts_out;
         if (cudaMemcpyAsync(h_nodes, d_nodes, nb, cudaMemcpyDeviceToHost, st) != cudaSuccess ||

@@ -88,6 +88,59 @@ RFMC_CLONES void mt_temper(const uint32_t* k, uint32_t* out) {
     }
 }
 
+#ifdef RFMC_HAVE_AVX2
+// AVX-512: next block and its tempered copy in one pass (the new words are tempered in registers).
+__attribute__((target("avx512f"))) void mt_regen_temper_avx512(uint32_t* k, uint32_t* out) {
+    const __m512i up = _mm512_set1_epi32((int)UPPER_MASK), one = _mm512_set1_epi32(1), va = _mm512_set1_epi32((int)MATRIX_A);
+    const __m512i c1 = _mm512_set1_epi32((int)0x9d2c5680u), c2 = _mm512_set1_epi32((int)0xefc60000u);
+#define RFMC_MT_STEP(i, from)                                                                              \
+    {                                                                                                      \
+        const __m512i a = _mm512_loadu_si512(k + (i)), b = _mm512_loadu_si512(k + (i) + 1);                 \
+        const __m512i m = _mm512_loadu_si512(k + (from));                                                  \
+        const __m512i y = _mm512_ternarylogic_epi32(up, a, b, 0xCA); /* (a & UPPER) | (b & LOWER) */        \
+        __m512i t = _mm512_xor_si512(m, _mm512_srli_epi32(y, 1));                                          \
+        t = _mm512_mask_xor_epi32(t, _mm512_test_epi32_mask(y, one), t, va);                               \
+        _mm512_storeu_si512(k + (i), t);                                                                   \
+        t = _mm512_xor_si512(t, _mm512_srli_epi32(t, 11));                                                 \
+        t = _mm512_ternarylogic_epi32(t, _mm512_slli_epi32(t, 7), c1, 0x78); /* t ^ ((t << 7) & c1) */     \
+        t = _mm512_ternarylogic_epi32(t, _mm512_slli_epi32(t, 15), c2, 0x78);                              \
+        t = _mm512_xor_si512(t, _mm512_srli_epi32(t, 18));                                                 \
+        _mm512_storeu_si512(out + (i), t);                                                                 \
+    }
+#define RFMC_MT_SCALAR(i, from, next)                                  \
+    {                                                                  \
+        uint32_t y = (k[(i)] & UPPER_MASK) | (k[(next)] & LOWER_MASK); \
+        y = k[(from)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);       \
+        k[(i)] = y;                                                    \
+        y ^= (y >> 11);                                                \
+        y ^= (y << 7) & 0x9d2c5680u;                                   \
+        y ^= (y << 15) & 0xefc60000u;                                  \
+        y ^= (y >> 18);                                                \
+        out[(i)] = y;                                                  \
+    }
+    int i = 0;
+    for (; i + 16 <= MT_N - MT_M; i += 16) RFMC_MT_STEP(i, i + MT_M)
+    for (; i < MT_N - MT_M; ++i) RFMC_MT_SCALAR(i, i + MT_M, i + 1)
+    for (; i + 16 <= MT_N - 1; i += 16) RFMC_MT_STEP(i, i + (MT_M - MT_N))  // reads words written >= 227 - 15 steps ago
+    for (; i < MT_N - 1; ++i) RFMC_MT_SCALAR(i, i + (MT_M - MT_N), i + 1)
+    RFMC_MT_SCALAR(MT_N - 1, MT_M - 1, 0)
+#undef RFMC_MT_STEP
+#undef RFMC_MT_SCALAR
+}
+#endif
+
+inline void mt_next_block(uint32_t* k, uint32_t* out) {
+#ifdef RFMC_HAVE_AVX2
+    static const bool avx512 = __builtin_cpu_supports("avx512f");
+    if (avx512) {
+        mt_regen_temper_avx512(k, out);
+        return;
+    }
+#endif
+    mt_regen(k);
+    mt_temper(k, out);
+}
+
 // A ring of MT19937 blocks filled by a producer thread: block b+1 = regen(block b), tempered.  The
 // stream itself does not depend on how it is consumed, so generation runs ahead of the rejection
 // walk; the consumer's end state is simply (untempered key of its current block, position).
@@ -110,8 +163,7 @@ struct BlockRing {
                 }
                 uint32_t* k = key[b % K];
                 memcpy(k, key[(b - 1) % K], sizeof(key[0]));
-                mt_regen(k);
-                mt_temper(k, tw[b % K]);
+                mt_next_block(k, tw[b % K]);
                 produced.store(b + 1, std::memory_order_release);
             }
         });
@@ -154,8 +206,7 @@ struct Stream {  // numpy's MT19937 state + the tempered copy of the current blo
             key = ring->key[block % BlockRing::K];
             tw = ring->tw[block % BlockRing::K];
         } else {
-            mt_regen(key);
-            mt_temper(key, own_tw);
+            mt_next_block(key, own_tw);
         }
         pos = 0;
     }
@@ -272,72 +323,140 @@ __attribute__((target("avx2"))) void reject_avx2(Stream& st, uint32_t mask, int6
     }
 }
 
-// AVX-512: 64 words per loop-carried update of i; accepted lanes leave through vpcompressd.
-// Levels whose mask is too small for a 64-word window (a neighbour-dependent lane would be common)
-// and the tail of each level go through the AVX2 path.
+// AVX-512: up to 64 words per loop-carried update of i (a block of 624 words is 9 groups of four
+// vectors and one of three); accepted lanes leave through vpcompressd.  The window shrinks with the
+// mask so that a neighbour-dependent lane stays rare; the last few draws of a level are left to the
+// paths below.
 __attribute__((target("avx512f,avx2"))) void reject_avx512(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uint32_t* A,
                                                             int64_t& k) {
     const __m512i vmask = _mm512_set1_epi32((int)mask);
+    const int max_nv = mask >= 131071 ? 4 : (mask >= 32767 ? 2 : 1);
     while (i > lo) {
         if (st.pos == MT_N) st.refill();
-        if (!(MT_N - st.pos >= 64 && i - 64 >= lo)) break;
-        const uint32_t* w = st.tw + st.pos;
-        const __m512i vi = _mm512_set1_epi32((int)i), vs = _mm512_set1_epi32((int)(i - 63));
-        const __m512i u0 = _mm512_and_si512(_mm512_loadu_si512(w), vmask);
-        const __m512i u1 = _mm512_and_si512(_mm512_loadu_si512(w + 16), vmask);
-        const __m512i u2 = _mm512_and_si512(_mm512_loadu_si512(w + 32), vmask);
-        const __m512i u3 = _mm512_and_si512(_mm512_loadu_si512(w + 48), vmask);
-        const __mmask16 g0 = _mm512_cmpgt_epi32_mask(u0, vi), g1 = _mm512_cmpgt_epi32_mask(u1, vi);
-        const __mmask16 g2 = _mm512_cmpgt_epi32_mask(u2, vi), g3 = _mm512_cmpgt_epi32_mask(u3, vi);
-        const unsigned amb = (unsigned)(g0 ^ _mm512_cmpgt_epi32_mask(u0, vs)) | (unsigned)(g1 ^ _mm512_cmpgt_epi32_mask(u1, vs)) |
-                             (unsigned)(g2 ^ _mm512_cmpgt_epi32_mask(u2, vs)) | (unsigned)(g3 ^ _mm512_cmpgt_epi32_mask(u3, vs));
-        if (amb) {
-            reject_scalar(st, mask, lo, i, A, k, 64);
+        const int avail = MT_N - st.pos;
+        if (avail < 16) {
+            reject_scalar(st, mask, lo, i, A, k, avail);
             continue;
         }
-        const __mmask16 m0 = (__mmask16)~g0, m1 = (__mmask16)~g1, m2 = (__mmask16)~g2, m3 = (__mmask16)~g3;
-        const int c0 = __builtin_popcount((unsigned)m0), c1 = __builtin_popcount((unsigned)m1);
-        const int c2 = __builtin_popcount((unsigned)m2), c3 = __builtin_popcount((unsigned)m3);
+        int nv = avail >> 4;
+        if (nv > max_nv) nv = max_nv;
+        const int W = nv << 4;
+        if (i - W < lo) break;
+        const uint32_t* w = st.tw + st.pos;
+        const __m512i vi = _mm512_set1_epi32((int)i), vs = _mm512_set1_epi32((int)(i - (W - 1)));
+        __m512i u[4];
+        __mmask16 g[4];
+        unsigned amb = 0;
+#pragma GCC unroll 4
+        for (int v = 0; v < 4; ++v) {
+            if (v < nv) {
+                u[v] = _mm512_and_si512(_mm512_loadu_si512(w + 16 * v), vmask);
+                g[v] = _mm512_cmpgt_epi32_mask(u[v], vi);
+                amb |= (unsigned)(g[v] ^ _mm512_cmpgt_epi32_mask(u[v], vs));
+            }
+        }
+        if (amb) {
+            reject_scalar(st, mask, lo, i, A, k, W);
+            continue;
+        }
         uint32_t* dst = A + k;
-        _mm512_storeu_si512(dst, _mm512_maskz_compress_epi32(m0, u0));
-        _mm512_storeu_si512(dst + c0, _mm512_maskz_compress_epi32(m1, u1));
-        _mm512_storeu_si512(dst + c0 + c1, _mm512_maskz_compress_epi32(m2, u2));
-        _mm512_storeu_si512(dst + c0 + c1 + c2, _mm512_maskz_compress_epi32(m3, u3));
-        const int c = c0 + c1 + c2 + c3;
+        int c = 0;
+#pragma GCC unroll 4
+        for (int v = 0; v < 4; ++v) {
+            if (v < nv) {
+                const __mmask16 m = (__mmask16)~g[v];
+                _mm512_storeu_si512(dst + c, _mm512_maskz_compress_epi32(m, u[v]));
+                c += __builtin_popcount((unsigned)m);
+            }
+        }
         k += c;
         i -= c;
-        st.pos += 64;
+        st.pos += W;
     }
 }
 
-// Ascending scan over steps q >= size (descending k): 8 membership tests per gather.
-__attribute__((target("avx2"))) void resolve_avx2(const uint32_t* A, int64_t n, int64_t size, uint32_t* live,
-                                                    int32_t* owner, int32_t* head) {
-    int64_t k = n - 1 - size;  // q = n-1-k
-    const __m256i one = _mm256_set1_epi32(1), m31 = _mm256_set1_epi32(31);
-    while (k >= 0) {
-        if (k >= 7) {
-            const __m256i j = _mm256_loadu_si256((const __m256i*)(A + k - 7));
-            const __m256i g = _mm256_i32gather_epi32((const int*)live, _mm256_srli_epi32(j, 5), 4);
-            const __m256i bit = _mm256_and_si256(_mm256_srlv_epi32(g, _mm256_and_si256(j, m31)), one);
-            if (_mm256_testz_si256(bit, bit)) {
-                k -= 8;
-                continue;
-            }
-        }
-        const int64_t stop = k >= 7 ? k - 8 : -1;
-        for (; k > stop; --k) {
-            const uint32_t j = A[k];
-            if ((live[j >> 5] >> (j & 31)) & 1u) {
-                const int64_t q = n - 1 - k;
-                const int32_t p = owner[j];
-                live[j >> 5] &= ~(1u << (j & 31));
-                live[q >> 5] |= 1u << (q & 31);
-                owner[q] = p;
-                head[p] = (int32_t)q;
-            }
-        }
+// Ascending scan over steps q >= size (descending k).  About size * ln(n / size) steps hit a live
+// position, and a hit rewrites the bitmap the next membership test reads: testing and updating in
+// one loop costs a pipeline flush per hit (a gather cannot take its data from the store buffer).
+// So the scan runs in chunks: the vector pass tests a whole chunk against the bitmap as it was when
+// the chunk began and only appends suspects -- bit set then, or j inside the chunk's own step
+// range (the only positions that can become live meanwhile) -- to a list; the scalar pass then
+// applies the suspects in order against the current bitmap.  Chunks grow with q so that the second
+// kind of suspect stays rare.
+inline void apply_hit(const uint32_t* A, int64_t n, int64_t k, uint32_t* live, int32_t* owner, int32_t* head) {
+    const uint32_t j = A[k];
+    if ((live[j >> 5] >> (j & 31)) & 1u) {
+        const int64_t q = n - 1 - k;
+        const int32_t p = owner[j];
+        live[j >> 5] &= ~(1u << (j & 31));
+        live[q >> 5] |= 1u << (q & 31);
+        owner[q] = p;
+        head[p] = (int32_t)q;
     }
+}
+
+inline int64_t chunk_len(int64_t q0) {
+    int64_t c = q0 / 64;
+    c = c < 256 ? 256 : (c > 8192 ? 8192 : c);
+    return c & ~(int64_t)15;
+}
+
+__attribute__((target("avx512f"))) void resolve_avx512(const uint32_t* A, int64_t n, int64_t size, uint32_t* live,
+                                                        int32_t* owner, int32_t* head, int32_t* suspects) {
+    int64_t k = n - 1 - size;  // q = n-1-k
+    const __m512i m31 = _mm512_set1_epi32(31), one = _mm512_set1_epi32(1);
+    const __m512i rev = _mm512_setr_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    while (k >= 15) {
+        const int64_t q0 = n - 1 - k;
+        int64_t len = chunk_len(q0);
+        if (len > k + 1) len = (k + 1) & ~(int64_t)15;
+        if (len == 0) break;
+        const __m512i vq0 = _mm512_set1_epi32((int)q0);
+        int cnt = 0;
+        for (int64_t kk = k; kk > k - len; kk -= 16) {
+            // lane 0 = A[kk] (first in scan order)
+            const __m512i j = _mm512_permutexvar_epi32(rev, _mm512_loadu_si512((const void*)(A + kk - 15)));
+            const __m512i g = _mm512_i32gather_epi32(_mm512_srli_epi32(j, 5), (const int*)live, 4);
+            const __mmask16 hit = _mm512_test_epi32_mask(_mm512_srlv_epi32(g, _mm512_and_si512(j, m31)), one);
+            const __mmask16 late = _mm512_cmpge_epu32_mask(j, vq0);
+            const __mmask16 m = hit | late;
+            const __m512i ks = _mm512_sub_epi32(_mm512_set1_epi32((int)kk), _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15));
+            _mm512_mask_compressstoreu_epi32(suspects + cnt, m, ks);
+            cnt += __builtin_popcount((unsigned)m);
+        }
+        for (int t = 0; t < cnt; ++t) apply_hit(A, n, suspects[t], live, owner, head);
+        k -= len;
+    }
+    for (; k >= 0; --k) apply_hit(A, n, k, live, owner, head);
+}
+
+__attribute__((target("avx2"))) void resolve_avx2(const uint32_t* A, int64_t n, int64_t size, uint32_t* live,
+                                                    int32_t* owner, int32_t* head, int32_t* suspects) {
+    int64_t k = n - 1 - size;
+    const __m256i m31 = _mm256_set1_epi32(31);
+    while (k >= 15) {
+        const int64_t q0 = n - 1 - k;
+        int64_t len = chunk_len(q0);
+        if (len > k + 1) len = (k + 1) & ~(int64_t)15;
+        if (len == 0) break;
+        const __m256i vq0 = _mm256_set1_epi32((int)q0 - 1);
+        int cnt = 0;
+        for (int64_t kk = k; kk > k - len; kk -= 8) {
+            const __m256i j = _mm256_loadu_si256((const __m256i*)(A + kk - 7));  // lane 7 = A[kk]
+            const __m256i g = _mm256_i32gather_epi32((const int*)live, _mm256_srli_epi32(j, 5), 4);
+            const __m256i sh = _mm256_sllv_epi32(g, _mm256_sub_epi32(m31, _mm256_and_si256(j, m31)));
+            const __m256i late = _mm256_cmpgt_epi32(j, vq0);  // j < 2^31 here
+            unsigned m = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_or_si256(sh, late)));
+            while (m) {  // highest lane first = scan order
+                const int L = 31 - __builtin_clz(m);
+                suspects[cnt++] = (int32_t)(kk - 7 + L);
+                m &= ~(1u << L);
+            }
+        }
+        for (int t = 0; t < cnt; ++t) apply_hit(A, n, suspects[t], live, owner, head);
+        k -= len;
+    }
+    for (; k >= 0; --k) apply_hit(A, n, k, live, owner, head);
 }
 #endif
 
@@ -377,7 +496,7 @@ void draw_accepted(Stream& st, int64_t n, uint32_t* A) {
     while (i >= 1) {
         const int64_t lo = (int64_t)(mask >> 1);  // this mask serves i in (lo, mask]
 #ifdef RFMC_HAVE_AVX2
-        if (avx512 && mask >= 131071) reject_avx512(st, mask, lo, i, A, k);  // leaves a tail for the paths below
+        if (avx512 && mask >= 2047) reject_avx512(st, mask, lo, i, A, k);  // leaves the end of the level to the paths below
         if (avx2 && mask >= 1023)
             reject_avx2(st, mask, lo, i, A, k);
         else
@@ -389,7 +508,7 @@ void draw_accepted(Stream& st, int64_t n, uint32_t* A) {
 
 struct Scratch {
     std::vector<uint32_t> A, live;
-    std::vector<int32_t> owner, head;
+    std::vector<int32_t> owner, head, suspects;
 };
 thread_local Scratch g_s;
 
@@ -411,9 +530,14 @@ const int32_t* resolve_prefix(const uint32_t* A, int64_t n, int64_t size) {
     }
     if (n >= 2) {
 #ifdef RFMC_HAVE_AVX2
-        if (have_avx2())
-            resolve_avx2(A, n, size, live, owner, head);
-        else
+        if (have_avx2()) {
+            if (s.suspects.size() < 8192 + 64) s.suspects.resize(8192 + 64);
+            static const bool avx512 = __builtin_cpu_supports("avx512f");
+            if (avx512)
+                resolve_avx512(A, n, size, live, owner, head, s.suspects.data());
+            else
+                resolve_avx2(A, n, size, live, owner, head, s.suspects.data());
+        } else
 #endif
             resolve_scalar(A, n, size, live, owner, head);
         for (int64_t q = size - 1; q >= 1; --q) {  // steps i < size act inside the prefix only

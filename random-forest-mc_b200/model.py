@@ -464,7 +464,8 @@ class RandomForestMC(BaseRandomForestMC):
                 stream = engine.stream_create(self.device)  # each host stream keeps its own launches in flight
                 self._tls.np_rng = np.random.RandomState(int(seeds[r]))
                 self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
-                self._tls.rng_flags = 1  # one resolve helper per stream, no producer thread
+                # one resolve helper per stream while there are cores for it; no producer thread
+                self._tls.rng_flags = 1 if 2 * k <= (os.cpu_count() or 1) else 0
                 lo, hi = shard_bounds(n_slots, r, k)
                 parts[r] = self._fit_slots(hi - lo, stream) if hi > lo else []
                 stats[r] = getattr(self._tls, "last_stats", None)
@@ -583,7 +584,7 @@ class RandomForestMC(BaseRandomForestMC):
         if dist.is_distributed():
             Forest = dist.fit_sharded(self)
         else:
-            k = max_workers or min(8, os.cpu_count() or 1)
+            k = max_workers or min(16, os.cpu_count() or 1)  # the reference's pool defaults to one worker per core
             k = max(1, min(int(k), self.n_trees))
             seeds = getattr(self, "worker_seeds", None)
             if seeds is None:  # derived from the global stream: reproducible under np.random.seed(s)
