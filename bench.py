@@ -333,57 +333,47 @@ def run_b200(args):
     total_nodes = int(n_nodes.sum())
 
     # ---- fit, end to end through the public API ----
-    def e2e_fit():
+    # Two numbers.  `e2e` (headline) is fitParallel: the slots shared over k independent host RNG
+    # streams per rank -- the semantics of the reference's process pool and of the CPU arm, which
+    # also runs one independent stream per core.  `e2e_fit_serial` is fit(): ONE stream, every draw
+    # in the serial reference's order (its floor is the host walk over that stream).
+    cores = os.cpu_count() or 1
+    k_streams = max(1, min(args.host_streams or max(1, min(16, cores) // world), cores, args.n_trees))
+
+    def e2e_fit(k):
         model.data, model.survived_scores = [], []
         np.random.seed(4321 + rank)
         random.seed(4321 + rank)
+        seeds = [9000 + 100 * rank + r for r in range(k)]
         torch.cuda.synchronize()
         t = time.perf_counter()
         if world > 1:
-            forest = dist.fit_sharded_local(model, args.n_trees)
+            forest = dist.fit_sharded_local(model, args.n_trees, k, seeds)
+        elif k > 1:
+            forest = model._fit_slots_streams(args.n_trees, seeds)
         else:
             forest = model._fit_slots(args.n_trees, stream)
         torch.cuda.synchronize()
         return time.perf_counter() - t, forest
 
-    def e2e_fit_parallel(k):
-        model.data, model.survived_scores = [], []
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        forest_p = model._fit_slots_streams(args.n_trees, [9000 + 100 * rank + r for r in range(k)])
-        torch.cuda.synchronize()
-        return time.perf_counter() - t, forest_p
-
-    e2e_fit()  # warm-up
-    barrier()
-    e2e_s, e2e_cands, forest, e2e_each = 0.0, 0, None, []
-    for _ in range(args.e2e_steps):
-        dt, forest = e2e_fit()
-        e2e_s += dt
-        e2e_each.append(round(dt * 1e3, 2))
-        print("e2e step", round(dt * 1e3, 1), "ms", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in model.fit_stats.items()}, file=sys.stderr)
-        e2e_cands += model.fit_stats["candidates_grown"]
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
-    stats = dict(model.fit_stats)
-    # fitParallel on this GPU: the slots shared over k independent host RNG streams (threads)
-    k_streams = max(1, min(args.host_streams, os.cpu_count() or 1, args.n_trees))
-    par = None
-    if world == 1 and k_streams > 1:
-        e2e_fit_parallel(k_streams)
-        par_each, par_cands = [], 0
+    def e2e_run(k):
+        e2e_fit(k)  # warm-up
+        barrier()
+        total, cands, each, forest = 0.0, 0, [], None
         for _ in range(args.e2e_steps):
-            dt, _fp = e2e_fit_parallel(k_streams)
-            par_each.append(round(dt * 1e3, 2))
-            par_cands += model.fit_stats["candidates_grown"]
-        par = {
-            "value": par_cands / (sum(par_each) / 1e3),
-            "unit": "candidate-trees/s",
-            "host_streams": k_streams,
-            "ms_each": par_each,
-            "api": "RandomForestMC.fitParallel(max_workers=k): k host threads with independent seeded RNG streams (the "
-            "semantics of the reference's process pool and of the CPU arm) feeding one GPU",
-        }
+            dt, forest = e2e_fit(k)
+            total += dt
+            each.append(round(dt * 1e3, 2))
+            print("e2e step", k, "streams", round(dt * 1e3, 1), "ms", {q: (round(v, 4) if isinstance(v, float) else v) for q, v in model.fit_stats.items()}, file=sys.stderr)
+            cands += model.fit_stats["candidates_grown"]
+        barrier()
+        return max_over_ranks(total), cands, each, forest, dict(model.fit_stats)
+
+    ser_s, ser_cands, ser_each, forest, ser_stats = e2e_run(1)
+    if k_streams > 1:
+        e2e_s, e2e_cands, e2e_each, forest, stats = e2e_run(k_streams)
+    else:
+        e2e_s, e2e_cands, e2e_each, stats = ser_s, ser_cands, ser_each, ser_stats
     surv_nodes = sum(t.soa.n_nodes for t in forest[: args.n_trees])
     h2d = int(args.n_trees * (batch.n_train + batch.n_val) * 4 + sum(len(f) for f in feats) * 2 + n_cand * 8)
     d2h = int(n_cand * 8 + surv_nodes * (24 + 4 * C))
@@ -486,13 +476,23 @@ def run_b200(args):
                 "unit": "candidate-trees/s",
                 "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
-                "api": "RandomForestMC fit loop (_fit_slots): host RNG draws + H2D + grow/score kernel + D2H scores + survivor tables"
+                "api": f"RandomForestMC.fitParallel: {k_streams} independent seeded host RNG stream(s) per rank (the semantics of the "
+                "reference's process pool and of the CPU arm): host RNG draws + H2D + grow/score kernel + D2H scores + survivor tables"
                 + ("; + all-gather of survivors" if world > 1 else ""),
+                "host_streams_per_rank": k_streams,
                 "ms_per_step": e2e_s / args.e2e_steps * 1e3,
                 "ms_each_rank0": e2e_each,
                 "fit_stats": stats,
             },
-            "e2e_fitParallel": par,
+            "e2e_fit_serial": {
+                "value": world * ser_cands / ser_s,
+                "unit": "candidate-trees/s",
+                "api": "RandomForestMC.fit loop (_fit_slots): ONE RNG stream per rank, every draw in the serial reference's order"
+                + ("; + all-gather of survivors" if world > 1 else ""),
+                "ms_per_step": ser_s / args.e2e_steps * 1e3,
+                "ms_each_rank0": ser_each,
+                "fit_stats": ser_stats,
+            },
             "gpu_launches": int(launches) + args.steps,
             "roofline": {
                 "kernel": "rfmc::grow_kernel",
@@ -564,7 +564,7 @@ def main():
     ap.add_argument("--predict-rows", type=int, default=1_000_000, dest="predict_rows")
     ap.add_argument("--e2e-steps", type=int, default=2, dest="e2e_steps")
     ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
-    ap.add_argument("--host-streams", type=int, default=8, dest="host_streams")
+    ap.add_argument("--host-streams", type=int, default=0, dest="host_streams", help="host RNG streams per rank for the e2e fit (0 = min(16, cores) / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.predict_rows = min(args.predict_rows, args.rows)

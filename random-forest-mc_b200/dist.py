@@ -104,8 +104,9 @@ class PackRecorder:
     pack kernel), copied to the host from there, and the device copy is kept as the all-gather
     send buffer -- the node tables never make a host -> device trip."""
 
-    def __init__(self, n_classes: int):
+    def __init__(self, n_classes: int, device: int = 0):
         self.n_classes = n_classes
+        self.device = device
         self.nodes, self.counts, self.sizes, self.n_trees = [], [], [], 0
 
     def __call__(self, batch, ids):
@@ -115,7 +116,7 @@ class PackRecorder:
             batch.results()
         sizes = batch.n_nodes[np.asarray(ids, dtype=np.int64)].astype(np.int64)
         total, C = int(sizes.sum()), self.n_classes
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device("cuda", self.device)
         tn = torch.empty(total * NODE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         tc = torch.empty(total * C * 4, dtype=torch.uint8, device=dev)
         batch.pack_to_device(ids, tn.data_ptr(), tc.data_ptr())
@@ -235,9 +236,39 @@ def _gather_forest(model, local, recorder=None):
 def _install_recorder(model):
     if _td().get_backend() != "nccl":
         return None
-    rec = PackRecorder(len(model.class_vals))
+    rec = PackRecorder(len(model.class_vals), int(getattr(model, "device", 0) or 0))
     model._tls.pack_hook = rec
     return rec
+
+
+def _merge_recorders(recs):
+    """Recorders of the host streams of one rank, in worker order (the order of the local forest)."""
+    recs = [r for r in recs if r is not None]
+    if not recs:
+        return None
+    out = PackRecorder(recs[0].n_classes, recs[0].device)
+    for r in recs:
+        out.nodes += r.nodes
+        out.counts += r.counts
+        out.sizes += r.sizes
+        out.n_trees += r.n_trees
+    return out
+
+
+def _fit_local(model, n_local: int, host_streams: int, seeds):
+    """This rank's slots: the serial loop, or ``host_streams`` independent host RNG streams."""
+    if host_streams <= 1 or n_local < 2:
+        recorder = _install_recorder(model)
+        try:
+            local = model._fit_slots(n_local) if n_local > 0 else []
+        finally:
+            model._tls.pack_hook = None
+        return local, recorder
+    nccl = _td().get_backend() == "nccl"
+    dev = int(getattr(model, "device", 0) or 0)
+    factory = (lambda: PackRecorder(len(model.class_vals), dev)) if nccl else None
+    local = model._fit_slots_streams(n_local, list(seeds), factory)
+    return local, _merge_recorders(model._stream_hooks)
 
 
 def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
@@ -248,24 +279,19 @@ def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
     if seeds is not None:
         np.random.seed(seeds[rank])
         _pyrandom.seed(seeds[rank])
-    recorder = _install_recorder(model)
-    try:
-        local = model._fit_slots(hi - lo) if hi > lo else []
-    finally:
-        model._tls.pack_hook = None
+    local, recorder = _fit_local(model, hi - lo, 1, None)
     return _gather_forest(model, local, recorder)
 
 
-def fit_sharded_local(model, n_local: int):
-    """Weak-scaling variant used by bench.py: every rank grows ``n_local`` slots from its current
-    RNG state, then the survivors are all-gathered (rank order)."""
+def fit_sharded_local(model, n_local: int, host_streams: int = 1, seeds=None):
+    """Weak-scaling variant used by bench.py: every rank grows ``n_local`` slots -- from its current
+    RNG state, or over ``host_streams`` independent host streams seeded by ``seeds`` -- then the
+    survivors are all-gathered (rank order, worker order inside a rank)."""
     if not is_distributed():
+        if host_streams > 1:
+            return model._fit_slots_streams(n_local, list(seeds))
         return model._fit_slots(n_local)
-    recorder = _install_recorder(model)
-    try:
-        local = model._fit_slots(n_local)
-    finally:
-        model._tls.pack_hook = None
+    local, recorder = _fit_local(model, n_local, host_streams, seeds)
     return _gather_forest(model, local, recorder)
 
 

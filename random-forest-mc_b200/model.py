@@ -145,8 +145,11 @@ class RandomForestMC(BaseRandomForestMC):
         self._tls = threading.local()
         self.max_candidates_per_launch = 4096
         self.max_batch_bytes = 24 << 30
-        self.rng_threads = max(0, min(6, (os.cpu_count() or 1) - 1))
-        self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "1" if (os.cpu_count() or 1) >= 12 else "0") == "1"  # MT19937 blocks from a producer thread
+        # resolve helpers of the host RNG walk: the sequential part (MT19937 blocks + rejection) is the
+        # floor; two helpers keep up with it.  A producer thread for the blocks is opt-in only: since
+        # the blocks are generated with AVX-512 the cache-to-cache hand-off costs more than it saves.
+        self.rng_threads = max(0, min(2, (os.cpu_count() or 1) - 1))
+        self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -447,7 +450,7 @@ class RandomForestMC(BaseRandomForestMC):
         self._tls.last_stats = stats
         return trees
 
-    def _fit_slots_streams(self, n_slots: int, seeds):
+    def _fit_slots_streams(self, n_slots: int, seeds, hook_factory=None):
         """``n_slots`` shared over ``len(seeds)`` independent host RNG streams, one thread each, all
         feeding this GPU.  Worker r is exactly the serial algorithm on its share of the slots under
         ``np.random.seed(seeds[r]); random.seed(seeds[r])`` (its own RandomState / Random objects);
@@ -457,11 +460,13 @@ class RandomForestMC(BaseRandomForestMC):
 
         k = len(seeds)
         parts, stats, errors = [None] * k, [None] * k, []
+        self._stream_hooks = [hook_factory() if hook_factory is not None else None for _ in range(k)]
 
         def work(r):
             stream = 0
             try:
                 stream = engine.stream_create(self.device)  # each host stream keeps its own launches in flight
+                self._tls.pack_hook = self._stream_hooks[r]
                 self._tls.np_rng = np.random.RandomState(int(seeds[r]))
                 self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
                 # one resolve helper per stream while there are cores for it; no producer thread
