@@ -126,6 +126,26 @@ def stream_destroy(device: int, stream: int) -> None:
         _check(load_library().rfmc_stream_destroy(device, _p(stream)))
 
 
+_STREAM_POOL = {}
+_STREAM_LOCK = __import__("threading").Lock()
+
+
+def stream_acquire(device: int = 0) -> int:
+    """A CUDA stream for one host thread of a multi-stream fit.  Streams are kept and reused:
+    creating and (above all) destroying one while other streams are busy costs milliseconds."""
+    with _STREAM_LOCK:
+        free = _STREAM_POOL.setdefault(device, [])
+        if free:
+            return free.pop()
+    return stream_create(device)
+
+
+def stream_release(device: int, stream: int) -> None:
+    if stream:
+        with _STREAM_LOCK:
+            _STREAM_POOL.setdefault(device, []).append(stream)
+
+
 def legacy_choice_indices(key: np.ndarray, pos: int, n: int, size: int):
     """permutation(n)[:size] on the legacy MT19937 stream (key is advanced in place).  Host code."""
     out = np.empty(size, dtype=np.int64)
@@ -136,15 +156,31 @@ def legacy_choice_indices(key: np.ndarray, pos: int, n: int, size: int):
     return out, p.value
 
 
+_FLAT_ROWS = {}
+
+
+def _flat_class_rows(class_rows):
+    """(rows back to back, offsets) of a dataset's per-class row lists; built once per list object
+    (a fit calls the draw plan hundreds of times, from several host threads)."""
+    hit = _FLAT_ROWS.get(id(class_rows))
+    if hit is not None and hit[0] is class_rows:
+        return hit[1], hit[2]
+    rows = np.ascontiguousarray(np.concatenate(class_rows), dtype=np.int64)
+    off = np.zeros(len(class_rows) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(r) for r in class_rows])
+    if len(_FLAT_ROWS) > 8:
+        _FLAT_ROWS.clear()
+    _FLAT_ROWS[id(class_rows)] = (class_rows, rows, off)
+    return rows, off
+
+
 def legacy_draw_plan(key: np.ndarray, pos: int, n_slots: int, class_rows: Sequence[np.ndarray], per_class: int,
                      n_train_pclass: int, n_cands: int, low: int, high: int, n_threads: int = 4):
     """The numpy-stream draws of ``n_slots`` tree slots (rows per class, then ``n_cands`` feature
     counts per slot) in one host call.  Returns (idx_train, idx_val, feat_counts, key_snap,
     pos_snap, new_pos); ``key`` is advanced in place."""
     C_ = len(class_rows)
-    rows = np.ascontiguousarray(np.concatenate(class_rows), dtype=np.int64)
-    off = np.zeros(C_ + 1, dtype=np.int64)
-    off[1:] = np.cumsum([len(r) for r in class_rows])
+    rows, off = _flat_class_rows(class_rows)
     n_tr = min(per_class, n_train_pclass)
     idx_train = np.empty((n_slots, C_ * n_tr), dtype=np.int32)
     idx_val = np.empty((n_slots, C_ * (per_class - n_tr)), dtype=np.int32)

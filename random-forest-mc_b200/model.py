@@ -465,7 +465,7 @@ class RandomForestMC(BaseRandomForestMC):
         def work(r):
             stream = 0
             try:
-                stream = engine.stream_create(self.device)  # each host stream keeps its own launches in flight
+                stream = engine.stream_acquire(self.device)  # each host stream keeps its own launches in flight
                 self._tls.pack_hook = self._stream_hooks[r]
                 self._tls.np_rng = np.random.RandomState(int(seeds[r]))
                 self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
@@ -477,10 +477,7 @@ class RandomForestMC(BaseRandomForestMC):
             except BaseException as e:  # surfaced on the calling thread
                 errors.append(e)
             finally:
-                try:
-                    engine.stream_destroy(self.device, stream)
-                except Exception:
-                    pass
+                engine.stream_release(self.device, stream)
 
         threads = [threading.Thread(target=work, args=(r,)) for r in range(k)]
         for t in threads:
