@@ -31,7 +31,7 @@ assert rc == 0, "build with -DRFMC_GROW_TIMING"
 t = out.astype(np.int64)
 levels = int(t[4])
 print(f"gather {t[1]-t[0]:>9d} cyc | levels {t[2]-t[1]:>9d} | scoring {t[3]-t[2]:>9d} | total {t[3]-t[0]}")
-print("lvl   tiny small large huge |   phase1   scan   emit")
+print("lvl   tiny small medium large huge |   phase1   scan   emit")
 for L in range(levels):
     b = 16 + 8 * L
-    print(f"{L:3d} {t[b+4]:6d} {t[b+5]:5d} {t[b+6]:5d} {t[b+7]:4d} | {t[b+1]-t[b]:8d} {t[b+2]-t[b+1]:6d} {t[b+3]-t[b+2]:6d}")
+    print(f"{L:3d} {t[b+4]:6d} {t[b+5]:5d} {t[b+6]:6d} {t[b+7] & 0xFFFF:5d} {t[b+7] >> 16:4d} | {t[b+1]-t[b]:8d} {t[b+2]-t[b+1]:6d} {t[b+3]-t[b+2]:6d}")

@@ -429,8 +429,8 @@ int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_
     rc |= upload(&b->d_cand_slot, cand_slot, (size_t)n_cand, st);
     rc |= upload(&b->d_feat_off, feat_off, (size_t)n_cand + 1, st);
     rc |= upload(&b->d_feat_list, feat_list, (size_t)feat_off[n_cand], st);
-    rc |= reserve((uint8_t**)&b->d_cc, g * fmax * ntp * ds->code_width);
-    rc |= reserve(&b->d_lab, g * ntp);
+    rc |= reserve((uint8_t**)&b->d_cc, (size_t)n_slots * ds->n_features * ntp * ds->code_width);  // [slot][feature][row]
+    rc |= reserve(&b->d_lab, (size_t)n_slots * ntp);
     rc |= reserve(&b->d_pos, g * 2 * ntp);
     rc |= reserve(&b->d_work, g * 2 * ntp);
     rc |= reserve(&b->d_resna, g * 2 * ntp);

@@ -67,9 +67,10 @@ struct rfmc_batch {
     int32_t* d_cand_slot = nullptr;
     int32_t* d_feat_off = nullptr;
     uint16_t* d_feat_list = nullptr;
-    // per-CTA scratch
+    // per tree slot: compact [feature][row] codes and labels of the bootstrap rows (slot_gather_kernel)
     void* d_cc = nullptr;
     uint8_t* d_lab = nullptr;
+    // per-CTA scratch
     uint32_t* d_pos = nullptr;
     rfmc::WorkItem* d_work = nullptr;
     uint32_t* d_resna = nullptr;

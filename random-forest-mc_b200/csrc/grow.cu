@@ -50,7 +50,7 @@ __device__ unsigned long long g_dbg[8192];
 #endif
 constexpr int HIST_WORDS = 512;  // per warp
 constexpr uint32_t NOT_FINAL = 0xFFu;
-constexpr int TINY_MAX = 8, SMALL_MAX = 32, HUGE_MIN = 1024;  // the sorting network in process_tiny is for 8
+constexpr int TINY_MAX = 8, SMALL_MAX = 32, MEDIUM_MAX = 128, HUGE_MIN = 1024;  // the sorting network in process_tiny is for 8
 
 template <typename CodeT, typename PosT>
 struct GrowArgs {
@@ -71,9 +71,12 @@ struct GrowArgs {
     const int32_t* cand_slot;
     const int32_t* feat_off;
     const uint16_t* feat_list;
+    // per tree slot (written by slot_gather_kernel): compact [feature][row] codes and labels of the slot's
+    // bootstrap rows -- shared by every candidate of the slot
+    const CodeT* slot_codes;
+    const uint8_t* slot_lab;
+    int32_t n_features;
     // scratch (per CTA)
-    CodeT* cc;
-    uint8_t* lab_g;   // used when the arrays do not fit shared memory
     PosT* pos_g;
     WorkItem* work;   // 2 buffers x list capacity
     uint32_t* resna;  // 2 buffers x nt_pad, indexed by level position
@@ -266,6 +269,26 @@ __device__ __forceinline__ uint32_t threshold_warp(const double* tab, uint32_t K
     return less + 1;
 }
 
+// The search above is the longest dependent-load chain of a node, and the node itself does not need
+// its result: no row OF THE NODE has a code strictly between the two middle order statistics, so when
+// va < sv < vb every threshold in (ca, cb] partitions the node's rows identically.  The node is split
+// with cb, the exact threshold is marked pending (thr = ca, the search's lower bound) and resolved
+// for all nodes of the tree at once, thread per node, before the hold-out rows are scored.
+constexpr uint32_t FLAG_PENDING = 0x80000000u;  // internal: never leaves the kernel
+__device__ __forceinline__ uint32_t threshold_deferred(const double* tab, uint32_t K, double sv, double va, double vb,
+                                                       uint32_t ca, uint32_t cb, uint32_t& t_store, uint32_t& pending) {
+    pending = 0;
+    if (sv != sv) return t_store = 0xFFFFFFFFu;  // every comparison with NaN is False
+    if (sv == va) return t_store = ca;
+    if (sv == vb) return t_store = cb;
+    if (va < sv && sv < vb) {
+        pending = FLAG_PENDING;
+        t_store = ca;
+        return cb;
+    }
+    return t_store = count_less_scalar(tab, 0, K, sv) + 1;
+}
+
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -275,10 +298,14 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+__device__ __forceinline__ int size_class(int n) {
+    return n <= TINY_MAX ? 0 : (n <= SMALL_MAX ? 1 : (n <= MEDIUM_MAX ? 2 : (n <= HUGE_MIN ? 3 : 4)));
+}
+
 template <typename CodeT, typename PosT>
 struct CandCtx {
     const GrowArgs<CodeT, PosT>* a;
-    CodeT* cc;
+    const CodeT* cc;  // this candidate's slot matrix: column of feature f at cc + f * nt_pad
     const uint8_t* lab;
     PosT* pos;  // nt_pad: every node owns a segment; small/tiny nodes partition it in place
     PosT* tmp;  // nt_pad (global): partition target of > 32-row nodes, copied back
@@ -345,11 +372,11 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
             if (fl >= c.nf) fl -= c.nf;
             const uint32_t f = c.flist[fl];
             const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
-            const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
+            const CodeT* col = c.cc + (size_t)f * a.nt_pad;
             uint32_t cv[TINY_MAX];
 #pragma unroll
             for (int q = 0; q < TINY_MAX; ++q) cv[q] = (q < n) ? (uint32_t)col[p[q]] : 0xFFFFFFFFu;
-            uint32_t t_store, t_part, go = 0, fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
+            uint32_t t_store, t_part, go = 0, pend = 0, fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
             if (n == 2) {  // model.py:258-262
                 t_store = t_part = cv[0] > cv[1] ? cv[0] : cv[1];
@@ -396,11 +423,11 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
                 const uint32_t K = (uint32_t)a.col_nuniq[f];
                 const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                 sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                t_store = t_part = threshold_scalar(tab, K, sv, va, vb, ca, cb);
+                t_part = threshold_deferred(tab, K, sv, va, vb, ca, cb, t_store, pend);
 #pragma unroll
                 for (int q = 0; q < TINY_MAX; ++q) go |= ((q < n) && cv[q] >= t_part) ? (1u << q) : 0u;
                 const int cnt = __popc(go);
-                if ((cnt == 0 || cnt == n) && t_store != 0xFFFFFFFFu) {  // model.py:242-245
+                if ((cnt == 0 || cnt == n) && t_store != 0xFFFFFFFFu && !pend) {  // model.py:242-245
                     const uint32_t i0 = t_store - 1;
                     t_part = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
                     go = 0;
@@ -429,7 +456,7 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
                 }
                 nd.feat = (int32_t)f;
                 nd.thr = t_store;
-                nd.flags = fl_flags;
+                nd.flags = fl_flags | pend;
                 nd.sval = (cat || (fl_flags & RFMC_FLAG_TWO_ROW)) ? 0.0 : sv;
                 na_out = (uint32_t)cnt_a;
                 fin_out = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
@@ -444,7 +471,289 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// small (9..32 rows, one row per lane) and large (> 32 rows) nodes: one WARP per node
+// small (9..32 rows) and medium (33..128 rows) nodes: a GROUP of G lanes per node, 4 rows per lane,
+// everything about the node in registers.  G = 8 runs four nodes per warp (four independent
+// dependent-load chains in flight instead of one), G = 32 one node per warp.  The rows' codes are
+// read once per attempted feature; the order statistics come from all-pairs rank counting against
+// the group's keys in shared memory (broadcast reads, no collectives inside the counting loop);
+// the partition goes back in place.  Warp collectives (ballots, shuffles) are only issued from
+// warp-uniform code: groups that are done or empty carry dummy values through them.
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ uint32_t group_ballot(bool p, int gi) {
+    const uint32_t b = __ballot_sync(FULL, p);
+    if (G == 32) return b;
+    return (b >> (gi * G)) & ((1u << G) - 1u);
+}
+template <int G>
+__device__ __forceinline__ uint32_t group_sum(uint32_t v) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ uint32_t group_min(uint32_t v) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(FULL, v, d));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ unsigned long long group_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, v, d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+template <typename CodeT, typename PosT, int G>
+__device__ void process_group(const CandCtx<CodeT, PosT>& c, WorkItem* items, uint32_t n_valid, uint32_t* wsm, int lane) {
+    constexpr int NG = 32 / G, R = 4, CAP = R * G, GW = HIST_WORDS / NG, HW = GW - CAP - 2;
+    constexpr bool PACKED = sizeof(CodeT) <= 2;  // key = code << 7 | row: one compare per pair
+    static_assert(HW >= RFMC_MAX_CLASSES, "group scratch too small for the class histogram");
+    const GrowArgs<CodeT, PosT>& a = *c.a;
+    const int gi = lane / G, gl = lane % G;
+    const bool valid = (uint32_t)gi < n_valid;
+    uint32_t* s_keys = wsm + gi * GW;  // CAP words
+    uint32_t* s_sel = s_keys + CAP;    // 2 words: codes of the two middle order statistics
+    uint32_t* s_h = s_sel + 2;         // HW words: class histogram, then categorical histograms
+    WorkItem w = WorkItem{0u, 0u, 0u, 0u};
+    if (valid) w = items[gi];
+    const uint32_t n = w.hi - w.lo;  // 0 for an empty group
+    PosT* P = c.pos + w.lo;
+    const int C = a.n_classes;
+    const uint32_t node = c.base + w.lpos;
+    const uint32_t ltg = (1u << gl) - 1u;
+    const uint32_t gmask = (G == 32) ? FULL : ((1u << G) - 1u);
+
+    uint32_t p[R], l[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const uint32_t r = (uint32_t)(q * G + gl);
+        p[q] = (r < n) ? (uint32_t)P[r] : 0u;
+        l[q] = (r < n) ? (uint32_t)c.lab[p[q]] : 0xFFu;
+    }
+    // ---- class histogram (np.unique(target_vals), model.py:267-268) ----
+    for (int b = gl; b < C; b += G) s_h[b] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+        if ((uint32_t)(q * G + gl) < n) atomicAdd(&s_h[l[q]], 1u);
+    __syncwarp();
+    uint32_t present = 0;
+    unsigned long long vk = 0;
+    for (int b = gl; b < C; b += G) {
+        const uint32_t cnt = s_h[b];
+        if (valid) c.counts[(size_t)node * C + b] = (int32_t)cnt;
+        present += cnt > 0;
+        const unsigned long long kk = ((unsigned long long)cnt << 8) | (unsigned long long)(255 - b);
+        vk = kk > vk ? kk : vk;
+    }
+    present = group_sum<G>(present);
+    vk = group_max_u64<G>(vk);
+    if (valid && gl == 0) c.votes[node] = (uint8_t)(255 - (int)(vk & 255));
+    __syncwarp();  // s_h is reused by categorical attempts
+
+    const int depth = c.level + 1;
+    bool searching = valid && c.nf > 0 && !(depth >= a.max_depth || present == 1);
+    bool accepted = false;
+    uint32_t thr_store = 0, na = 0, flags = 0, f_acc = 0, off_next = 0, fin = NOT_FINAL | (NOT_FINAL << 8);
+    double sv_acc = 0.0;
+    int k = 0;
+
+    while (__any_sync(FULL, searching)) {  // model.py:273-280: at most one full rotation per node
+        int fl = (int)w.off + k;
+        if (fl >= c.nf) fl -= c.nf;
+        if (!searching) fl = 0;
+        const uint32_t f = c.flist[fl];
+        const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
+        const CodeT* col = c.cc + (size_t)f * a.nt_pad;
+        const uint32_t K = (uint32_t)a.col_nuniq[f];
+        const bool use_hist = cat && (K + 1 <= (uint32_t)HW);
+        uint32_t cv[R], key[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const uint32_t r = (uint32_t)(q * G + gl);
+            cv[q] = (searching && r < n) ? (uint32_t)col[p[q]] : 0xFFFFFFFFu;
+            key[q] = PACKED ? ((cv[q] << 7) | r) : cv[q];
+        }
+        if (searching) {
+            if (use_hist) {
+                for (uint32_t b = gl; b <= K; b += G) s_h[b] = 0;
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if ((uint32_t)(q * G + gl) < n) s_keys[q * G + gl] = key[q];
+            }
+        }
+        __syncwarp();
+        unsigned long long mk = 0;
+        if (searching) {
+            if (!cat) {  // median (model.py:237): ranks (n-1)/2 and (n-1)/2 + 1 by all-pairs counting
+                uint32_t rk[R];
+#pragma unroll
+                for (int q = 0; q < R; ++q) rk[q] = 0;
+                for (uint32_t jj = 0; jj < n; ++jj) {
+                    const uint32_t o = s_keys[jj];
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        if (PACKED)
+                            rk[q] += (o < key[q]);
+                        else
+                            rk[q] += (o < key[q]) || (o == key[q] && jj < (uint32_t)(q * G + gl));
+                    }
+                }
+                const uint32_t k0 = (n - 1) >> 1;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if ((uint32_t)(q * G + gl) < n) {
+                        if (rk[q] == k0) s_sel[0] = cv[q];
+                        if (rk[q] == k0 + 1) s_sel[1] = cv[q];
+                    }
+                }
+            } else if (use_hist) {  // mode (model.py:249-250)
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if ((uint32_t)(q * G + gl) < n) atomicAdd(&s_h[cv[q]], 1u);
+            } else {  // high-cardinality categorical: all-pairs equality counting (rare path)
+                uint32_t eq[R];
+#pragma unroll
+                for (int q = 0; q < R; ++q) eq[q] = 0;
+                for (uint32_t jj = 0; jj < n; ++jj) {
+                    const uint32_t o = PACKED ? (s_keys[jj] >> 7) : s_keys[jj];
+#pragma unroll
+                    for (int q = 0; q < R; ++q) eq[q] += (o == cv[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if ((uint32_t)(q * G + gl) < n) {
+                        const unsigned long long kk = ((unsigned long long)eq[q] << 32) | (unsigned long long)(0xFFFFFFFFu - cv[q]);
+                        mk = kk > mk ? kk : mk;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t t_store = 0, t_part = 0, pend = 0;
+        double sv = 0.0;
+        const double* tab = a.tables + a.tab_off[f];
+        if (searching) {
+            if (!cat) {
+                const uint32_t ca = s_sel[0], cb = s_sel[1];
+                const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
+                sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
+                t_part = threshold_deferred(tab, K, sv, va, vb, ca, cb, t_store, pend);
+            } else if (use_hist) {
+                for (uint32_t b = gl; b <= K; b += G) {
+                    const unsigned long long kk = ((unsigned long long)s_h[b] << 32) | (unsigned long long)(0xFFFFFFFFu - b);
+                    mk = kk > mk ? kk : mk;
+                }
+            }
+        }
+        mk = group_max_u64<G>(mk);
+        if (searching && cat) t_store = t_part = 0xFFFFFFFFu - (uint32_t)(mk & 0xFFFFFFFFull);
+        // ---- side sizes ----
+        uint32_t ba[R], cnt_a = 0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const bool go = searching && (uint32_t)(q * G + gl) < n && (cat ? cv[q] == t_part : cv[q] >= t_part);
+            ba[q] = group_ballot<G>(go, gi);
+            cnt_a += __popc(ba[q]);
+        }
+        const bool degenerate = searching && !cat && (cnt_a == 0 || cnt_a == n) && t_store != 0xFFFFFFFFu && !pend;
+        if (__any_sync(FULL, degenerate)) {  // model.py:242-245: retry with '>'
+            if (degenerate) {
+                const uint32_t i0 = t_store - 1;
+                t_part = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
+            }
+            cnt_a = 0;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const bool go = searching && (uint32_t)(q * G + gl) < n && (cat ? cv[q] == t_part : cv[q] >= t_part);
+                ba[q] = group_ballot<G>(go, gi);
+                cnt_a += __popc(ba[q]);
+            }
+        }
+        const bool acc_now = searching && cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss;
+        if (__any_sync(FULL, acc_now)) {
+            // a side whose rows all carry one label is a finished leaf (model.py:268)
+            uint32_t ka = 0xFFFFFFFFu, kb = 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const uint32_t r = (uint32_t)(q * G + gl);
+                if (r < n) {
+                    const uint32_t kk = (r << 8) | l[q];
+                    if ((ba[q] >> gl) & 1u)
+                        ka = min(ka, kk);
+                    else
+                        kb = min(kb, kk);
+                }
+            }
+            ka = group_min<G>(ka);
+            kb = group_min<G>(kb);
+            const uint32_t la = ka & 0xFFu, lb = kb & 0xFFu;
+            bool bad_a = false, bad_b = false;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                if ((uint32_t)(q * G + gl) < n) {
+                    if ((ba[q] >> gl) & 1u)
+                        bad_a |= l[q] != la;
+                    else
+                        bad_b |= l[q] != lb;
+                }
+            }
+            const bool pa = group_ballot<G>(bad_a, gi) == 0u, pb = group_ballot<G>(bad_b, gi) == 0u;
+            if (acc_now) {  // stable partition, in place (every row of the node is in a register)
+                uint32_t before_a = 0, before_b = 0;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const uint32_t r0 = (uint32_t)(q * G);
+                    const uint32_t actm = (n >= r0 + G) ? gmask : (n > r0 ? ((1u << (n - r0)) - 1u) : 0u);
+                    const uint32_t bb = ~ba[q] & actm;
+                    if (r0 + gl < n) {
+                        const bool go = (ba[q] >> gl) & 1u;
+                        const uint32_t dst = go ? before_a + __popc(ba[q] & ltg) : cnt_a + before_b + __popc(bb & ltg);
+                        P[dst] = (PosT)p[q];
+                    }
+                    before_a += __popc(ba[q]);
+                    before_b += __popc(bb);
+                }
+                accepted = true;
+                searching = false;
+                thr_store = t_store;
+                na = cnt_a;
+                flags = (cat ? RFMC_FLAG_CATEGORICAL : 0u) | pend;
+                f_acc = f;
+                sv_acc = cat ? 0.0 : sv;
+                off_next = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
+                fin = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
+            }
+        }
+        if (searching) {
+            ++k;
+            if (k >= c.nf) searching = false;
+        }
+        __syncwarp();  // scratch is rewritten by the next attempt
+    }
+    if (valid && gl == 0) {
+        rfmc_node nd;
+        write_leaf(&nd);
+        if (accepted) {
+            nd.feat = (int32_t)f_acc;
+            nd.thr = thr_store;
+            nd.flags = flags;
+            nd.sval = sv_acc;
+            items[gi].off = off_next;
+        }
+        c.nodes[node] = nd;
+        c.resna[w.lpos] = accepted ? na : 0u;
+        c.resfin[w.lpos] = (uint16_t)fin;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// large (129..1024 rows) nodes: one WARP per node
 // ---------------------------------------------------------------------------------------------
 template <typename CodeT, typename PosT>
 __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint32_t* hist, int lane) {
@@ -452,22 +761,15 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
     const WorkItem w = *item;
     const uint32_t n = w.hi - w.lo;
     PosT* P = c.pos + w.lo;
-    PosT* Pn = (n <= SMALL_MAX) ? P : (c.tmp + w.lo);  // small: in place (rows are in registers)
+    PosT* Pn = c.tmp + w.lo;  // partition target, copied back
     const int C = a.n_classes;
     const uint32_t lt = lanemask_lt();
     const uint32_t node = c.base + w.lpos;
-    const bool small = n <= SMALL_MAX;
 
     // ---- class histogram of the node (np.unique(target_vals), model.py:267-268) ----
     for (int i = lane; i < RFMC_MAX_CLASSES; i += 32) hist[i] = 0;
     __syncwarp();
-    uint32_t my_p = 0, my_l = 0xFFFFu;  // small nodes keep their row and label in registers
-    if (small) {
-        const bool act = lane < (int)n;
-        my_p = act ? (uint32_t)P[lane] : 0u;
-        my_l = act ? (uint32_t)c.lab[my_p] : 0xFFFFu;
-        hist_add(hist, my_l, act, lane);
-    } else {
+    {
         for (uint32_t base = 0; base < n; base += 128) {
             uint32_t l[4];
             bool act[4];
@@ -515,65 +817,12 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
             if (fl >= c.nf) fl -= c.nf;
             const uint32_t f = c.flist[fl];
             const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
-            const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
-            uint32_t t_store = 0, t_part = 0, cnt_a = 0;
+            const CodeT* col = c.cc + (size_t)f * a.nt_pad;
+            uint32_t t_store = 0, t_part = 0, cnt_a = 0, pend = 0;
             const uint32_t fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
 
-            if (small) {
-                const bool act = lane < (int)n;
-                const uint32_t my = act ? (uint32_t)col[my_p] : 0xFFFFFFFFu;
-                if (cat) {  // mode, ties -> lowest code (model.py:249-250)
-                    uint32_t grp = __match_any_sync(FULL, my);
-                    unsigned long long key =
-                        act ? (((unsigned long long)__popc(grp) << 32) | (unsigned long long)(0xFFFFFFFFu - my)) : 0ull;
-                    key = warp_max_u64(key);
-                    t_store = t_part = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
-                } else {  // median (model.py:237)
-                    uint32_t rank = 0;
-                    for (uint32_t jj = 0; jj < n; ++jj) {
-                        uint32_t o = __shfl_sync(FULL, my, jj);
-                        rank += (o < my) || (o == my && (int)jj < lane);
-                    }
-                    const uint32_t k0 = (n - 1) >> 1;
-                    uint32_t mA = __ballot_sync(FULL, act && rank == k0);
-                    uint32_t mB = __ballot_sync(FULL, act && rank == k0 + 1);
-                    uint32_t ca = __shfl_sync(FULL, my, __ffs(mA) - 1);
-                    uint32_t cb = __shfl_sync(FULL, my, __ffs(mB) - 1);
-                    const double* tab = a.tables + a.tab_off[f];
-                    const uint32_t K = (uint32_t)a.col_nuniq[f];
-                    double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
-                    sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                    t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
-                }
-                uint32_t ma = __ballot_sync(FULL, act && (cat ? my == t_part : my >= t_part));
-                cnt_a = __popc(ma);
-                if (!cat && (cnt_a == 0 || cnt_a == n) && t_store != 0xFFFFFFFFu) {  // model.py:242-245
-                    const double* tab = a.tables + a.tab_off[f];
-                    const uint32_t K = (uint32_t)a.col_nuniq[f];
-                    uint32_t i0 = t_store - 1;
-                    t_part = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
-                    ma = __ballot_sync(FULL, act && my >= t_part);
-                    cnt_a = __popc(ma);
-                }
-                if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
-                    accepted = true;
-                    const uint32_t all = (n == 32) ? FULL : ((1u << n) - 1u);
-                    const uint32_t mb = ~ma & all;
-                    __syncwarp();
-                    if (act) {
-                        bool go = (ma >> lane) & 1u;
-                        uint32_t dst = go ? __popc(ma & lt) : cnt_a + __popc(mb & lt);
-                        Pn[dst] = (PosT)my_p;
-                    }
-                    // a side whose rows all carry one label is a finished leaf (model.py:268)
-                    const uint32_t la = __shfl_sync(FULL, my_l, __ffs(ma) - 1);
-                    const uint32_t lb = __shfl_sync(FULL, my_l, __ffs(mb) - 1);
-                    const bool pa = __ballot_sync(FULL, ((ma >> lane) & 1u) && my_l == la) == ma;
-                    const bool pb = __ballot_sync(FULL, ((mb >> lane) & 1u) && my_l == lb) == mb;
-                    fin = (pa ? la : NOT_FINAL) | ((pb ? lb : NOT_FINAL) << 8);
-                }
-            } else {
+            {
                 const uint32_t K = (uint32_t)a.col_nuniq[f];
                 if (cat) {
                     if (K + 1 <= (uint32_t)HIST_WORDS) {
@@ -630,7 +879,7 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
                     const double* tab = a.tables + a.tab_off[f];
                     double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                     sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                    t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
+                    t_part = threshold_deferred(tab, K, sv, va, vb, ca, cb, t_store, pend);
                 }
                 // side sizes
                 for (int attempt = 0; attempt < 2; ++attempt) {
@@ -652,7 +901,7 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
                             cnt_a += __popc(__ballot_sync(FULL, go));
                         }
                     }
-                    if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu) break;
+                    if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu || pend) break;
                     const double* tab = a.tables + a.tab_off[f];
                     uint32_t i0 = t_store - 1;
                     uint32_t t2 = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
@@ -681,7 +930,7 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
             if (accepted) {
                 thr_store = t_store;
                 na = cnt_a;
-                flags = fl_flags;
+                flags = fl_flags | pend;
                 f_acc = f;
                 sv_acc = cat ? 0.0 : sv;
                 off_next = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
@@ -781,9 +1030,9 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
             if (fl >= c.nf) fl -= c.nf;
             const uint32_t f = c.flist[fl];
             const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
-            const CodeT* col = c.cc + (size_t)fl * a.nt_pad;
+            const CodeT* col = c.cc + (size_t)f * a.nt_pad;
             const uint32_t K = (uint32_t)a.col_nuniq[f];
-            uint32_t t_store = 0, t_part = 0, cnt_a = 0;
+            uint32_t t_store = 0, t_part = 0, cnt_a = 0, pend = 0;
             const uint32_t fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
             if (cat) {
@@ -895,7 +1144,7 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
                 const double* tab = a.tables + a.tab_off[f];
                 const double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                 sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
-                t_store = t_part = threshold_warp(tab, K, sv, va, vb, ca, cb, lane);
+                t_part = threshold_deferred(tab, K, sv, va, vb, ca, cb, t_store, pend);
             }
             // ---- side sizes (per-warp slices, summed through shared memory) ----
             uint32_t mine_a = 0;
@@ -924,7 +1173,7 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
                 cnt_a = 0;
 #pragma unroll
                 for (int w8 = 0; w8 < GROW_WARPS; ++w8) cnt_a += s_part[w8];
-                if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu) break;
+                if (cat || attempt == 1 || !(cnt_a == 0 || cnt_a == n) || t_store == 0xFFFFFFFFu || pend) break;
                 const double* tab = a.tables + a.tab_off[f];
                 const uint32_t i0 = t_store - 1;
                 const uint32_t t2 = t_store + ((i0 < K && __ldg(&tab[i0]) == sv) ? 1u : 0u);
@@ -960,7 +1209,7 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
                 __syncthreads();
                 thr_store = t_store;
                 na = cnt_a;
-                flags = fl_flags;
+                flags = fl_flags | pend;
                 f_acc = f;
                 sv_acc = cat ? 0.0 : sv;
                 off_next = (uint32_t)((fl + 1 == c.nf) ? 0 : fl + 1);
@@ -985,14 +1234,79 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Slot gather: the bootstrap rows of every tree slot, read once from the row-major code matrix and
+// written as a compact [slot][feature][row] matrix (+ the rows' labels).  Every candidate of a slot
+// grows from the same rows (model.py:324-342 draws them once per survivedTree call), so this replaces
+// one gather per CANDIDATE inside the grower by one per SLOT, spread over the whole GPU.
+// A warp owns 32 rows: it copies a chunk of words of each row verbatim into shared memory with
+// coalesced loads (consecutive lanes = consecutive words of a row), then reads the tile back
+// lane-per-row -- conflict-free, the tile pitch is an odd number of words -- and stores 32
+// consecutive codes of one feature per instruction.  HBM-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATHER_WARPS = 8, GATHER_CHUNK_WORDS = 65;
+
+template <typename CodeT>
+__global__ void __launch_bounds__(GATHER_WARPS * 32) slot_gather_kernel(const CodeT* __restrict__ codes, int64_t stride,
+                                                                         const uint8_t* __restrict__ labels, int n_features,
+                                                                         const int32_t* __restrict__ idx_train, int n_train,
+                                                                         int nt_pad, CodeT* __restrict__ slot_codes,
+                                                                         uint8_t* __restrict__ slot_lab) {
+    extern __shared__ __align__(16) uint32_t g_tile[];
+    constexpr int PER = (int)(sizeof(uint32_t) / sizeof(CodeT));  // codes per word
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int pitch_w = (int)((stride * (int64_t)sizeof(CodeT)) >> 2);
+    const int cw_max = pitch_w < GATHER_CHUNK_WORDS ? pitch_w : GATHER_CHUNK_WORDS;
+    const int tp = cw_max | 1;
+    uint32_t* tile = g_tile + (size_t)warp * 32 * tp;
+    const CodeT* tile_c = reinterpret_cast<const CodeT*>(tile);
+    const uint32_t* codes_w = reinterpret_cast<const uint32_t*>(codes);
+    const int i0 = (blockIdx.x * GATHER_WARPS + warp) * 32;
+    if (i0 >= n_train) return;
+    const int rows = n_train - i0 < 32 ? n_train - i0 : 32;
+    int64_t my_off = 0;
+    if (lane < rows) {
+        const int64_t row = (int64_t)__ldg(&idx_train[(size_t)slot * n_train + i0 + lane]);
+        my_off = row * pitch_w;
+        slot_lab[(size_t)slot * nt_pad + i0 + lane] = __ldg(&labels[row]);
+    }
+    CodeT* out = slot_codes + (size_t)slot * n_features * nt_pad + i0 + lane;
+    for (int w0 = 0; w0 < pitch_w; w0 += cw_max) {
+        const int cw = pitch_w - w0 < cw_max ? pitch_w - w0 : cw_max;
+        const int total = rows * cw;
+        const int dq = 32 / cw, dr = 32 % cw;
+        int t = lane / cw, r = lane % cw;
+        for (int e = lane; e - lane < total; e += 32) {
+            const int64_t off = __shfl_sync(FULL, my_off, t < rows ? t : 0);
+            if (e < total) tile[t * tp + r] = __ldg(&codes_w[off + w0 + r]);
+            t += dq;
+            r += dr;
+            if (r >= cw) {
+                r -= cw;
+                ++t;
+            }
+        }
+        __syncwarp();
+        const int f_end = (w0 + cw) * PER < n_features ? (w0 + cw) * PER : n_features;
+        if (lane < rows) {
+            const CodeT* mine = tile_c + (size_t)lane * tp * PER - (size_t)w0 * PER;
+#pragma unroll 4
+            for (int f = w0 * PER; f < f_end; ++f) out[(size_t)f * nt_pad] = mine[f];
+        }
+        __syncwarp();
+    }
+}
+
 template <typename CodeT, typename PosT>
 __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(GrowArgs<CodeT, PosT> a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ uint32_t s_hist[GROW_WARPS][HIST_WORDS];
+    __shared__ __align__(16) uint32_t s_scratch[(GROW_WARPS + 1) * HIST_WORDS];
+    uint32_t(*s_hist)[HIST_WORDS] = reinterpret_cast<uint32_t(*)[HIST_WORDS]>(s_scratch);  // per-warp histograms
+    uint32_t* s_comb = s_scratch + GROW_WARPS * HIST_WORDS;                                 // the CTA's combined one
     __shared__ uint32_t s_wtot[GROW_WARPS];
-    __shared__ uint32_t s_ticket[3];
-    __shared__ uint32_t s_cnt[2][4];  // items per size class (tiny, small, large, huge), this level / next level
-    __shared__ uint32_t s_comb[HIST_WORDS];
+    __shared__ uint32_t s_ticket[4];
+    __shared__ uint32_t s_cnt[2][5];  // items per size class (tiny, small, medium, large, huge), this level / next level
     __shared__ uint32_t s_part[GROW_WARPS];
     __shared__ uint32_t s_total;
     __shared__ int s_correct;
@@ -1000,28 +1314,20 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     const int nt = a.n_train;
-    // list regions inside one work buffer: tiny items hold >= 2 rows, small >= 5, large >= 33
-    const uint32_t cap_t = (uint32_t)nt / 2 + 1, cap_s = (uint32_t)nt / 5 + 1, cap_l = (uint32_t)nt / 33 + 1;
-    const uint32_t cap_h = (uint32_t)nt / (HUGE_MIN + 1) + 1;
-    const uint32_t reg0[4] = {0u, cap_t, cap_t + cap_s, cap_t + cap_s + cap_l};
-    const uint32_t cap_all = cap_t + cap_s + cap_l + cap_h;
+    // list regions inside one work buffer: tiny items hold >= 2 rows, small >= 9, medium >= 33, large >= 129
+    const uint32_t cap_t = (uint32_t)nt / 2 + 1, cap_s = (uint32_t)nt / (TINY_MAX + 1) + 1, cap_m = (uint32_t)nt / (SMALL_MAX + 1) + 1;
+    const uint32_t cap_l = (uint32_t)nt / (MEDIUM_MAX + 1) + 1, cap_h = (uint32_t)nt / (HUGE_MIN + 1) + 1;
+    const uint32_t reg0[5] = {0u, cap_t, cap_t + cap_s, cap_t + cap_s + cap_m, cap_t + cap_s + cap_m + cap_l};
+    const uint32_t cap_all = cap_t + cap_s + cap_m + cap_l + cap_h;
 
-    uint8_t* lab;
-    PosT* pos;
-    if (a.use_smem) {
-        lab = s_dyn;
-        pos = reinterpret_cast<PosT*>(s_dyn + (((size_t)a.nt_pad + 15) / 16) * 16);
-    } else {
-        lab = a.lab_g + (size_t)blockIdx.x * a.nt_pad;
-        pos = a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad;
-    }
+    uint8_t* lab_s = s_dyn;  // shared-memory copy of the slot's labels (when it fits)
+    PosT* pos = a.use_smem ? reinterpret_cast<PosT*>(s_dyn + (((size_t)a.nt_pad + 15) / 16) * 16)
+                           : a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad;
     PosT* tmp = a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad + a.nt_pad;
 
     for (int cand = blockIdx.x; cand < a.n_cand; cand += gridDim.x) {
         CandCtx<CodeT, PosT> c;
         c.a = &a;
-        c.cc = a.cc + (size_t)blockIdx.x * a.fmax * a.nt_pad;
-        c.lab = lab;
         c.pos = pos;
         c.tmp = tmp;
         c.resfin = a.resfin + (size_t)blockIdx.x * a.nt_pad;
@@ -1035,42 +1341,23 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         uint32_t* resna = a.resna + (size_t)blockIdx.x * 2 * a.nt_pad;
         uint32_t* rank = a.rank + (size_t)blockIdx.x * a.nt_pad;
         const int slot = a.cand_slot[cand];
-        const int32_t* idxT = a.idx_train + (size_t)slot * a.n_train;
         const int32_t* idxV = a.idx_val + (size_t)slot * a.n_val;
         const int C = a.n_classes;
 
-        // ---- gather the bootstrap rows once: coalesced row read -> compact [feature][row] ----
+        // ---- the slot's rows were gathered by slot_gather_kernel: only positions and labels to set up ----
         RFMC_TICK(0);
-        // One lane per row: the row ids of 32 rows are one coalesced load, each lane then walks
-        // its own 132-byte row (L1-resident after the first touch; the loads of the unrolled
-        // feature loop are independent), and every store is 32 consecutive codes of one feature.
-        for (int i0 = warp * 32; i0 < nt; i0 += GROW_WARPS * 32) {
-            const int i = i0 + lane;
-            const bool act = i < nt;
-            const int64_t row = act ? (int64_t)__ldg(&idxT[i]) : 0;
-            const CodeT* src = a.codes + row * a.stride;
-            if (act) {
-                lab[i] = __ldg(&a.labels[row]);
+        c.cc = a.slot_codes + (size_t)slot * a.n_features * a.nt_pad;
+        {
+            const uint8_t* lab_g = a.slot_lab + (size_t)slot * a.nt_pad;
+            c.lab = a.use_smem ? lab_s : lab_g;
+            for (int i = tid; i < nt; i += GROW_THREADS) {
+                if (a.use_smem) lab_s[i] = lab_g[i];
                 pos[i] = (PosT)i;
-            }
-            int fl = 0;
-            for (; fl + 8 <= c.nf; fl += 8) {
-                CodeT v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(&src[c.flist[fl + u]]);
-                if (act) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) c.cc[(size_t)(fl + u) * a.nt_pad + i] = v[u];
-                }
-            }
-            for (; fl < c.nf; ++fl) {
-                const CodeT v = __ldg(&src[c.flist[fl]]);
-                if (act) c.cc[(size_t)fl * a.nt_pad + i] = v;
             }
         }
         if (tid == 0) {
-            const int cls = nt <= TINY_MAX ? 0 : (nt <= SMALL_MAX ? 1 : (nt <= HUGE_MIN ? 2 : 3));
-            s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = s_cnt[0][3] = 0;
+            const int cls = size_class(nt);
+            s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = s_cnt[0][3] = s_cnt[0][4] = 0;
             s_cnt[0][cls] = 1;
             work[reg0[cls]] = WorkItem{0u, (uint32_t)nt, 0u, 0u};
             resna[0] = 0;
@@ -1090,9 +1377,10 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             c.resna = resna_cur;
             c.base = base;
             c.level = level;
-            const uint32_t n_tiny = s_cnt[cb][0], n_small = s_cnt[cb][1], n_large = s_cnt[cb][2], n_huge = s_cnt[cb][3];
-            if (tid < 4) {
-                if (tid < 3) s_ticket[tid] = 0;
+            const uint32_t n_tiny = s_cnt[cb][0], n_small = s_cnt[cb][1], n_medium = s_cnt[cb][2], n_large = s_cnt[cb][3],
+                           n_huge = s_cnt[cb][4];
+            if (tid < 5) {
+                if (tid < 4) s_ticket[tid] = 0;
                 s_cnt[nb][tid] = 0;
             }
             __syncthreads();
@@ -1101,26 +1389,34 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                 g_dbg[16 + 8 * level + 0] = clock64();
                 g_dbg[16 + 8 * level + 4] = n_tiny;
                 g_dbg[16 + 8 * level + 5] = n_small;
-                g_dbg[16 + 8 * level + 6] = n_large;
-                g_dbg[16 + 8 * level + 7] = n_huge;
+                g_dbg[16 + 8 * level + 6] = n_medium;
+                g_dbg[16 + 8 * level + 7] = n_large + (n_huge << 16);
             }
 #endif
-            // ---- phase 1: huge nodes by the whole CTA, large and small nodes by warps, tiny by threads ----
+            // ---- phase 1: huge nodes by the whole CTA, large and medium nodes by warps, small nodes by
+            //      quarter warps, tiny nodes by threads ----
             for (uint32_t j = 0; j < n_huge; ++j)
-                process_cta<CodeT, PosT>(c, cur + reg0[3] + j, s_hist, s_comb, s_part, tid);
+                process_cta<CodeT, PosT>(c, cur + reg0[4] + j, s_hist, s_comb, s_part, tid);
+            while (true) {
+                uint32_t j = 0;
+                if (lane == 0) j = atomicAdd(&s_ticket[3], 1u);
+                j = __shfl_sync(FULL, j, 0);
+                if (j >= n_large) break;
+                process_warp<CodeT, PosT>(c, cur + reg0[3] + j, s_hist[warp], lane);
+            }
             while (true) {
                 uint32_t j = 0;
                 if (lane == 0) j = atomicAdd(&s_ticket[2], 1u);
                 j = __shfl_sync(FULL, j, 0);
-                if (j >= n_large) break;
-                process_warp<CodeT, PosT>(c, cur + reg0[2] + j, s_hist[warp], lane);
+                if (j >= n_medium) break;
+                process_group<CodeT, PosT, 32>(c, cur + reg0[2] + j, 1u, s_hist[warp], lane);
             }
             while (true) {
                 uint32_t j = 0;
-                if (lane == 0) j = atomicAdd(&s_ticket[1], 1u);
+                if (lane == 0) j = atomicAdd(&s_ticket[1], 4u);
                 j = __shfl_sync(FULL, j, 0);
                 if (j >= n_small) break;
-                process_warp<CodeT, PosT>(c, cur + reg0[1] + j, s_hist[warp], lane);
+                process_group<CodeT, PosT, 8>(c, cur + reg0[1] + j, n_small - j, s_hist[warp], lane);
             }
             while (true) {
                 uint32_t j = 0;
@@ -1158,12 +1454,15 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             RFMC_TICK(16 + 8 * level + 2);
             // ---- phase 2b: child ids, finished leaves, next level's work lists ----
             const uint32_t base_next = base + width;
-            const uint32_t n_items = n_tiny + n_small + n_large + n_huge;
+            const uint32_t n_items = n_tiny + n_small + n_medium + n_large + n_huge;
             for (uint32_t q = tid; q < n_items; q += GROW_THREADS) {
-                const WorkItem w = q < n_tiny ? cur[reg0[0] + q]
-                                   : (q < n_tiny + n_small ? cur[reg0[1] + q - n_tiny]
-                                      : (q < n_tiny + n_small + n_large ? cur[reg0[2] + q - n_tiny - n_small]
-                                                                         : cur[reg0[3] + q - n_tiny - n_small - n_large]));
+                uint32_t qq = q;
+                int rc = 0;
+                if (qq >= n_tiny) { qq -= n_tiny; rc = 1;
+                    if (qq >= n_small) { qq -= n_small; rc = 2;
+                        if (qq >= n_medium) { qq -= n_medium; rc = 3;
+                            if (qq >= n_large) { qq -= n_large; rc = 4; } } } }
+                const WorkItem w = cur[reg0[rc] + qq];
                 const uint32_t na = resna_cur[w.lpos];
                 if (na == 0) continue;
                 const uint32_t s = rank[w.lpos];
@@ -1180,7 +1479,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                         for (int k = 0; k < C; ++k) c.counts[(size_t)cn * C + k] = (k == (int)f8) ? (int32_t)sz : 0;
                         c.votes[cn] = (uint8_t)f8;
                     } else {
-                        const int cls = sz <= TINY_MAX ? 0 : (sz <= SMALL_MAX ? 1 : (sz <= (uint32_t)HUGE_MIN ? 2 : 3));
+                        const int cls = size_class((int)sz);
                         const uint32_t at = atomicAdd(&s_cnt[nb][cls], 1u);
                         nxt[reg0[cls] + at] = WorkItem{lo, hi, cpos, w.off};
                     }
@@ -1195,20 +1494,101 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         RFMC_TICK(2);
         const uint32_t n_nodes = base;
 
-        // ---- validationTree (model.py:296-314): hold-out rows through the finished tree ----
-        int good = 0;
-        for (int i = tid; i < a.n_val; i += GROW_THREADS) {
-            const int64_t row = idxV[i];
-            const CodeT* src = a.codes + row * a.stride;
-            uint32_t node = 0;
-            while (true) {
-                const rfmc_node nd = c.nodes[node];
-                if (nd.feat < 0) break;
-                uint32_t cv = __ldg(&src[nd.feat]);
-                bool go = (nd.flags & RFMC_FLAG_CATEGORICAL) ? (cv == nd.thr) : (cv >= nd.thr);
-                node = (uint32_t)nd.child + (go ? 0u : 1u);
+        // ---- exact code thresholds of the splits that deferred their table search ----
+        // thread per node, four nodes interleaved per thread: the binary searches are chains of
+        // dependent L2 loads, so the only way to make them cheap is to keep several in flight
+        for (uint32_t i0 = tid; i0 < n_nodes; i0 += 4 * GROW_THREADS) {
+            const double* tab[4];
+            uint32_t lo[4], hi[4];
+            double sv[4];
+            bool pend[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * GROW_THREADS;
+                pend[u] = i < n_nodes && (c.nodes[i].flags & FLAG_PENDING);
             }
-            good += (c.votes[node] == __ldg(&a.labels[row]));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * GROW_THREADS;
+                lo[u] = hi[u] = 0;
+                sv[u] = 0.0;
+                tab[u] = a.tables;
+                if (pend[u]) {
+                    const int32_t f = c.nodes[i].feat;
+                    tab[u] = a.tables + a.tab_off[f];
+                    lo[u] = c.nodes[i].thr;
+                    hi[u] = (uint32_t)a.col_nuniq[f];
+                    sv[u] = c.nodes[i].sval;
+                }
+            }
+            while ((hi[0] > lo[0]) | (hi[1] > lo[1]) | (hi[2] > lo[2]) | (hi[3] > lo[3])) {
+                uint32_t mid[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1);
+                    v[u] = (hi[u] > lo[u]) ? __ldg(&tab[u][mid[u]]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (hi[u] > lo[u]) {
+                        if (v[u] < sv[u])
+                            lo[u] = mid[u] + 1;
+                        else
+                            hi[u] = mid[u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pend[u]) {
+                    const uint32_t i = i0 + u * GROW_THREADS;
+                    c.nodes[i].thr = lo[u] + 1u;
+                    c.nodes[i].flags &= ~FLAG_PENDING;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- validationTree (model.py:296-314): hold-out rows through the finished tree ----
+        // four rows per thread at a time: a walk is a chain of dependent (node, code) loads
+        int good = 0;
+        for (int i0 = tid; i0 < a.n_val; i0 += 4 * GROW_THREADS) {
+            const CodeT* src[4];
+            uint32_t node[4], lbl[4];
+            bool live[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * GROW_THREADS;
+                live[u] = i < a.n_val;
+                const int64_t row = live[u] ? (int64_t)__ldg(&idxV[i]) : 0;
+                src[u] = a.codes + row * a.stride;
+                lbl[u] = live[u] ? (uint32_t)__ldg(&a.labels[row]) : 0xFFFFu;
+                node[u] = 0;
+            }
+            while (live[0] | live[1] | live[2] | live[3]) {
+                uint2 ft[4], cf[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint2* nd = reinterpret_cast<const uint2*>(&c.nodes[node[u]]);
+                    ft[u] = nd[0];  // feat, thr
+                    cf[u] = nd[1];  // child, flags
+                }
+                uint32_t cv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    live[u] = live[u] && (int32_t)ft[u].x >= 0;
+                    cv[u] = live[u] ? (uint32_t)__ldg(&src[u][ft[u].x]) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (live[u]) {
+                        const bool go = (cf[u].y & RFMC_FLAG_CATEGORICAL) ? (cv[u] == ft[u].y) : (cv[u] >= ft[u].y);
+                        node[u] = cf[u].x + (go ? 0u : 1u);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) good += (i0 + u * GROW_THREADS < a.n_val) && (c.votes[node[u]] == lbl[u]);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) good += __shfl_xor_sync(FULL, good, d);
@@ -1259,8 +1639,9 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     a.cand_slot = b->d_cand_slot;
     a.feat_off = b->d_feat_off;
     a.feat_list = b->d_feat_list;
-    a.cc = (CodeT*)b->d_cc;
-    a.lab_g = b->d_lab;
+    a.slot_codes = (const CodeT*)b->d_cc;
+    a.slot_lab = b->d_lab;
+    a.n_features = ds->n_features;
     a.pos_g = (PosT*)b->d_pos;
     a.work = b->d_work;
     a.resna = b->d_resna;
@@ -1273,12 +1654,23 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     a.votes = b->d_votes;
     a.nnodes = b->d_nnodes;
     a.correct = b->d_correct;
+    {   // one pass over every slot's bootstrap rows: [row][feature] in HBM -> [slot][feature][row]
+        const int pitch_w = (int)((ds->stride * (int64_t)sizeof(CodeT)) >> 2);
+        const int cw = pitch_w < GATHER_CHUNK_WORDS ? pitch_w : GATHER_CHUNK_WORDS;
+        const size_t gsm = (size_t)GATHER_WARPS * 32 * (cw | 1) * sizeof(uint32_t);
+        auto gk = slot_gather_kernel<CodeT>;
+        RFMC_CUDA(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        dim3 grid((unsigned)((b->n_train + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32)), (unsigned)b->n_slots);
+        gk<<<grid, GATHER_WARPS * 32, gsm, stream>>>((const CodeT*)ds->d_codes, ds->stride, ds->d_labels, ds->n_features,
+                                                      b->d_idx_train, b->n_train, b->nt_pad, (CodeT*)b->d_cc, b->d_lab);
+        RFMC_CUDA(cudaGetLastError());
+    }
     auto k = grow_kernel<CodeT, PosT>;
     const size_t smem = a.use_smem ? dyn : 0;
     if (smem > 0) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     k<<<b->grid, GROW_THREADS, smem, stream>>>(a);
     RFMC_CUDA(cudaGetLastError());
-    b->launches = 1;
+    b->launches = 2;
     return 0;
 }
 

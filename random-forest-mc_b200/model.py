@@ -357,7 +357,9 @@ class RandomForestMC(BaseRandomForestMC):
 
     def _candidate_bytes(self) -> int:
         n_train = self.batch_train_pclass * len(self.class_vals) if self._N > self.batch_train_pclass else self._N * len(self.class_vals)
-        return 2 * max(1, n_train) * (24 + 4 * len(self.class_vals) + 1)
+        # node table + counts + votes, plus the slot's gathered [feature][row] matrix (a slot may end up
+        # with a single candidate)
+        return max(1, n_train) * (2 * (24 + 4 * len(self.class_vals) + 1) + len(self.feature_cols) * self.encoded.width)
 
     def _grow_plan(self, plan, stream=None):
         """One launch for every (slot, candidate) of the plan.  Returns (batch, first cand id per slot)."""
