@@ -211,30 +211,7 @@ __device__ __forceinline__ double median_value(double va, double vb, bool odd, i
 }
 
 // Number of entries of the sorted table tab[0..K) that are < sv, given that every entry below lo
-// is < sv and every entry at or above hi is >= sv.  32-ary search by the whole warp.
-__device__ uint32_t count_less(const double* __restrict__ tab, uint32_t lo, uint32_t hi, double sv, int lane) {
-    while (hi > lo) {
-        uint32_t len = hi - lo;
-        if (len <= 32) {
-            bool p = (lane < (int)len) && (__ldg(&tab[lo + lane]) < sv);
-            lo += __popc(__ballot_sync(FULL, p));
-            break;
-        }
-        uint32_t chunk = (len + 31) / 32;
-        uint32_t idx = lo + (lane + 1) * chunk - 1;
-        bool p = (idx < hi) && (__ldg(&tab[idx]) < sv);
-        uint32_t cnt = __popc(__ballot_sync(FULL, p));
-        uint32_t nlo = lo + cnt * chunk;
-        if (nlo > hi) nlo = hi;
-        uint32_t nhi = nlo + chunk - 1;
-        if (nhi > hi) nhi = hi;
-        lo = nlo;
-        hi = nhi;
-    }
-    return lo;
-}
-
-// Same contract, one thread (binary search).
+// is < sv and every entry at or above hi is >= sv (binary search, one thread).
 __device__ uint32_t count_less_scalar(const double* __restrict__ tab, uint32_t lo, uint32_t hi, double sv) {
     while (hi > lo) {
         uint32_t mid = lo + ((hi - lo) >> 1);
@@ -246,31 +223,8 @@ __device__ uint32_t count_less_scalar(const double* __restrict__ tab, uint32_t l
     return lo;
 }
 
-// lower_bound(table, sv) + 1 given the codes ca <= cb of the two order statistics that produced sv.
-__device__ __forceinline__ uint32_t threshold_scalar(const double* tab, uint32_t K, double sv, double va, double vb,
-                                                     uint32_t ca, uint32_t cb) {
-    if (sv != sv) return 0xFFFFFFFFu;  // every comparison with NaN is False
-    uint32_t less;
-    if (sv == va) less = ca - 1;
-    else if (sv == vb) less = cb - 1;
-    else if (va < sv && sv < vb) less = count_less_scalar(tab, ca, cb - 1, sv);
-    else less = count_less_scalar(tab, 0, K, sv);
-    return less + 1;
-}
-
-__device__ __forceinline__ uint32_t threshold_warp(const double* tab, uint32_t K, double sv, double va, double vb,
-                                                   uint32_t ca, uint32_t cb, int lane) {
-    if (sv != sv) return 0xFFFFFFFFu;
-    uint32_t less;
-    if (sv == va) less = ca - 1;
-    else if (sv == vb) less = cb - 1;
-    else if (va < sv && sv < vb) less = count_less(tab, ca, cb - 1, sv, lane);
-    else less = count_less(tab, 0, K, sv, lane);
-    return less + 1;
-}
-
-// The search above is the longest dependent-load chain of a node, and the node itself does not need
-// its result: no row OF THE NODE has a code strictly between the two middle order statistics, so when
+// A split stores lower_bound(table, sv) + 1 as its code threshold.  That search is the longest
+// dependent-load chain of a node, and the node itself does not need its result: no row OF THE NODE has a code strictly between the two middle order statistics, so when
 // va < sv < vb every threshold in (ca, cb] partitions the node's rows identically.  The node is split
 // with cb, the exact threshold is marked pending (thr = ca, the search's lower bound) and resolved
 // for all nodes of the tree at once, thread per node, before the hold-out rows are scored.
@@ -483,7 +437,7 @@ template <int G>
 __device__ __forceinline__ uint32_t group_ballot(bool p, int gi) {
     const uint32_t b = __ballot_sync(FULL, p);
     if (G == 32) return b;
-    return (b >> (gi * G)) & ((1u << G) - 1u);
+    return (b >> (gi * G)) & ((1u << (G & 31)) - 1u);
 }
 template <int G>
 __device__ __forceinline__ uint32_t group_sum(uint32_t v) {
@@ -525,7 +479,7 @@ __device__ void process_group(const CandCtx<CodeT, PosT>& c, WorkItem* items, ui
     const int C = a.n_classes;
     const uint32_t node = c.base + w.lpos;
     const uint32_t ltg = (1u << gl) - 1u;
-    const uint32_t gmask = (G == 32) ? FULL : ((1u << G) - 1u);
+    const uint32_t gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
 
     uint32_t p[R], l[R];
 #pragma unroll
@@ -581,7 +535,7 @@ __device__ void process_group(const CandCtx<CodeT, PosT>& c, WorkItem* items, ui
         if (searching) {
             if (use_hist) {
                 for (uint32_t b = gl; b <= K; b += G) s_h[b] = 0;
-            } else {
+            } else if (cat || G != 32 || !PACKED) {
 #pragma unroll
                 for (int q = 0; q < R; ++q)
                     if ((uint32_t)(q * G + gl) < n) s_keys[q * G + gl] = key[q];
@@ -590,7 +544,29 @@ __device__ void process_group(const CandCtx<CodeT, PosT>& c, WorkItem* items, ui
         __syncwarp();
         unsigned long long mk = 0;
         if (searching) {
-            if (!cat) {  // median (model.py:237): ranks (n-1)/2 and (n-1)/2 + 1 by all-pairs counting
+            if (!cat && G == 32 && PACKED) {
+                // median (model.py:237), whole warp on one node: bitwise radix select of the key of rank
+                // (n-1)/2 over the registers (4 compares + 4 ballots per bit; the branch is warp-uniform),
+                // then the smallest key above it.  3x fewer instructions than all-pairs at 128 rows.
+                const uint32_t k0 = (n - 1) >> 1;
+                uint32_t res = 0;
+                for (int bit = 31 - __clz((int)((K << 7) | 127u)); bit >= 0; --bit) {
+                    const uint32_t trial = res | (1u << bit);
+                    uint32_t below = 0;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) below += __popc(__ballot_sync(FULL, key[q] < trial));
+                    if (below <= k0) res = trial;
+                }
+                uint32_t nx = 0xFFFFFFFFu;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (key[q] > res) nx = min(nx, key[q]);
+                nx = group_min<32>(nx);
+                if (lane == 0) {
+                    s_sel[0] = res >> 7;
+                    s_sel[1] = nx >> 7;
+                }
+            } else if (!cat) {  // median by all-pairs rank counting against the group's keys
                 uint32_t rk[R];
 #pragma unroll
                 for (int q = 0; q < R; ++q) rk[q] = 0;
@@ -1308,7 +1284,6 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
     __shared__ uint32_t s_ticket[4];
     __shared__ uint32_t s_cnt[2][5];  // items per size class (tiny, small, medium, large, huge), this level / next level
     __shared__ uint32_t s_part[GROW_WARPS];
-    __shared__ uint32_t s_total;
     __shared__ int s_correct;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1494,101 +1469,31 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         RFMC_TICK(2);
         const uint32_t n_nodes = base;
 
-        // ---- exact code thresholds of the splits that deferred their table search ----
-        // thread per node, four nodes interleaved per thread: the binary searches are chains of
-        // dependent L2 loads, so the only way to make them cheap is to keep several in flight
-        for (uint32_t i0 = tid; i0 < n_nodes; i0 += 4 * GROW_THREADS) {
-            const double* tab[4];
-            uint32_t lo[4], hi[4];
-            double sv[4];
-            bool pend[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = i0 + u * GROW_THREADS;
-                pend[u] = i < n_nodes && (c.nodes[i].flags & FLAG_PENDING);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = i0 + u * GROW_THREADS;
-                lo[u] = hi[u] = 0;
-                sv[u] = 0.0;
-                tab[u] = a.tables;
-                if (pend[u]) {
-                    const int32_t f = c.nodes[i].feat;
-                    tab[u] = a.tables + a.tab_off[f];
-                    lo[u] = c.nodes[i].thr;
-                    hi[u] = (uint32_t)a.col_nuniq[f];
-                    sv[u] = c.nodes[i].sval;
-                }
-            }
-            while ((hi[0] > lo[0]) | (hi[1] > lo[1]) | (hi[2] > lo[2]) | (hi[3] > lo[3])) {
-                uint32_t mid[4];
-                double v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1);
-                    v[u] = (hi[u] > lo[u]) ? __ldg(&tab[u][mid[u]]) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (hi[u] > lo[u]) {
-                        if (v[u] < sv[u])
-                            lo[u] = mid[u] + 1;
-                        else
-                            hi[u] = mid[u];
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (pend[u]) {
-                    const uint32_t i = i0 + u * GROW_THREADS;
-                    c.nodes[i].thr = lo[u] + 1u;
-                    c.nodes[i].flags &= ~FLAG_PENDING;
-                }
+        // ---- exact code thresholds of the splits that deferred their table search (thread per node) ----
+        for (uint32_t i = tid; i < n_nodes; i += GROW_THREADS) {
+            const uint32_t fl = c.nodes[i].flags;
+            if (fl & FLAG_PENDING) {
+                const int32_t f = c.nodes[i].feat;
+                const double* tab = a.tables + a.tab_off[f];
+                c.nodes[i].thr = count_less_scalar(tab, c.nodes[i].thr, (uint32_t)a.col_nuniq[f], c.nodes[i].sval) + 1u;
+                c.nodes[i].flags = fl & ~FLAG_PENDING;
             }
         }
         __syncthreads();
         // ---- validationTree (model.py:296-314): hold-out rows through the finished tree ----
-        // four rows per thread at a time: a walk is a chain of dependent (node, code) loads
         int good = 0;
-        for (int i0 = tid; i0 < a.n_val; i0 += 4 * GROW_THREADS) {
-            const CodeT* src[4];
-            uint32_t node[4], lbl[4];
-            bool live[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * GROW_THREADS;
-                live[u] = i < a.n_val;
-                const int64_t row = live[u] ? (int64_t)__ldg(&idxV[i]) : 0;
-                src[u] = a.codes + row * a.stride;
-                lbl[u] = live[u] ? (uint32_t)__ldg(&a.labels[row]) : 0xFFFFu;
-                node[u] = 0;
+        for (int i = tid; i < a.n_val; i += GROW_THREADS) {
+            const int64_t row = idxV[i];
+            const CodeT* src = a.codes + row * a.stride;
+            uint32_t node = 0;
+            while (true) {
+                const rfmc_node nd = c.nodes[node];
+                if (nd.feat < 0) break;
+                uint32_t cv = __ldg(&src[nd.feat]);
+                bool go = (nd.flags & RFMC_FLAG_CATEGORICAL) ? (cv == nd.thr) : (cv >= nd.thr);
+                node = (uint32_t)nd.child + (go ? 0u : 1u);
             }
-            while (live[0] | live[1] | live[2] | live[3]) {
-                uint2 ft[4], cf[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint2* nd = reinterpret_cast<const uint2*>(&c.nodes[node[u]]);
-                    ft[u] = nd[0];  // feat, thr
-                    cf[u] = nd[1];  // child, flags
-                }
-                uint32_t cv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    live[u] = live[u] && (int32_t)ft[u].x >= 0;
-                    cv[u] = live[u] ? (uint32_t)__ldg(&src[u][ft[u].x]) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (live[u]) {
-                        const bool go = (cf[u].y & RFMC_FLAG_CATEGORICAL) ? (cv[u] == ft[u].y) : (cv[u] >= ft[u].y);
-                        node[u] = cf[u].x + (go ? 0u : 1u);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) good += (i0 + u * GROW_THREADS < a.n_val) && (c.votes[node[u]] == lbl[u]);
+            good += (c.votes[node] == __ldg(&a.labels[row]));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) good += __shfl_xor_sync(FULL, good, d);
