@@ -312,14 +312,20 @@ def run_b200(args):
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
+    batch.set_timing(True)  # events between the two kernels of a run (slot gather, grower), on the launching stream
+    k_ms = []
     for a, b in ev:
         flush_l2()
         a.record(stream)
         batch.run(stream)
         b.record(stream)
         launches += batch.launches
+        k_ms.append(batch.kernel_ms())
+    batch.set_timing(False)
     barrier()
     fit_ms = [a.elapsed_time(b) for a, b in ev]
+    gather_ms = float(np.mean([g for g, _ in k_ms]))
+    grow_ms = float(np.mean([k for _, k in k_ms]))
     fit_total_s = max_over_ranks(sum(fit_ms) / 1e3)
     fit_value = world * n_cand * args.steps / fit_total_s
     # algorithmic HBM bytes of the grower per launch (DESIGN.md "roofline"): every sampled row's
@@ -329,7 +335,10 @@ def run_b200(args):
     nf = np.array([len(f) for f in feats], dtype=np.float64)
     algo_bytes = float(((batch.n_train + batch.n_val) * (nf * w + 4 + 1)).sum() + (n_nodes.astype(np.float64) * (24 + 4 * C + 1)).sum())
     hbm_peak, peak_src = peaks()
-    grow_gbs = algo_bytes / (np.mean(fit_ms) / 1e3) / 1e9
+    grow_gbs = algo_bytes / (grow_ms / 1e3) / 1e9
+    # slot gather: every bootstrap row read once (its row id, codes and label) and written once, transposed
+    gather_bytes = float(args.n_trees * batch.n_train * (4 + 2 * (args.features * w + 1)))
+    gather_gbs = gather_bytes / (gather_ms / 1e3) / 1e9
     total_nodes = int(n_nodes.sum())
 
     # ---- fit, end to end through the public API ----
@@ -504,6 +513,20 @@ def run_b200(args):
                 "traffic": ncu_traffic("grow_kernel", workload_name(args)),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
+                "ms_per_launch": grow_ms,
+                "share_of_step": grow_ms / float(np.mean(fit_ms)),
+            },
+            "roofline_slot_gather": {
+                "kernel": "rfmc::slot_gather_kernel",
+                "bound": "hbm",
+                "achieved": gather_gbs,
+                "peak": hbm_peak,
+                "unit": "GB/s",
+                "frac": gather_gbs / hbm_peak,
+                "traffic": ncu_traffic("slot_gather_kernel", workload_name(args)),
+                "algorithmic_bytes_per_launch": gather_bytes,
+                "ms_per_launch": gather_ms,
+                "share_of_step": gather_ms / float(np.mean(fit_ms)),
             },
             "predict": {
                 "metric": "predict_rows_trees_per_s",

@@ -112,6 +112,11 @@ int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_
 int rfmc_batch_destroy(rfmc_batch* b);
 /* launches made by the last rfmc_batch_run on this batch (for bench.py's gpu_launches) */
 int rfmc_batch_launches(rfmc_batch* b);
+/* Measurement hook (bench.py's roofline): with timing enabled, rfmc_batch_run brackets its two
+ * kernels with CUDA events on the launching stream; rfmc_batch_kernel_ms waits for the last run and
+ * returns the device time of the slot gather and of the grower in milliseconds.                  */
+int rfmc_batch_set_timing(rfmc_batch* b, int enabled);
+int rfmc_batch_kernel_ms(rfmc_batch* b, float* ms_gather, float* ms_grow);
 
 /* ---- useForest / testForest / testForestProbs (forest.py:204-258, tree.py:155-212) -----------
  * A forest flattened on the host: per leaf payload a vote and class probabilities, plus the

@@ -2,9 +2,11 @@
 set -x
 CMD="python bench.py --no-cpu-baseline --e2e-steps 1"
 $CMD > gpurun_out/plainF.json 2> gpurun_out/plainF.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launchesF.csv $CMD > gpurun_out/ncu_launchF.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launchesF.csv $CMD > gpurun_out/ncu_launchF.log 2>&1
 echo rc_launch=$?
 ncu --set full --clock-control none --import-source on -k regex:grow_kernel -s 3 -c 1 -o gpurun_out/prof_growF $CMD > gpurun_out/ncu_growF.log 2>&1
 echo rc_grow=$?
+ncu --set full --clock-control none --import-source on -k regex:slot_gather_kernel -s 3 -c 1 -o gpurun_out/prof_gatherF $CMD > gpurun_out/ncu_gatherF.log 2>&1
+echo rc_gather=$?
 ncu --set full --clock-control none --import-source on -k regex:predict_kernel -s 3 -c 1 -o gpurun_out/prof_predictF $CMD > gpurun_out/ncu_predF.log 2>&1
 echo rc_pred=$?

@@ -459,6 +459,25 @@ int rfmc_batch_run(rfmc_batch* b, void* stream) {
 
 int rfmc_batch_launches(rfmc_batch* b) { return b ? b->launches : 0; }
 
+int rfmc_batch_set_timing(rfmc_batch* b, int enabled) {
+    RFMC_REQUIRE(b != nullptr, "batch is NULL");
+    RFMC_CUDA(cudaSetDevice(b->ds->device));
+    if (enabled && !b->ev[0])
+        for (int i = 0; i < 3; ++i) RFMC_CUDA(cudaEventCreate(&b->ev[i]));
+    b->timing = enabled != 0;
+    return 0;
+}
+
+int rfmc_batch_kernel_ms(rfmc_batch* b, float* ms_gather, float* ms_grow) {
+    RFMC_REQUIRE(b != nullptr && ms_gather != nullptr && ms_grow != nullptr, "NULL argument");
+    RFMC_REQUIRE(b->timing && b->ev[0], "timing was not enabled before the run");
+    RFMC_CUDA(cudaSetDevice(b->ds->device));
+    RFMC_CUDA(cudaEventSynchronize(b->ev[2]));
+    RFMC_CUDA(cudaEventElapsedTime(ms_gather, b->ev[0], b->ev[1]));
+    RFMC_CUDA(cudaEventElapsedTime(ms_grow, b->ev[1], b->ev[2]));
+    return 0;
+}
+
 int rfmc_batch_results(rfmc_batch* b, int32_t* correct, int32_t* n_nodes) {
     RFMC_REQUIRE(b != nullptr, "batch is NULL");
     RFMC_CUDA(cudaSetDevice(b->ds->device));
@@ -554,6 +573,8 @@ int rfmc_batch_destroy(rfmc_batch* b) {
     release(b->d_votes);
     release(b->d_nnodes);
     release(b->d_correct);
+    for (int i = 0; i < 3; ++i)
+        if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
     return 0;
 }

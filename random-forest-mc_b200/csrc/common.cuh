@@ -85,6 +85,8 @@ struct rfmc_batch {
     std::vector<int32_t> h_nnodes;
     bool have_results = false;
     cudaStream_t stream = nullptr;
+    bool timing = false;  // measurement hook: events around the two kernels of a run
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 struct PredictPipe;

@@ -1566,6 +1566,7 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
         auto gk = slot_gather_kernel<CodeT>;
         RFMC_CUDA(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
         dim3 grid((unsigned)((b->n_train + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32)), (unsigned)b->n_slots);
+        if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[0], stream));
         gk<<<grid, GATHER_WARPS * 32, gsm, stream>>>((const CodeT*)ds->d_codes, ds->stride, ds->d_labels, ds->n_features,
                                                       b->d_idx_train, b->n_train, b->nt_pad, (CodeT*)b->d_cc, b->d_lab);
         RFMC_CUDA(cudaGetLastError());
@@ -1573,8 +1574,10 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     auto k = grow_kernel<CodeT, PosT>;
     const size_t smem = a.use_smem ? dyn : 0;
     if (smem > 0) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[1], stream));
     k<<<b->grid, GROW_THREADS, smem, stream>>>(a);
     RFMC_CUDA(cudaGetLastError());
+    if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[2], stream));
     b->launches = 2;
     return 0;
 }

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "rfmc_batch_pack": (C.c_int, [_p, _p, C.c_int32, _p, _p, C.c_int, _p]),
     "rfmc_batch_destroy": (C.c_int, [_p]),
     "rfmc_batch_launches": (C.c_int, [_p]),
+    "rfmc_batch_set_timing": (C.c_int, [_p, C.c_int]),
+    "rfmc_batch_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rfmc_forest_create": (C.c_int, [C.c_int, _p, C.c_int64, _p, C.c_int32, C.c_int64, _p, _p, _p, _p, C.c_int32, _p, C.c_double, C.POINTER(_p)]),
     "rfmc_forest_destroy": (C.c_int, [_p]),
     "rfmc_forest_predict": (C.c_int, [_p, _p, C.c_int, C.c_int64, C.c_int64, C.c_int32, _p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
@@ -308,6 +310,16 @@ class GrowBatch:
     @property
     def launches(self) -> int:
         return load_library().rfmc_batch_launches(self._h)
+
+    def set_timing(self, enabled: bool = True) -> None:
+        """Measurement hook: bracket the kernels of every following run() with CUDA events."""
+        _check(load_library().rfmc_batch_set_timing(self._h, int(bool(enabled))))
+
+    def kernel_ms(self):
+        """(slot gather ms, grower ms) of the last run(); waits for it."""
+        g, k = C.c_float(0), C.c_float(0)
+        _check(load_library().rfmc_batch_kernel_ms(self._h, C.byref(g), C.byref(k)))
+        return float(g.value), float(k.value)
 
     def fetch(self, cand_ids: Sequence[int]) -> List[TreeSoA]:
         """Device -> host copy of the node tables of the selected candidates."""
