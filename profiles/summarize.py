@@ -61,7 +61,7 @@ if os.path.exists(src):
         lines.append(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {sum(v)/tot*100:.1f}% |")
     lines.append("")
 traffic = {}
-for rep, name in (("prof_growF", "grow_kernel"), ("prof_predictF", "predict_kernel")):
+for rep, name in (("prof_growF", "grow_kernel"), ("prof_gatherF", "slot_gather_kernel"), ("prof_predictF", "predict_kernel")):
     path = os.path.join(OUT, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
