@@ -87,6 +87,27 @@ int rfmc_dataset_create(int device, const void* codes, int code_width, int64_t n
                         const double* tables, rfmc_dataset** out);
 int rfmc_dataset_destroy(rfmc_dataset* ds);
 
+/* ---- process_dataset on the device (model.py:162-195) --------------------
+ * Replaces the construction of `dataset_numpy` (model.py:194) by a rank-coded matrix built in HBM.
+ * col_ptr[c]   host column of n_rows contiguous elements, rows with missing values already dropped
+ *              (model.py:181); col_dtype[c] = RFMC_DT_* (below).  Numeric columns go to the GPU raw:
+ *              sorted distinct values (the value table) by a bitonic sort + ordered compaction, then
+ *              code = 1 + rank by binary search.  RFMC_DT_CODE = int32 codes 1..cat_nunique[c] of a
+ *              categorical column, ranked on the host in np.unique order (strings stay on the host).
+ * col_tag[c]   packed arithmetic tag of numeric columns (RFMC_TAG_* | bits<<8 | signed<<16)
+ * labels       [n_rows] class code in sorted-label order
+ * The code width (1/2/4 bytes) and the row pitch (odd number of 32-bit words) are chosen by the
+ * library; read them back with rfmc_dataset_describe.  table_off [n_features+1], tables_out
+ * [table_off[n_features]] float64.  rfmc_dataset_codes copies the matrix to the host
+ * ([n_rows][row_stride] of code_width bytes) for inspection and tests.                           */
+int rfmc_dataset_encode(int device, int64_t n_rows, int32_t n_features, const void* const* col_ptr,
+                        const int32_t* col_dtype, const int32_t* col_tag, const int32_t* cat_nunique,
+                        const uint8_t* labels, int32_t n_classes, rfmc_dataset** out);
+int rfmc_dataset_describe(rfmc_dataset* ds, int32_t* code_width, int64_t* row_stride, int32_t* col_nunique,
+                          int64_t* table_off);
+int rfmc_dataset_tables(rfmc_dataset* ds, double* tables_out);
+int rfmc_dataset_codes(rfmc_dataset* ds, void* codes_out);
+
 /* ---- plantTree + validationTree for a batch of candidates (model.py:222-314) ----------------
  * The host draws rows and features with the reference's own RNGs (model.py:198-219) and hands
  * them over; the GPU grows every candidate and scores it on its slot's hold-out rows.

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librfmc_b200.so")
-SOURCES = ["abi.cu", "grow.cu", "predict.cu"]
+SOURCES = ["abi.cu", "grow.cu", "predict.cu", "rank_encode.cu"]
 HOST_SOURCES = ["host_rng.cpp"]  # plain g++ (-O3, AVX2 clones dispatched at load time)
 FLAGS = [
     "-O3",

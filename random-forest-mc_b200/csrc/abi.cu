@@ -374,6 +374,180 @@ int rfmc_dataset_create(int device, const void* codes, int code_width, int64_t n
     return 0;
 }
 
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case RFMC_DT_F64: case RFMC_DT_I64: case RFMC_DT_U64: return 8;
+        case RFMC_DT_F32: case RFMC_DT_I32: case RFMC_DT_U32: case RFMC_DT_CODE: return 4;
+        case RFMC_DT_I16: case RFMC_DT_U16: return 2;
+        case RFMC_DT_I8: case RFMC_DT_U8: return 1;
+    }
+    return 0;
+}
+
+namespace {
+// scratch of rfmc_dataset_encode, released on every exit path
+struct EncodeScratch {
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    void* raw[2] = {nullptr, nullptr};
+    uint64_t* keys[2] = {nullptr, nullptr};
+    uint32_t* block[2] = {nullptr, nullptr};
+    double* table[2] = {nullptr, nullptr};
+    uint32_t* n_distinct[2] = {nullptr, nullptr};
+    uint32_t* col_codes = nullptr;
+    ~EncodeScratch() {
+        for (int s = 0; s < 2; ++s) {
+            if (stream[s]) {
+                cudaStreamSynchronize(stream[s]);
+                cudaStreamDestroy(stream[s]);
+            }
+            release(raw[s]);
+            release(keys[s]);
+            release(block[s]);
+            release(table[s]);
+            release(n_distinct[s]);
+        }
+        release(col_codes);
+    }
+};
+}  // namespace
+
+int rfmc_dataset_encode(int device, int64_t n_rows, int32_t n_features, const void* const* col_ptr,
+                        const int32_t* col_dtype, const int32_t* col_tag, const int32_t* cat_nunique,
+                        const uint8_t* labels, int32_t n_classes, rfmc_dataset** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_REQUIRE(n_rows > 0 && n_rows < (1ll << 31) && n_features > 0 && n_features <= 65535, "bad matrix shape");
+    RFMC_REQUIRE(n_classes >= 1 && n_classes <= RFMC_MAX_CLASSES, "n_classes must be in 1..64");
+    RFMC_REQUIRE(col_ptr && col_dtype && col_tag && cat_nunique && labels, "NULL argument");
+    for (int c = 0; c < n_features; ++c) RFMC_REQUIRE(dtype_size(col_dtype[c]) != 0 && col_ptr[c], "bad column dtype / pointer");
+    RFMC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RFMC_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int64_t padded = rank_padded_rows(n_rows);
+    const int nb = rank_scan_blocks(padded);
+    EncodeScratch sc;
+    for (int s = 0; s < 2; ++s) {
+        RFMC_CUDA(cudaStreamCreateWithFlags(&sc.stream[s], cudaStreamNonBlocking));
+        RFMC_CUDA(dev_alloc(&sc.raw[s], (size_t)n_rows * 8));
+        RFMC_CUDA(dev_alloc((void**)&sc.keys[s], (size_t)padded * 8));
+        RFMC_CUDA(dev_alloc((void**)&sc.block[s], (size_t)nb * 4));
+        RFMC_CUDA(dev_alloc((void**)&sc.table[s], (size_t)n_rows * 8));
+        RFMC_CUDA(dev_alloc((void**)&sc.n_distinct[s], 4));
+    }
+    RFMC_CUDA(dev_alloc((void**)&sc.col_codes, (size_t)n_features * n_rows * 4));
+
+    std::vector<std::vector<double>> tables(n_features);
+    std::vector<int32_t> nuniq(n_features, 0);
+    int pending[2] = {-1, -1};
+    auto harvest = [&](int s) -> int {  // wait for the column in flight on stream s and fetch its value table
+        const int c = pending[s];
+        if (c < 0) return 0;
+        pending[s] = -1;
+        RFMC_CUDA(cudaStreamSynchronize(sc.stream[s]));
+        uint32_t m = 0;
+        RFMC_CUDA(cudaMemcpy(&m, sc.n_distinct[s], 4, cudaMemcpyDeviceToHost));
+        tables[c].resize(m);
+        if (m) RFMC_CUDA(cudaMemcpy(tables[c].data(), sc.table[s], (size_t)m * 8, cudaMemcpyDeviceToHost));
+        nuniq[c] = (int32_t)m;
+        return 0;
+    };
+    int turn = 0;
+    for (int c = 0; c < n_features; ++c) {
+        if (col_dtype[c] == RFMC_DT_CODE) continue;
+        const int s = turn;
+        turn ^= 1;
+        if (harvest(s)) return 1;
+        RFMC_CUDA(cudaMemcpyAsync(sc.raw[s], col_ptr[c], (size_t)n_rows * dtype_size(col_dtype[c]), cudaMemcpyHostToDevice,
+                                  sc.stream[s]));
+        if (launch_rank_column(sc.raw[s], col_dtype[c], n_rows, padded, sc.keys[s], sc.block[s], sc.table[s],
+                               sc.n_distinct[s], sc.col_codes + (size_t)c * n_rows, sc.stream[s]))
+            return 1;
+        pending[s] = c;
+    }
+    for (int c = 0; c < n_features; ++c) {  // categorical columns: final codes ranked on the host (strings stay there)
+        if (col_dtype[c] != RFMC_DT_CODE) continue;
+        RFMC_REQUIRE(cat_nunique[c] >= 0, "cat_nunique must be >= 0");
+        nuniq[c] = cat_nunique[c];
+        RFMC_CUDA(cudaMemcpyAsync(sc.col_codes + (size_t)c * n_rows, col_ptr[c], (size_t)n_rows * 4, cudaMemcpyHostToDevice,
+                                  sc.stream[turn]));
+    }
+    if (harvest(0) || harvest(1)) return 1;
+    RFMC_CUDA(cudaStreamSynchronize(sc.stream[0]));
+    RFMC_CUDA(cudaStreamSynchronize(sc.stream[1]));
+
+    int32_t top = 1;
+    for (int c = 0; c < n_features; ++c) top = nuniq[c] > top ? nuniq[c] : top;
+    const int width = top <= 0xFF ? 1 : top <= 0xFFFF ? 2 : 4;
+    int64_t words = ((int64_t)n_features * width + 3) / 4;
+    if (words % 2 == 0) ++words;  // odd number of 32-bit words per row: conflict-free shared-memory tiles
+    const int64_t stride = words * 4 / width;
+
+    rfmc_dataset* ds = new rfmc_dataset();
+    ds->device = device;
+    ds->code_width = width;
+    ds->n_rows = n_rows;
+    ds->n_features = n_features;
+    ds->stride = stride;
+    ds->n_classes = n_classes;
+    ds->sm_count = prop.multiProcessorCount;
+    ds->h_nuniq = nuniq;
+    ds->h_taboff.assign(n_features + 1, 0);
+    std::vector<uint8_t> kind(n_features);
+    for (int c = 0; c < n_features; ++c) {
+        kind[c] = col_dtype[c] == RFMC_DT_CODE ? RFMC_KIND_CATEGORICAL : RFMC_KIND_NUMERIC;
+        ds->h_taboff[c + 1] = ds->h_taboff[c] + (int64_t)tables[c].size();
+    }
+    ds->h_tables.reserve((size_t)ds->h_taboff[n_features] + 1);
+    for (int c = 0; c < n_features; ++c) ds->h_tables.insert(ds->h_tables.end(), tables[c].begin(), tables[c].end());
+    int rc = 0;
+    rc |= reserve((uint8_t**)&ds->d_codes, (size_t)n_rows * stride * width);
+    rc |= upload(&ds->d_labels, labels, (size_t)n_rows, sc.stream[0]);
+    rc |= upload(&ds->d_kind, kind.data(), (size_t)n_features, sc.stream[0]);
+    rc |= upload(&ds->d_tag, col_tag, (size_t)n_features, sc.stream[0]);
+    rc |= upload(&ds->d_nuniq, nuniq.data(), (size_t)n_features, sc.stream[0]);
+    rc |= upload(&ds->d_taboff, ds->h_taboff.data(), (size_t)n_features + 1, sc.stream[0]);
+    if (ds->h_tables.empty())
+        rc |= reserve(&ds->d_tables, 1);
+    else
+        rc |= upload(&ds->d_tables, ds->h_tables.data(), ds->h_tables.size(), sc.stream[0]);
+    if (rc == 0) rc = launch_interleave(sc.col_codes, n_rows, n_features, stride, width, ds->d_codes, sc.stream[0]);
+    if (rc == 0 && cudaStreamSynchronize(sc.stream[0]) != cudaSuccess) {
+        set_error(std::string("dataset encode failed: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+    }
+    if (rc) {
+        rfmc_dataset_destroy(ds);
+        return 1;
+    }
+    *out = ds;
+    return 0;
+}
+
+int rfmc_dataset_describe(rfmc_dataset* ds, int32_t* code_width, int64_t* row_stride, int32_t* col_nunique,
+                          int64_t* table_off) {
+    RFMC_REQUIRE(ds != nullptr, "dataset is NULL");
+    RFMC_REQUIRE((int)ds->h_nuniq.size() == ds->n_features, "dataset was not built by rfmc_dataset_encode");
+    if (code_width) *code_width = ds->code_width;
+    if (row_stride) *row_stride = ds->stride;
+    if (col_nunique) memcpy(col_nunique, ds->h_nuniq.data(), sizeof(int32_t) * ds->n_features);
+    if (table_off) memcpy(table_off, ds->h_taboff.data(), sizeof(int64_t) * (ds->n_features + 1));
+    return 0;
+}
+
+int rfmc_dataset_tables(rfmc_dataset* ds, double* tables_out) {
+    RFMC_REQUIRE(ds != nullptr && tables_out != nullptr, "NULL argument");
+    RFMC_REQUIRE((int)ds->h_nuniq.size() == ds->n_features, "dataset was not built by rfmc_dataset_encode");
+    if (!ds->h_tables.empty()) memcpy(tables_out, ds->h_tables.data(), sizeof(double) * ds->h_tables.size());
+    return 0;
+}
+
+int rfmc_dataset_codes(rfmc_dataset* ds, void* codes_out) {
+    RFMC_REQUIRE(ds != nullptr && codes_out != nullptr, "NULL argument");
+    RFMC_CUDA(cudaSetDevice(ds->device));
+    RFMC_CUDA(cudaMemcpy(codes_out, ds->d_codes, (size_t)ds->n_rows * ds->stride * ds->code_width, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int rfmc_dataset_destroy(rfmc_dataset* ds) {
     if (!ds) return 0;
     cudaSetDevice(ds->device);
@@ -750,16 +924,6 @@ int rfmc_forest_set_codebook(rfmc_forest* f, int32_t n_features, const int64_t* 
     }
     f->n_features_book = n_features;
     return rc;
-}
-
-static size_t dtype_size(int dt) {
-    switch (dt) {
-        case RFMC_DT_F64: case RFMC_DT_I64: case RFMC_DT_U64: return 8;
-        case RFMC_DT_F32: case RFMC_DT_I32: case RFMC_DT_U32: case RFMC_DT_CODE: return 4;
-        case RFMC_DT_I16: case RFMC_DT_U16: return 2;
-        case RFMC_DT_I8: case RFMC_DT_U8: return 1;
-    }
-    return 0;
 }
 
 int rfmc_forest_predict_frame(rfmc_forest* f, int64_t n_rows, int32_t n_features, int64_t row_stride, int code_width,

@@ -54,6 +54,10 @@ struct rfmc_dataset {
     int32_t* d_nuniq = nullptr;
     int64_t* d_taboff = nullptr;
     double* d_tables = nullptr;
+    // host copies of what rfmc_dataset_encode derived on the device (rfmc_dataset_describe / _tables)
+    std::vector<int32_t> h_nuniq;
+    std::vector<int64_t> h_taboff;
+    std::vector<double> h_tables;
 };
 
 struct rfmc_batch {
@@ -127,4 +131,10 @@ int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n
 int launch_encode(const void* d_raw, const int64_t* d_col_off, const int32_t* d_col_feat, const int32_t* d_col_dtype,
                   int32_t n_cols, int64_t n_rows, int64_t row_stride, int code_width, const double* d_thresholds,
                   const int64_t* d_thr_off, void* d_codes, cudaStream_t stream);
+int64_t rank_padded_rows(int64_t n_rows);
+int rank_scan_blocks(int64_t padded);
+int launch_rank_column(const void* d_raw, int dtype, int64_t n_rows, int64_t padded, uint64_t* d_keys, uint32_t* d_block,
+                       double* d_table, uint32_t* d_n_distinct, uint32_t* d_col_codes, cudaStream_t stream);
+int launch_interleave(const uint32_t* d_col_codes, int64_t n_rows, int32_t n_features, int64_t stride, int code_width,
+                      void* d_codes, cudaStream_t stream);
 }  // namespace rfmc

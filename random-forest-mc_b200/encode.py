@@ -25,8 +25,8 @@ consecutive rows copied verbatim into shared memory is bank-conflict-free for th
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 import pandas as pd
@@ -56,22 +56,47 @@ class ColumnCode:
         return len(self.uniq)
 
 
-@dataclass
 class EncodedDataset:
-    feature_cols: List[str]
-    columns: List[ColumnCode]
-    codes: np.ndarray  # [n_rows, stride] uint8/16/32, row-major, pitch = odd number of 32-bit words
-    width: int  # bytes per code
-    stride: int  # elements per row
-    labels: np.ndarray  # uint8 [n_rows]: index into class_sorted
-    class_sorted: List  # labels in np.unique order (leaf-dict key order)
-    class_vals: List  # first-appearance order (model.py:184)
-    sorted_to_classvals: np.ndarray  # int32 [C]
-    class_rows: List[np.ndarray] = field(default_factory=list)  # per class_vals entry: ascending row ids
+    """Host-side description of the rank-coded training matrix.  The matrix itself lives in HBM
+    (``engine.DeviceDataset``); ``codes`` is a host copy fetched on first use (tests, inspection)."""
+
+    def __init__(
+        self,
+        feature_cols: List[str],
+        columns: List[ColumnCode],
+        codes: Optional[np.ndarray],  # [n_rows, stride] uint8/16/32, row-major, pitch = odd number of 32-bit words
+        width: int,  # bytes per code
+        stride: int,  # elements per row
+        labels: np.ndarray,  # uint8 [n_rows]: index into class_sorted
+        class_sorted: List,  # labels in np.unique order (leaf-dict key order)
+        class_vals: List,  # first-appearance order (model.py:184)
+        sorted_to_classvals: np.ndarray,  # int32 [C]
+        class_rows: Optional[List[np.ndarray]] = None,  # per class_vals entry: ascending row ids
+        fetch_codes: Optional[Callable[[], np.ndarray]] = None,
+    ):
+        self.feature_cols = feature_cols
+        self.columns = columns
+        self._codes = codes
+        self._fetch_codes = fetch_codes
+        self.width = width
+        self.stride = stride
+        self.labels = labels
+        self.class_sorted = class_sorted
+        self.class_vals = class_vals
+        self.sorted_to_classvals = sorted_to_classvals
+        self.class_rows = class_rows if class_rows is not None else []
+
+    @property
+    def codes(self) -> np.ndarray:
+        if self._codes is None:
+            if self._fetch_codes is None:
+                raise RuntimeError("the code matrix of this dataset is not available on the host")
+            self._codes = self._fetch_codes()
+        return self._codes
 
     @property
     def n_rows(self) -> int:
-        return self.codes.shape[0]
+        return len(self.labels)
 
     @property
     def n_features(self) -> int:
@@ -90,8 +115,64 @@ def odd_word_stride(n_features: int, width: int) -> int:
     return words * 4 // width
 
 
-def _rank(values: np.ndarray):
-    """(sorted distinct values, 0-based rank of every element).  Same order as np.unique."""
+class LazyColumns(dict):
+    """``dataset_numpy`` (model.py:194): ``{col: ndarray}``.  Numeric columns are views of the frame and
+    are stored right away; string columns (Arrow-backed in pandas 3) become object arrays only when
+    someone reads them -- the engine ranks them inside Arrow and never needs the object arrays."""
+
+    def __init__(self, frame: pd.DataFrame, eager: Sequence[str]):
+        super().__init__()
+        self._frame = frame
+        self._order = list(frame.columns)
+        for c in eager:
+            dict.__setitem__(self, c, frame[c].to_numpy())
+
+    def __missing__(self, key):
+        if key not in self._order:
+            raise KeyError(key)
+        v = self._frame[key].to_numpy()
+        dict.__setitem__(self, key, v)
+        return v
+
+    def column(self, key) -> pd.Series:
+        return self._frame[key]
+
+    def __contains__(self, key):
+        return key in self._order
+
+    def __iter__(self):
+        return iter(self._order)
+
+    def __len__(self):
+        return len(self._order)
+
+    def keys(self):
+        return list(self._order)
+
+    def values(self):
+        return [self[k] for k in self._order]
+
+    def items(self):
+        return [(k, self[k]) for k in self._order]
+
+    def get(self, key, default=None):
+        return self[key] if key in self._order else default
+
+
+def rank_series(col: pd.Series):
+    """rank_values for a frame column: Series.factorize keeps Arrow-backed strings in Arrow
+    (dictionary encode, GIL released); only the distinct values become Python objects."""
+    inv0, firsts = col.factorize(use_na_sentinel=False)
+    firsts = firsts.to_numpy()  # the dtype Series.to_numpy() would give (model.py:194): object for strings, bool for bool
+    order = np.argsort(firsts, kind="stable")
+    rank_of = np.empty(len(firsts), dtype=np.int64)
+    rank_of[order] = np.arange(len(firsts))
+    return firsts[order], rank_of[inv0]
+
+
+def rank_values(values: np.ndarray):
+    """(sorted distinct values, 0-based rank of every element).  Same order as np.unique.  Host code,
+    used for categorical columns and the target: strings never go to the GPU."""
     # factorize is O(n) hashing; sorting only the distinct values keeps np.unique's order
     # (object arrays sort with Python comparisons in both, so "10" < "2" as in the reference)
     inv0, firsts = pd.factorize(values, sort=False)
@@ -102,59 +183,29 @@ def _rank(values: np.ndarray):
     return firsts[order], rank_of[inv0]
 
 
-def encode_column(name: str, values: np.ndarray, numeric: bool):
-    uniq, rank = _rank(values)
-    if numeric and values.dtype.kind == "f":
-        # -0.0 and 0.0 compare equal and share one code; which of the two the reference prints as a
-        # split value depends on numpy's introselect element order, so the engine always emits +0.0
-        uniq = uniq + uniq.dtype.type(0)
-    if not numeric:
-        return ColumnCode(name, KIND_CATEGORICAL, uniq, None, 0), rank
-    dt = values.dtype
+def numeric_tag(name: str, dt: np.dtype) -> int:
+    """Packed arithmetic tag of a numeric column: the dtype numpy's median interpolates in."""
     if dt == np.float64:
-        tag = pack_tag(TAG_F64)
-    elif dt == np.float32:
-        tag = pack_tag(TAG_F32)
-    elif dt.kind in "iu":
-        if len(uniq) and max(abs(int(uniq[0])), abs(int(uniq[-1]))) >= 2**52:
-            raise NotImplementedError(
-                f"column {name!r}: integer magnitudes >= 2**52 are not representable in the float64 value table"
-            )
-        tag = pack_tag(TAG_INT, dt.itemsize * 8, dt.kind == "i")
-    else:
-        raise NotImplementedError(f"column {name!r}: numeric dtype {dt} is not supported by the B200 engine")
-    return ColumnCode(name, KIND_NUMERIC, uniq, uniq.astype(np.float64), tag), rank
+        return pack_tag(TAG_F64)
+    if dt == np.float32:
+        return pack_tag(TAG_F32)
+    if dt.kind in "iu" and dt.itemsize in (1, 2, 4, 8):
+        return pack_tag(TAG_INT, dt.itemsize * 8, dt.kind == "i")
+    raise NotImplementedError(f"column {name!r}: numeric dtype {dt} is not supported by the B200 engine")
 
 
-def encode_dataset(
-    dataset_numpy: Dict[str, np.ndarray],
-    feature_cols: Sequence[str],
-    numeric_cols: Sequence[str],
-    target_col: str,
-    class_vals: Sequence,
-) -> EncodedDataset:
-    """Encode the (already NaN-free) column dict produced by ``process_dataset``."""
-    numeric = set(numeric_cols)
-    cols: List[ColumnCode] = []
-    ranks = []
-    for name in feature_cols:
-        cc, rank = encode_column(name, dataset_numpy[name], name in numeric)
-        cols.append(cc)
-        ranks.append(rank)
-    n = len(dataset_numpy[target_col])
-    top = max([c.n_unique for c in cols] + [1])
-    if top <= 0xFF:
-        dtype, width = np.uint8, 1
-    elif top <= 0xFFFF:
-        dtype, width = np.uint16, 2
-    else:
-        dtype, width = np.uint32, 4
-    stride = odd_word_stride(len(cols), width)
-    codes = np.zeros((n, stride), dtype=dtype)
-    for j, rank in enumerate(ranks):
-        codes[:, j] = rank + 1
-    y = dataset_numpy[target_col]
-    class_sorted, yrank = _rank(y)
+def check_int_range(name: str, lo: float, hi: float) -> None:
+    if max(abs(lo), abs(hi)) >= 2**52:
+        raise NotImplementedError(
+            f"column {name!r}: integer magnitudes >= 2**52 are not representable in the float64 value table"
+        )
+
+
+def encode_labels(y, class_vals: Sequence):
+    """Target column -> (class_sorted, labels uint8, sorted_to_classvals, class_rows).  Labels are
+    coded in lexicographic order (the key order of every leaf dict, model.py:224-227); class_rows
+    are the cached ``indices[target_vals == val]`` of model.py:205, in ``class_vals`` order."""
+    class_sorted, yrank = rank_series(y) if isinstance(y, pd.Series) else rank_values(y)
     if len(class_sorted) > 255:
         raise NotImplementedError("more than 255 classes")
     class_sorted = list(class_sorted)
@@ -162,18 +213,7 @@ def encode_dataset(
     labels = yrank.astype(np.uint8)
     rows_by_sorted = [np.flatnonzero(labels == k) for k in range(len(class_sorted))]
     class_rows = [rows_by_sorted[class_sorted.index(c)] for c in class_vals]
-    return EncodedDataset(
-        feature_cols=list(feature_cols),
-        columns=cols,
-        codes=codes,
-        width=width,
-        stride=stride,
-        labels=labels,
-        class_sorted=class_sorted,
-        class_vals=list(class_vals),
-        sorted_to_classvals=s2c,
-        class_rows=class_rows,
-    )
+    return class_sorted, labels, s2c, class_rows
 
 
 def median_value(va: float, vb: float, odd: bool, tag: int) -> float:

@@ -12,7 +12,17 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .encode import KIND_CATEGORICAL, EncodedDataset
+from .encode import (
+    KIND_CATEGORICAL,
+    KIND_NUMERIC,
+    ColumnCode,
+    EncodedDataset,
+    check_int_range,
+    encode_labels,
+    numeric_tag,
+    rank_series,
+    rank_values,
+)
 from .flat import NODE_DTYPE, TreeSoA
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,6 +53,10 @@ _SIGNATURES = {
     "rfmc_stream_destroy": (C.c_int, [C.c_int, _p]),
     "rfmc_dataset_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int32, C.c_int64, _p, C.c_int32, _p, _p, _p, _p, _p, C.POINTER(_p)]),
     "rfmc_dataset_destroy": (C.c_int, [_p]),
+    "rfmc_dataset_encode": (C.c_int, [C.c_int, C.c_int64, C.c_int32, _p, _p, _p, _p, _p, C.c_int32, C.POINTER(_p)]),
+    "rfmc_dataset_describe": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), _p, _p]),
+    "rfmc_dataset_tables": (C.c_int, [_p, _p]),
+    "rfmc_dataset_codes": (C.c_int, [_p, _p]),
     "rfmc_batch_create": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
     "rfmc_batch_run": (C.c_int, [_p, _p]),
     "rfmc_batch_results": (C.c_int, [_p, _p, _p]),
@@ -253,6 +267,111 @@ class DeviceDataset:
             self.close()
         except Exception:
             pass
+
+
+# numpy dtype -> RFMC_DT_* (include/rfmc_b200.h)
+_RAW_DTYPES = {"f8": 0, "f4": 1, "i8": 2, "i4": 3, "i2": 4, "i1": 5, "u1": 6, "u2": 7, "u4": 8, "u8": 9}
+DT_CODE = 10
+
+
+def encode_dataset_device(dataset_numpy, feature_cols, numeric_cols, target_col, class_vals, device: int = 0):
+    """``process_dataset``'s encode step on the GPU (rfmc_dataset_encode): numeric columns are sent
+    raw and rank-coded on the device; categorical columns and the target are ranked on the host
+    (strings) and sent as codes.  Returns (EncodedDataset, DeviceDataset); the code matrix stays in
+    HBM and is copied to the host only if someone reads ``EncodedDataset.codes``."""
+    require_gpu()
+    numeric = set(numeric_cols)
+    series_of = getattr(dataset_numpy, "column", None)  # LazyColumns: rank strings inside Arrow
+    n = len(series_of(target_col)) if series_of else len(dataset_numpy[target_col])
+    nfeat = len(feature_cols)
+    keep = []  # host buffers the pointers refer to
+    ptrs = (C.c_void_p * nfeat)()
+    dtypes = np.zeros(nfeat, dtype=np.int32)
+    tags = np.zeros(nfeat, dtype=np.int32)
+    cat_n = np.zeros(nfeat, dtype=np.int32)
+    cat_uniq = {}
+    def rank_categorical(name):
+        uniq, rank = rank_series(series_of(name)) if series_of else rank_values(dataset_numpy[name])
+        return uniq, (rank + 1).astype(np.int32)
+
+    cat_names = [name for name in feature_cols if name not in numeric]
+    if len(cat_names) > 1 and n >= 100_000:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(8, len(cat_names))) as pool:
+            ranked = dict(zip(cat_names, pool.map(rank_categorical, cat_names)))
+    else:
+        ranked = {name: rank_categorical(name) for name in cat_names}
+    for j, name in enumerate(feature_cols):
+        if name in numeric:
+            v = dataset_numpy[name]
+            tags[j] = numeric_tag(name, v.dtype)
+            v = np.ascontiguousarray(v, dtype=v.dtype.newbyteorder("="))
+            dtypes[j] = _RAW_DTYPES[v.dtype.str[1:]]
+        else:
+            cat_uniq[j], v = ranked[name]
+            cat_n[j] = len(cat_uniq[j])
+            dtypes[j] = DT_CODE
+        keep.append(v)
+        ptrs[j] = v.ctypes.data
+    class_sorted, labels, s2c, class_rows = encode_labels(
+        series_of(target_col) if series_of else dataset_numpy[target_col], class_vals
+    )
+    if len(class_sorted) > MAX_CLASSES:
+        raise NotImplementedError(f"more than {MAX_CLASSES} classes")
+    h = _p()
+    _check(
+        load_library().rfmc_dataset_encode(
+            device, n, nfeat, C.cast(ptrs, _p), _ptr(dtypes), _ptr(tags), _ptr(cat_n), _ptr(labels), len(class_sorted),
+            C.byref(h),
+        )
+    )
+    dev = DeviceDataset.__new__(DeviceDataset)
+    dev.device = device
+    dev._h = h
+    try:
+        width, stride = C.c_int32(0), C.c_int64(0)
+        nuniq = np.zeros(nfeat, dtype=np.int32)
+        off = np.zeros(nfeat + 1, dtype=np.int64)
+        _check(load_library().rfmc_dataset_describe(h, C.byref(width), C.byref(stride), _ptr(nuniq), _ptr(off)))
+        tables = np.zeros(max(1, int(off[-1])), dtype=np.float64)
+        _check(load_library().rfmc_dataset_tables(h, _ptr(tables)))
+        cols = []
+        for j, name in enumerate(feature_cols):
+            if j in cat_uniq:
+                cols.append(ColumnCode(name, KIND_CATEGORICAL, cat_uniq[j], None, 0))
+                continue
+            table = tables[off[j] : off[j + 1]].copy()
+            dt = dataset_numpy[name].dtype
+            if dt.kind in "iu" and len(table):
+                check_int_range(name, float(table[0]), float(table[-1]))
+            cols.append(ColumnCode(name, KIND_NUMERIC, table.astype(dt), table, int(tags[j])))
+    except Exception:
+        dev.close()
+        raise
+    code_dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width.value]
+    shape = (n, int(stride.value))
+
+    def fetch_codes():
+        out = np.empty(shape, dtype=code_dtype)
+        _check(load_library().rfmc_dataset_codes(dev._h, _ptr(out)))
+        return out
+
+    enc = EncodedDataset(
+        feature_cols=list(feature_cols),
+        columns=cols,
+        codes=None,
+        width=int(width.value),
+        stride=int(stride.value),
+        labels=labels,
+        class_sorted=class_sorted,
+        class_vals=list(class_vals),
+        sorted_to_classvals=s2c,
+        class_rows=class_rows,
+        fetch_codes=fetch_codes,
+    )
+    dev.enc = enc
+    return enc, dev
 
 
 class GrowBatch:

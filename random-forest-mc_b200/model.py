@@ -31,7 +31,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .encode import EncodedDataset, encode_dataset
+from .encode import EncodedDataset, LazyColumns
 from .flat import encode_frame, forest_tables_from_dicts, used_feature_ids
 from .forest import BaseRandomForestMC
 from .tree import DecisionTreeMC
@@ -176,15 +176,17 @@ class RandomForestMC(BaseRandomForestMC):
             log.warning("Temporal features ordering disable: you do not have all orderable features!")
         min_class = dataset[self.target_col].value_counts().min()
         self._N = min(self._N, min_class)
-        self.dataset_numpy = {col: dataset[col].to_numpy() for col in dataset.columns}
+        self.dataset_numpy = LazyColumns(dataset, numeric_cols)
         self.n_samples = len(dataset)
         # engine: encode once, upload once
         if self.min_samples_split < 1:
             raise ValueError("min_samples_split must be >= 1")
-        self.encoded = encode_dataset(self.dataset_numpy, feature_cols, numeric_cols, self.target_col, self.class_vals)
         if self._dev_dataset is not None:
             self._dev_dataset.close()
-        self._dev_dataset = engine.DeviceDataset(self.encoded, self.device)
+            self._dev_dataset = None
+        self.encoded, self._dev_dataset = engine.encode_dataset_device(
+            self.dataset_numpy, feature_cols, numeric_cols, self.target_col, self.class_vals, self.device
+        )
 
     # ---------------------------------------------------------------------------------------------
     # host RNG draws, exactly the reference's (model.py:198-219)

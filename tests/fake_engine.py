@@ -96,12 +96,20 @@ class FakeForest:
         pass
 
 
+def fake_encode_dataset_device(dataset_numpy, feature_cols, numeric_cols, target_col, class_vals, device=0):
+    from oracle import encode_ref
+
+    enc = encode_ref.encode_dataset(dataset_numpy, feature_cols, numeric_cols, target_col, class_vals)
+    return enc, FakeDataset(enc, device)
+
+
 def install(monkeypatch):
     from random_forest_mc_b200 import engine
 
     monkeypatch.setattr(engine, "stream_create", lambda device=0: 0)
     monkeypatch.setattr(engine, "stream_destroy", lambda device, stream: None)
     monkeypatch.setattr(engine, "DeviceDataset", FakeDataset)
+    monkeypatch.setattr(engine, "encode_dataset_device", fake_encode_dataset_device)
     monkeypatch.setattr(engine, "GrowBatch", FakeBatch)
     monkeypatch.setattr(engine, "DeviceForest", FakeForest)
 
@@ -110,5 +118,6 @@ def install_plain():
     from random_forest_mc_b200 import engine
 
     engine.DeviceDataset, engine.GrowBatch, engine.DeviceForest = FakeDataset, FakeBatch, FakeForest
+    engine.encode_dataset_device = fake_encode_dataset_device
     engine.stream_create = lambda device=0: 0
     engine.stream_destroy = lambda device, stream: None

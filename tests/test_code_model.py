@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import code_model as cm
+from oracle import encode_ref as ref_enc
 from random_forest_mc_b200 import encode as enc_mod
 from random_forest_mc_b200.flat import TreeSoA, soa_to_dict
 from tests.helpers import golden_names, load_golden, tree_diff
@@ -15,7 +16,7 @@ def encode_golden(g):
     frame[tcol] = frame[tcol].astype(str)
     frame = frame.dropna()
     cols = {c: frame[c].to_numpy() for c in frame.columns}
-    return enc_mod.encode_dataset(cols, g["feature_cols"], g["numeric_cols"], tcol, g["class_vals"])
+    return ref_enc.encode_dataset(cols, g["feature_cols"], g["numeric_cols"], tcol, g["class_vals"])
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -64,6 +65,6 @@ def test_median_value_equals_numpy_quantile(dtype):
         want = float(np.quantile(v, 0.5))
         s = np.sort(v)
         k0 = (n - 1) // 2
-        cc, _ = enc_mod.encode_column("x", v, True)
+        cc, _ = ref_enc.encode_column("x", v, True)
         got = enc_mod.median_value(float(s[k0]), float(s[k0 + 1]), n % 2 == 1, cc.tag)
         assert got == want or (got != got and want != want), (v, got, want)

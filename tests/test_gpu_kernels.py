@@ -6,6 +6,7 @@ import pandas as pd
 import pytest
 
 from oracle import code_model as cm
+from oracle import encode_ref as ref_enc
 from random_forest_mc_b200 import encode as enc_mod
 from random_forest_mc_b200.flat import TreeSoA, encode_frame, forest_tables_from_dicts, soa_to_dict
 from tests.helpers import golden_names, load_golden, tree_diff
@@ -94,7 +95,7 @@ def test_grow_matches_code_model_on_synthetic(seed, n, n_train, n_val, high_card
     feats_all = [c for c in df.columns if c != "target"]
     numeric = df.select_dtypes([np.number]).columns.to_list()
     cols = {c: df[c].to_numpy() for c in df.columns}
-    enc = enc_mod.encode_dataset(cols, feats_all, numeric, "target", df["target"].unique().tolist())
+    enc = ref_enc.encode_dataset(cols, feats_all, numeric, "target", df["target"].unique().tolist())
     g = np.random.default_rng(seed + 1000)
     n_slots, per_slot = 3, 3
     idx_T = np.stack([g.choice(n, n_train, replace=False) for _ in range(n_slots)])

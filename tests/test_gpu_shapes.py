@@ -7,6 +7,7 @@ import pandas as pd
 import pytest
 
 from oracle import code_model as cm
+from oracle import encode_ref as ref_enc
 from random_forest_mc_b200 import encode as enc_mod
 
 pytestmark = pytest.mark.gpu
@@ -67,7 +68,7 @@ def test_dispatch_space_matches_code_model(seed, n, n_classes, kind, n_train, n_
     feats_all = [c for c in df.columns if c != "target"]
     numeric = df.select_dtypes([np.number]).columns.to_list()
     cols = {c: df[c].to_numpy() for c in df.columns}
-    enc = enc_mod.encode_dataset(cols, feats_all, numeric, "target", df["target"].unique().tolist())
+    enc = ref_enc.encode_dataset(cols, feats_all, numeric, "target", df["target"].unique().tolist())
     assert enc.width == {"u8": 1, "u16": 2, "u32": 4}[kind]
     g = np.random.default_rng(seed + 500)
     idx_T = np.stack([g.choice(n, n_train, replace=False) for _ in range(2)])
