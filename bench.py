@@ -440,6 +440,61 @@ def run_b200(args):
     frame_e2e = world * R * T / frame_s
     raw_bytes = int(sum(pframe[c].to_numpy().nbytes for c in pframe.columns if pframe[c].dtype != object))
 
+    # ---- optional: BASELINE config 5, one GPU's shard (12.5M of the 100M rows) x 4096 merged trees ----
+    c5 = None
+    if args.c5_rows > 0:
+        m5 = RandomForestMC(n_trees=256, target_col="target", max_discard_trees=args.max_discard_trees)  # C2a defaults
+        m5.device = local
+        m5.process_dataset(frame.copy())
+        for seed in range(16):  # 16 fits appended == 16 models merged with mergeForest(by="add") (model.py:369, forest.py:123)
+            np.random.seed(seed)
+            random.seed(seed)
+            m5.fit(disable_progress_bar=True)
+        m5.setSoftVoting(True)
+        m5.setWeightedTrees(True)
+        dev5 = m5._device_forest()
+        t5 = m5._forest_tables
+        R5 = args.c5_rows
+        top = torch.tensor([c.n_unique + 1 for c in m5.encoded.columns] + [1] * (t5.stride - len(m5.encoded.columns)), device="cuda", dtype=torch.int32)
+        assert int(top.max()) < 32768 and t5.width == 2
+        codes5 = torch.empty((R5, t5.stride), dtype=torch.int16, device="cuda")
+        g5 = torch.Generator(device="cuda")
+        g5.manual_seed(5 + rank)
+        for lo in range(0, R5, 1 << 20):  # rows drawn on the device, code 0 (missing) included
+            hi = min(R5, lo + (1 << 20))
+            codes5[lo:hi] = (torch.randint(0, 1 << 30, (hi - lo, t5.stride), device="cuda", dtype=torch.int32, generator=g5) % top).to(torch.int16)
+        probs5 = torch.empty((R5, C), dtype=torch.float64, device="cuda")
+
+        def pred5():
+            dev5.predict_device(codes5.data_ptr(), t5.width, R5, t5.stride, None, True, True, probs5.data_ptr(), 0, stream)
+
+        for _ in range(args.warmup):
+            pred5()
+        barrier()
+        ev5 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev5:
+            a.record(stream)
+            pred5()
+            b.record(stream)
+        barrier()
+        ms5 = [a.elapsed_time(b) for a, b in ev5]
+        s5 = max_over_ranks(sum(ms5) / 1e3)
+        algo5 = float(R5 * (args.features * t5.width + 8 * C) + len(t5.pnodes) * 16 + t5.probs.nbytes * 2)
+        sums = probs5[: 1 << 16].sum(dim=1)
+        assert bool(((sums - 1.0).abs() < 1e-12).all())
+        c5 = {
+            "workload": f"C5 shard: {R5} rows x {t5.n_trees} trees (16 fits x 256 slots at the default 10+10 rows per class, appended = mergeForest by add), weighted soft voting, float64 probabilities out",
+            "value": world * R5 * t5.n_trees * args.steps / s5,
+            "unit": "rows*trees/s",
+            "ms_per_step": float(np.mean(ms5)),
+            "forest_nodes": int(len(t5.pnodes)),
+            "data": "code rows drawn on the device (torch.randint per column, missing code included); inputs (1.65 GB) larger than L2",
+            "roofline": {"kernel": "rfmc::predict_kernel", "bound": "hbm", "achieved": algo5 / (np.mean(ms5) / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": algo5 / (np.mean(ms5) / 1e3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": algo5},
+        }
+        del codes5, probs5
+        dev5.close()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = args.ref_cores or os.cpu_count() or 1
@@ -563,6 +618,12 @@ def run_b200(args):
                 },
             },
             "process_dataset_s": t_process,
+            "process_dataset": {
+                "seconds": t_process,
+                "api": "RandomForestMC.process_dataset(DataFrame): pandas dropna/typing + strings ranked in Arrow on the host + raw numeric columns H2D + device rank coding (sort, distinct, rank, interleave)",
+                "h2d_bytes": int(sum(model.dataset_numpy[c].nbytes for c in model.numeric_cols) + 4 * enc.n_rows * (len(model.feature_cols) - len(model.numeric_cols)) + enc.n_rows),
+            },
+            **({"predict_c5": c5} if c5 is not None else {}),
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
@@ -589,6 +650,7 @@ def main():
     ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
     ap.add_argument("--host-streams", type=int, default=0, dest="host_streams", help="host RNG streams per rank for the e2e fit (0 = min(16, cores) / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-rows", type=int, default=0, dest="c5_rows", help="also vote this many device-generated rows through a 4096-tree merged forest (BASELINE config 5; 12500000 = one GPU's shard)")
     args = ap.parse_args()
     args.predict_rows = min(args.predict_rows, args.rows)
     # stdout carries exactly ONE JSON line: anything a library prints (NCCL's version banner ...)
