@@ -11,7 +11,9 @@ the product has no CPU fallback.
 Parity pin: the oracle is pinned against the *real* reference (imported from /root/reference in the
 build container) by ``tests/golden/make_golden.py`` -> ``tests/golden/*.pkl.gz`` and checked in
 ``tests/test_oracle_golden.py`` (tree dicts incl. value types and key order, kept/discarded sets,
-scores, labels and probabilities in all four voting modes, NaN cells, absent columns).
+scores, labels and probabilities in all four voting modes, NaN cells, absent columns); in the build
+container ``tests/test_oracle_live_reference.py`` also runs the real reference live on 30 randomized
+cases and requires equality, RNG end states included.
 
 Every function cites the reference lines it follows (paths relative to the reference repo root).
 It deliberately issues the same numpy calls per node as the reference (np.quantile, np.unique,
