@@ -646,7 +646,7 @@ def main():
     ap.add_argument("--n-trees", type=int, default=256, dest="n_trees")
     ap.add_argument("--max-discard-trees", type=int, default=4, dest="max_discard_trees")
     ap.add_argument("--predict-rows", type=int, default=1_000_000, dest="predict_rows")
-    ap.add_argument("--e2e-steps", type=int, default=2, dest="e2e_steps")
+    ap.add_argument("--e2e-steps", type=int, default=4, dest="e2e_steps")
     ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
     ap.add_argument("--host-streams", type=int, default=0, dest="host_streams", help="host RNG streams per rank for the e2e fit (0 = min(16, cores) / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
