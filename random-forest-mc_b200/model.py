@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import logging as log
 import os
+import sys
 import threading
 import random as _pyrandom
 from sys import getrecursionlimit
@@ -150,6 +151,7 @@ class RandomForestMC(BaseRandomForestMC):
         # the blocks are generated with AVX-512 the cache-to-cache hand-off costs more than it saves.
         self.rng_threads = max(0, min(2, (os.cpu_count() or 1) - 1))
         self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"
+        self.gil_switch_interval = float(os.environ.get("RFMC_GIL_SWITCH_INTERVAL", "1e-4"))  # seconds, host-stream fits only
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -483,11 +485,20 @@ class RandomForestMC(BaseRandomForestMC):
             finally:
                 engine.stream_release(self.device, stream)
 
-        threads = [threading.Thread(target=work, args=(r,)) for r in range(k)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        # Every C call of a worker (draws, launch, wait, fetch) releases the GIL and has to win it back
+        # on return; with CPython's default 5 ms switch interval a returning worker can wait that long
+        # behind another worker's numpy glue, several times per batch.  A short interval while the
+        # workers run turns those hand-offs into microseconds.
+        switch = sys.getswitchinterval()
+        sys.setswitchinterval(min(switch, self.gil_switch_interval))
+        try:
+            threads = [threading.Thread(target=work, args=(r,)) for r in range(k)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(switch)
         if errors:
             raise errors[0]
         total = {}
