@@ -410,10 +410,11 @@ __global__ void __launch_bounds__(PRED_THREADS) encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CodeT* tile = reinterpret_cast<CodeT*>(smem_raw);
     const int tid = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * PRED_THREADS;
-    const int rows = (int)((a.n_rows - row0) < PRED_THREADS ? (a.n_rows - row0) : PRED_THREADS);
-    const int words = (int)((size_t)PRED_THREADS * a.stride * sizeof(CodeT) / 4);
-    for (int i = tid; i < words; i += PRED_THREADS) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+    const int T = (int)blockDim.x;  // rows per tile: 128, or fewer when the rows are wide
+    const int64_t row0 = (int64_t)blockIdx.x * T;
+    const int rows = (int)((a.n_rows - row0) < T ? (a.n_rows - row0) : T);
+    const int words = (int)((size_t)T * a.stride * sizeof(CodeT) / 4);
+    for (int i = tid; i < words; i += T) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
     __syncthreads();
     if (tid < rows) {
         CodeT* myrow = tile + (size_t)tid * a.stride;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(PRED_THREADS) encode_kernel(EncodeArgs a) {
     __syncthreads();
     const int out_words = (int)((size_t)rows * a.stride * sizeof(CodeT) / 4);
     uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<CodeT*>(a.codes) + row0 * a.stride);
-    for (int i = tid; i < out_words; i += PRED_THREADS) dst[i] = reinterpret_cast<const uint32_t*>(tile)[i];
+    for (int i = tid; i < out_words; i += T) dst[i] = reinterpret_cast<const uint32_t*>(tile)[i];
 }
 
 int launch_encode(const void* d_raw, const int64_t* d_col_off, const int32_t* d_col_feat, const int32_t* d_col_dtype,
@@ -462,25 +463,27 @@ int launch_encode(const void* d_raw, const int64_t* d_col_off, const int32_t* d_
     a.thresholds = d_thresholds;
     a.thr_off = d_thr_off;
     a.codes = d_codes;
-    const unsigned blocks = (unsigned)((n_rows + PRED_THREADS - 1) / PRED_THREADS);
-    if (blocks == 0) return 0;
-    const size_t smem = (size_t)PRED_THREADS * row_stride * code_width;
+    if (n_rows == 0) return 0;
+    int T = PRED_THREADS;  // rows per tile; wide frames get smaller tiles so the tile still fits shared memory
+    while (T > 32 && (size_t)T * row_stride * code_width > 200 * 1024) T >>= 1;
+    const size_t smem = (size_t)T * row_stride * code_width;
     if (smem > 200 * 1024) {
         set_error("frame encode: too many feature columns for the shared-memory tile");
         return 1;
     }
+    const unsigned blocks = (unsigned)((n_rows + T - 1) / T);
     switch (code_width) {
         case 1:
             if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            encode_kernel<uint8_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            encode_kernel<uint8_t><<<blocks, T, smem, stream>>>(a);
             break;
         case 2:
             if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            encode_kernel<uint16_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            encode_kernel<uint16_t><<<blocks, T, smem, stream>>>(a);
             break;
         case 4:
             if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(encode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            encode_kernel<uint32_t><<<blocks, PRED_THREADS, smem, stream>>>(a);
+            encode_kernel<uint32_t><<<blocks, T, smem, stream>>>(a);
             break;
         default: set_error("unsupported code width"); return 1;
     }

@@ -173,3 +173,43 @@ def test_c5_merged_forest_row_sharded_predict():
         assert probs_equal(merged.predict_proba(rows.iloc[lo:hi]), whole[lo:hi])
     want = orc.forest_probs([t.data for t in merged.data], list(merged.survived_scores), merged.class_vals, rows.iloc[:24], soft=True, weighted=True)
     assert probs_equal(whole[:24], want)
+
+
+def test_wide_frame_1500_features_matches_oracle():
+    """Rows too wide for the 128-row shared-memory tiles (1500 features x 2-byte codes = 3 KB per row):
+    the frame encoder shrinks its tile, the vote kernel reads rows from global memory, the slot gather
+    and the grower take candidates of up to 1500 features.  Forest and votes == the oracle's."""
+    from oracle import rfmc_oracle as orc
+    from random_forest_mc_b200.model import RandomForestMC
+    from tests.helpers import tree_diff
+
+    logging.disable(logging.WARNING)
+    r = np.random.default_rng(11)
+    n, F = 3000, 1500
+    cols = {f"x_{j}": r.integers(-20, 20, size=n).astype(np.int8) for j in range(F - 3)}
+    cols["wide_0"] = np.round(r.normal(size=n), 3)            # > 255 distinct values -> uint16 codes for the whole matrix
+    cols["cat_0"] = r.choice(np.array(["a", "b", "c"], dtype=object), size=n)
+    cols["f32_0"] = np.round(r.normal(size=n), 1).astype(np.float32)
+    frame = pd.DataFrame(cols)
+    s = frame["x_0"] + frame["x_1"] + 10 * frame["wide_0"] + r.normal(size=n) * 5
+    frame["target"] = pd.qcut(s, 3, labels=["lo", "mid", "hi"]).astype(str)
+    kw = dict(n_trees=3, target_col="target", max_discard_trees=2, batch_train_pclass=40, batch_val_pclass=15)
+    ds = orc.ingest(frame.copy(), target_col="target", batch_train_pclass=40, batch_val_pclass=15, max_depth=None, min_samples_split=1)
+    np.random.seed(11)
+    random.seed(11)
+    want_trees, want_scores, _ = orc.fit(ds, 3, max_discard_trees=2)
+    m = RandomForestMC(**kw)
+    np.random.seed(11)
+    random.seed(11)
+    m.fit(frame.copy(), disable_progress_bar=True)
+    assert m.encoded.width == 2 and m.encoded.stride * 2 > 1600
+    assert [float(x) for x in m.survived_scores] == [float(x) for x in want_scores]
+    for a, b in zip(m.data, want_trees):
+        assert tree_diff(a.data, b) is None
+    pred = frame.drop(columns=["target"]).head(300).copy()
+    pred["wide_0"] = pred["wide_0"].where(r.random(300) > 0.2)
+    for fr in (pred, pred.drop(columns=["x_5", "cat_0"])):
+        for soft, weighted in ((False, False), (True, True)):
+            m.setSoftVoting(soft)
+            m.setWeightedTrees(weighted)
+            assert probs_equal(m.testForestProbs(fr), orc.forest_probs(want_trees, want_scores, ds.class_vals, fr, soft, weighted))
