@@ -1,8 +1,10 @@
 # Round-end capture at the DEFAULT bench configuration (so per-launch numbers match the bench line).
+# The launch list is filtered to the kernels of the fit / vote steps: process_dataset (outside the metric) alone
+# launches ~2,400 rank-coding kernels first -- their list is profiles/r1f_encode_launches.csv.
 set -x
 CMD="python bench.py --no-cpu-baseline --e2e-steps 1"
 $CMD > gpurun_out/plainF.json 2> gpurun_out/plainF.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launchesF.csv $CMD > gpurun_out/ncu_launchF.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"grow_kernel|slot_gather_kernel|predict_kernel|pack_kernel|encode_kernel|leaves_kernel|FillFunctor" -c 160 --csv --log-file gpurun_out/launchesF.csv $CMD > gpurun_out/ncu_launchF.log 2>&1
 echo rc_launch=$?
 ncu --set full --clock-control none --import-source on -k regex:grow_kernel -s 3 -c 1 -o gpurun_out/prof_growF $CMD > gpurun_out/ncu_growF.log 2>&1
 echo rc_grow=$?
