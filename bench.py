@@ -347,7 +347,7 @@ def run_b200(args):
     # also runs one independent stream per core.  `e2e_fit_serial` is fit(): ONE stream, every draw
     # in the serial reference's order (its floor is the host walk over that stream).
     cores = os.cpu_count() or 1
-    k_streams = max(1, min(args.host_streams or max(1, min(16, cores) // world), cores, args.n_trees))
+    k_streams = max(1, min(args.host_streams or max(1, min(16, cores // world)), cores, args.n_trees))
 
     def e2e_fit(k):
         model.data, model.survived_scores = [], []
@@ -648,7 +648,7 @@ def main():
     ap.add_argument("--predict-rows", type=int, default=1_000_000, dest="predict_rows")
     ap.add_argument("--e2e-steps", type=int, default=4, dest="e2e_steps")
     ap.add_argument("--ref-cores", type=int, default=0, dest="ref_cores")
-    ap.add_argument("--host-streams", type=int, default=0, dest="host_streams", help="host RNG streams per rank for the e2e fit (0 = min(16, cores) / ranks)")
+    ap.add_argument("--host-streams", type=int, default=0, dest="host_streams", help="host RNG streams per rank for the e2e fit (0 = min(16, cores / ranks))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5-rows", type=int, default=0, dest="c5_rows", help="also vote this many device-generated rows through a 4096-tree merged forest (BASELINE config 5; 12500000 = one GPU's shard)")
     args = ap.parse_args()
