@@ -292,7 +292,13 @@ def fit_sharded_local(model, n_local: int, host_streams: int = 1, seeds=None):
             return model._fit_slots_streams(n_local, list(seeds))
         return model._fit_slots(n_local)
     local, recorder = _fit_local(model, n_local, host_streams, seeds)
-    return _gather_forest(model, local, recorder)
+    from time import perf_counter
+
+    t0 = perf_counter()
+    forest = _gather_forest(model, local, recorder)
+    if isinstance(getattr(model, "fit_stats", None), dict):
+        model.fit_stats["t_gather"] = perf_counter() - t0
+    return forest
 
 
 def predict_sharded(model, frame, want_probs: bool):
