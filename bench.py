@@ -19,7 +19,6 @@ calls per node as the reference) on all host cores, one process per core, one sl
 """
 import argparse
 import json
-import math
 import os
 import random
 import subprocess

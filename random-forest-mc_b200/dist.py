@@ -15,7 +15,7 @@ Predict: rows are sharded contiguously over ranks, the forest is replicated, no 
 from __future__ import annotations
 
 import random as _pyrandom
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 

@@ -26,7 +26,7 @@ consecutive rows copied verbatim into shared memory is bank-conflict-free for th
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import pandas as pd

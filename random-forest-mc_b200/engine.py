@@ -257,6 +257,15 @@ class DeviceDataset:
         )
         self._h = h
 
+    @classmethod
+    def from_handle(cls, handle, device: int = 0) -> "DeviceDataset":
+        """Wrap a dataset the library built itself (rfmc_dataset_encode)."""
+        self = cls.__new__(cls)
+        self.enc = None
+        self.device = device
+        self._h = handle
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             load_library().rfmc_dataset_destroy(self._h)
@@ -326,9 +335,7 @@ def encode_dataset_device(dataset_numpy, feature_cols, numeric_cols, target_col,
             C.byref(h),
         )
     )
-    dev = DeviceDataset.__new__(DeviceDataset)
-    dev.device = device
-    dev._h = h
+    dev = DeviceDataset.from_handle(h, device)
     try:
         width, stride = C.c_int32(0), C.c_int64(0)
         nuniq = np.zeros(nfeat, dtype=np.int32)

@@ -13,7 +13,6 @@ The forest is flattened once per distinct tree list (``flat.forest_tables_*``), 
 from __future__ import annotations
 
 from collections import UserList
-from math import fsum
 from random import shuffle
 from typing import List, Optional
 

@@ -1,6 +1,5 @@
 """CPU: the C-ABI library builds, loads, and exports every symbol include/rfmc_b200.h declares
 (no compute call is made without a GPU); compute entry points refuse to run without a device."""
-import ctypes
 import os
 import re
 

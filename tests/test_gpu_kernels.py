@@ -7,7 +7,6 @@ import pytest
 
 from oracle import code_model as cm
 from oracle import encode_ref as ref_enc
-from random_forest_mc_b200 import encode as enc_mod
 from random_forest_mc_b200.flat import TreeSoA, encode_frame, forest_tables_from_dicts, soa_to_dict
 from tests.helpers import golden_names, load_golden, tree_diff
 from tests.test_code_model import encode_golden

@@ -8,7 +8,6 @@ import pytest
 
 from oracle import code_model as cm
 from oracle import encode_ref as ref_enc
-from random_forest_mc_b200 import encode as enc_mod
 
 pytestmark = pytest.mark.gpu
 

@@ -1,7 +1,6 @@
 """CPU: the drop-in API's host logic (speculative batching + RNG rewind, policy, flattening,
 persistence, merge) on an oracle-backed fake engine, against the reference's recorded vectors."""
 import numpy as np
-import pandas as pd
 import pytest
 
 from tests import fake_engine, model_checks
