@@ -387,6 +387,14 @@ class RandomForestMC(BaseRandomForestMC):
     def _fit_slots(self, n_slots: int, stream=None):
         """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's."""
         self._require_dataset()
+        if n_slots > 0 and int(self._N) <= int(self.batch_train_pclass):
+            # Empty hold-out set (a class smaller than batch_train_pclass, or batch_val_pclass == 0): the
+            # reference's split_train_val returns np.array([]) -- float64 -- for idx_val (model.py:199-210)
+            # and its first validationTree dies indexing with it (model.py:306), after the slot's row draw,
+            # one sampleFeats and one plantTree.  Same exception, same RNG streams consumed.
+            self.split_train_val()
+            self.sampleFeats(self.feature_cols[:])
+            raise IndexError("arrays used as indices must be of integer (or boolean) type")
         trees: List[DecisionTreeMC] = []
         stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0,
                      t_draw=0.0, t_launch=0.0, t_wait=0.0, t_fetch=0.0)

@@ -73,19 +73,24 @@ def run_case(seed):
                     batch_val_pclass=kw["batch_val_pclass"], max_depth=kw["max_depth"], min_samples_split=kw["min_samples_split"])
     np.random.seed(seed)
     random.seed(seed)
+    expect = AttributeError  # the reference raises it when every candidate of a slot scores 0.0 (model.py:345)
     try:
         want_trees, want_scores, _ = orc.fit(ds, kw["n_trees"], th_start=kw["th_start"], delta_th=kw["delta_th"],
                                              max_discard_trees=kw["max_discard_trees"], get_best_tree=kw["get_best_tree"])
         failed = any(t is None for t in want_trees)
-    except Exception:
-        failed = True
+    except Exception as e:  # e.g. IndexError for an empty hold-out set (model.py:210, 306): same type required below
+        failed, expect = True, type(e)
+    want_rng = (np.random.get_state()[1].copy(), int(np.random.get_state()[2]), random.getstate())
     m = RandomForestMC(**kw)
     m.max_candidates_per_launch = int(g.choice([2, 7, 4096]))
     np.random.seed(seed)
     random.seed(seed)
-    if failed:  # the reference raises when every candidate of a slot scores 0.0 (model.py:345)
-        with pytest.raises(AttributeError):
+    if failed:
+        with pytest.raises(expect):
             m.fit(frame.copy(), disable_progress_bar=True)
+        if expect is IndexError:  # fails before anything is speculated: both RNG streams end where the reference's do
+            assert np.array_equal(np.random.get_state()[1], want_rng[0]) and int(np.random.get_state()[2]) == want_rng[1]
+            assert random.getstate() == want_rng[2]
         return
     m.fit(frame.copy(), disable_progress_bar=True)
     assert [float(s) if s == s else "nan" for s in m.survived_scores] == [float(s) if s == s else "nan" for s in want_scores]

@@ -27,7 +27,7 @@ def _reference_class():
     return RandomForestMC
 
 
-@pytest.mark.parametrize("seed", range(200, 230))
+@pytest.mark.parametrize("seed", list(range(200, 230)) + [1001, 1130, 1189, 1304])
 def test_oracle_equals_live_reference(seed):
     logging.disable(logging.WARNING)
     Ref = _reference_class()
@@ -51,9 +51,9 @@ def test_oracle_equals_live_reference(seed):
     random.seed(seed)
     try:
         ref.fit(frame.copy(), disable_progress_bar=True)
-        ref_failed = False
-    except AttributeError:  # every candidate of a slot scored 0.0 (model.py:345)
-        ref_failed = True
+        ref_failed = None
+    except (AttributeError, IndexError) as e:  # every candidate of a slot scored 0.0 (model.py:345) / empty hold-out set (:306)
+        ref_failed = type(e)
     ref_state = (np.random.get_state()[1].copy(), np.random.get_state()[2], random.getstate())
 
     ds = orc.ingest(frame.copy(), target_col="target", batch_train_pclass=kw["batch_train_pclass"],
@@ -63,10 +63,13 @@ def test_oracle_equals_live_reference(seed):
     try:
         trees, scores, _ = orc.fit(ds, kw["n_trees"], th_start=kw["th_start"], delta_th=kw["delta_th"],
                                    max_discard_trees=kw["max_discard_trees"], get_best_tree=kw["get_best_tree"])
-        failed = any(t is None for t in trees)
-    except Exception:
-        failed = True
+        failed = AttributeError if any(t is None for t in trees) else None
+    except Exception as e:
+        failed = type(e)
     assert failed == ref_failed
+    if failed is IndexError:  # dies in the first validationTree: the streams stop at the same place
+        assert np.array_equal(np.random.get_state()[1], ref_state[0]) and np.random.get_state()[2] == ref_state[1]
+        assert random.getstate() == ref_state[2]
     if failed:
         return
     assert np.array_equal(np.random.get_state()[1], ref_state[0]) and np.random.get_state()[2] == ref_state[1]
