@@ -14,3 +14,8 @@ def _fake(monkeypatch):
 @pytest.mark.parametrize("seed", list(range(100, 112)) + [1001, 1304])  # the last two: empty hold-out set -> the reference's IndexError
 def test_random_config_matches_oracle_on_fake_engine(seed):
     run_case(seed)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_wide_random_config_matches_oracle_on_fake_engine(seed):
+    run_case(seed, wide=True)

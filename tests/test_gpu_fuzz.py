@@ -48,13 +48,89 @@ def random_frame(g, n):
     return df
 
 
-def run_case(seed):
-    import logging
+def random_frame_wide(g, n):
+    """A wider space than random_frame: every integer width incl. values whose difference wraps in numpy's
+    integer lerp, infinities, raw continuous floats (uint32 codes), 100+ level categoricals, up to 8 classes."""
+    cols = {}
+    n_cols = int(g.integers(2, 15))
+    for j in range(n_cols):
+        kind = g.choice(["f64", "f64raw", "f32", "f32raw", "inf", "i64", "i32wrap", "i16", "i8", "u8", "u16", "u32", "u64",
+                         "cat", "manycat", "bool", "const", "dup"])
+        name = f"c{j}_{j}"
+        if kind == "f64":
+            cols[name] = np.round(g.normal(size=n) * 10 ** int(g.integers(-2, 4)), int(g.integers(0, 4)))
+        elif kind == "f64raw":
+            cols[name] = g.normal(size=n) * 10.0 ** int(g.integers(-6, 7))
+        elif kind == "f32":
+            cols[name] = np.round(g.normal(size=n), int(g.integers(0, 3))).astype(np.float32)
+        elif kind == "f32raw":
+            cols[name] = (g.normal(size=n) * 10.0 ** int(g.integers(-3, 4))).astype(np.float32)
+        elif kind == "inf":
+            v = np.round(g.normal(size=n), 1)
+            v[g.random(n) < 0.05] = np.inf
+            v[g.random(n) < 0.05] = -np.inf
+            cols[name] = v
+        elif kind == "i64":
+            cols[name] = g.integers(-(10 ** int(g.integers(1, 12))), 10 ** int(g.integers(1, 12)), size=n)
+        elif kind == "i32wrap":
+            cols[name] = g.choice(np.array([-(2**31), -(2**31) + 1, -5, 0, 7, 2**31 - 2, 2**31 - 1], dtype=np.int32), size=n)
+        elif kind == "i16":
+            cols[name] = g.integers(-32768, 32768, size=n).astype(np.int16)
+        elif kind == "i8":
+            cols[name] = g.choice(np.array([-128, -100, -1, 0, 1, 100, 127], dtype=np.int8), size=n)
+        elif kind == "u8":
+            cols[name] = g.integers(0, 256, size=n).astype(np.uint8)
+        elif kind == "u16":
+            cols[name] = g.integers(0, 65536, size=n).astype(np.uint16)
+        elif kind == "u32":
+            cols[name] = g.choice(np.array([0, 1, 2**31, 2**32 - 2, 2**32 - 1], dtype=np.uint32), size=n)
+        elif kind == "u64":
+            cols[name] = g.integers(0, 2**40, size=n).astype(np.uint64)
+        elif kind == "cat":
+            cols[name] = g.choice(np.array(["a", "B", "10", "2", "zz", ""], dtype=object)[: int(g.integers(2, 7))], size=n)
+        elif kind == "manycat":
+            cols[name] = g.choice(np.array([f"L{k}" for k in range(int(g.integers(20, 200)))], dtype=object), size=n)
+        elif kind == "bool":
+            cols[name] = g.random(n) < 0.4
+        elif kind == "const":
+            cols[name] = np.full(n, 3.5)
+        else:
+            cols[name] = g.choice([-0.0, 0.0, 1.0, 1.0, 1.0, 2.5], size=n)
+    df = pd.DataFrame(cols)
+    n_classes = int(g.integers(2, 9))
+    labels = [str(x) for x in g.permutation(["10", "9", "b", "A", "c", "zz", "0", "Z"])[:n_classes]]
+    first = df.iloc[:, 0]
+    is_num = pd.api.types.is_numeric_dtype(first) and not pd.api.types.is_bool_dtype(first)
+    base = np.nan_to_num(first.to_numpy(dtype=float), posinf=0.0, neginf=0.0) if is_num else pd.factorize(first)[0]
+    s = np.asarray(base, dtype=float) + g.normal(size=n) * (np.std(base) + 1.0)
+    df["target"] = np.array(labels)[np.argsort(np.argsort(s)) * n_classes // n]
+    return df
 
-    from random_forest_mc_b200.model import RandomForestMC
 
-    logging.disable(logging.WARNING)
-    g = np.random.default_rng(1000 + seed)
+def case_config(seed, wide=False):
+    """(frame, constructor kwargs) of one randomized case; ``wide`` draws from the larger space."""
+    g = np.random.default_rng((5000 if wide else 1000) + seed)
+    if wide:
+        n = int(g.integers(200, 4000))
+        frame = random_frame_wide(g, n)
+        n_feat = frame.shape[1] - 1
+        lo = int(g.integers(1, n_feat + 1))
+        kw = dict(
+            n_trees=int(g.integers(1, 5)),
+            target_col="target",
+            max_discard_trees=int(g.integers(1, 5)),
+            batch_train_pclass=int(g.choice([1, 2, 3, 10, 40, 150])),
+            batch_val_pclass=int(g.choice([0, 1, 5, 20, 40], p=[0.05, 0.2, 0.25, 0.25, 0.25])),
+            min_samples_split=int(g.integers(1, 7)),
+            max_depth=None if g.random() < 0.6 else int(g.integers(1, 13)),
+            get_best_tree=bool(g.random() < 0.7),
+            th_start=float(g.choice([1.0, 0.8, 0.5, 0.2])),
+            delta_th=float(g.choice([0.1, 0.25, 0.05])),
+            min_feature=None if g.random() < 0.5 else lo,
+            max_feature=None if g.random() < 0.5 else int(g.integers(lo, n_feat + 1)),
+            temporal_features=bool(g.random() < 0.3),
+        )
+        return frame, kw
     n = int(g.integers(120, 900))
     frame = random_frame(g, n)
     kw = dict(
@@ -69,8 +145,25 @@ def run_case(seed):
         th_start=float(g.choice([1.0, 0.8, 0.5])),
         delta_th=float(g.choice([0.1, 0.25])),
     )
-    ds = orc.ingest(frame.copy(), target_col="target", batch_train_pclass=kw["batch_train_pclass"],
-                    batch_val_pclass=kw["batch_val_pclass"], max_depth=kw["max_depth"], min_samples_split=kw["min_samples_split"])
+    return frame, kw
+
+
+def oracle_ingest(frame, kw):
+    return orc.ingest(frame, target_col="target", batch_train_pclass=kw["batch_train_pclass"], batch_val_pclass=kw["batch_val_pclass"],
+                      min_feature=kw.get("min_feature"), max_feature=kw.get("max_feature"),
+                      temporal_features=kw.get("temporal_features", False), max_depth=kw["max_depth"],
+                      min_samples_split=kw["min_samples_split"])
+
+
+def run_case(seed, wide=False):
+    import logging
+
+    from random_forest_mc_b200.model import RandomForestMC
+
+    logging.disable(logging.WARNING)
+    frame, kw = case_config(seed, wide)
+    g = np.random.default_rng(77 + seed)
+    ds = oracle_ingest(frame.copy(), kw)
     np.random.seed(seed)
     random.seed(seed)
     expect = AttributeError  # the reference raises it when every candidate of a slot scores 0.0 (model.py:345)

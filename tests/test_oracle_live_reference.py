@@ -13,7 +13,7 @@ import pytest
 
 from oracle import rfmc_oracle as orc
 from tests.helpers import probs_equal, tree_diff
-from tests.test_gpu_fuzz import random_frame
+from tests.test_gpu_fuzz import case_config, oracle_ingest
 
 REF_SRC = "/root/reference/src"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference is only present in the build container")
@@ -27,37 +27,25 @@ def _reference_class():
     return RandomForestMC
 
 
-@pytest.mark.parametrize("seed", list(range(200, 230)) + [1001, 1130, 1189, 1304])
-def test_oracle_equals_live_reference(seed):
+CASES = [(s, False) for s in list(range(200, 230)) + [1001, 1130, 1189, 1304]] + [(s, True) for s in range(40)]
+
+
+@pytest.mark.parametrize("seed,wide", CASES)
+def test_oracle_equals_live_reference(seed, wide):
     logging.disable(logging.WARNING)
     Ref = _reference_class()
-    g = np.random.default_rng(1000 + seed)
-    n = int(g.integers(120, 900))
-    frame = random_frame(g, n)
-    kw = dict(
-        n_trees=int(g.integers(2, 6)),
-        target_col="target",
-        max_discard_trees=int(g.integers(1, 5)),
-        batch_train_pclass=int(g.integers(3, 40)),
-        batch_val_pclass=int(g.integers(1, 20)),
-        min_samples_split=int(g.integers(1, 4)),
-        max_depth=None if g.random() < 0.6 else int(g.integers(1, 8)),
-        get_best_tree=bool(g.random() < 0.7),
-        th_start=float(g.choice([1.0, 0.8, 0.5])),
-        delta_th=float(g.choice([0.1, 0.25])),
-    )
+    frame, kw = case_config(seed, wide)
     ref = Ref(**kw)
     np.random.seed(seed)
     random.seed(seed)
     try:
         ref.fit(frame.copy(), disable_progress_bar=True)
         ref_failed = None
-    except (AttributeError, IndexError) as e:  # every candidate of a slot scored 0.0 (model.py:345) / empty hold-out set (:306)
+    except Exception as e:  # every candidate of a slot scored 0.0 (model.py:345), empty hold-out set (:306), ...
         ref_failed = type(e)
     ref_state = (np.random.get_state()[1].copy(), np.random.get_state()[2], random.getstate())
 
-    ds = orc.ingest(frame.copy(), target_col="target", batch_train_pclass=kw["batch_train_pclass"],
-                    batch_val_pclass=kw["batch_val_pclass"], max_depth=kw["max_depth"], min_samples_split=kw["min_samples_split"])
+    ds = oracle_ingest(frame.copy(), kw)
     np.random.seed(seed)
     random.seed(seed)
     try:
