@@ -215,3 +215,9 @@ def run_case(seed, wide=False):
 @pytest.mark.parametrize("seed", range(24))
 def test_random_config_matches_oracle(seed):
     run_case(seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_wide_random_config_matches_oracle(seed):
+    run_case(seed, wide=True)
