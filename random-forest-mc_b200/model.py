@@ -717,7 +717,9 @@ class RandomForestMC(BaseRandomForestMC):
         return self.featScoreMean(self.sampleClass2trees(row=row, Class=Class))
 
     def sampleClassFeatPairImportance(self, row, Class):
-        return self.featPairImportance(Forest=self.sampleClass2trees(row=row, Class=Class))
+        # As in the reference (model.py:473-476) the tree list is passed POSITIONALLY, i.e. as
+        # `disable_progress_bar`: the result is the pair importance of the whole forest.
+        return self.featPairImportance(self.sampleClass2trees(row=row, Class=Class))
 
     def sampleClassFeatCorrDataFrame(self, row, Class):
         return self.featCorrDataFrame(self.sampleClass2trees(row=row, Class=Class))

@@ -1,0 +1,116 @@
+"""CPU, build container only (skipped where /root/reference is absent): persistence, merge, de-duplication and the
+explainability helpers of the drop-in API against the REAL reference run live under the same seeds (oracle-backed fake
+engine under the host logic).  `used_features` is a hash-ordered list in the reference (model.py:413-417), so lists of
+features are compared as sets and dicts without regard to key order."""
+import json
+import logging
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+from tests import fake_engine
+from tests.helpers import load_golden, probs_equal
+
+REF_SRC = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference is only present in the build container")
+
+
+@pytest.fixture(scope="module", params=["mixed_default", "titanic_c1", "ties_default"])
+def ctx(request):
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    from random_forest_mc.model import RandomForestMC as Ref
+    from random_forest_mc.utils import json_encoder
+
+    from random_forest_mc_b200.model import RandomForestMC as Mine
+
+    mp = pytest.MonkeyPatch()
+    fake_engine.install(mp)
+    logging.disable(logging.WARNING)
+    g = load_golden(request.param)
+    kw = dict(g["kwargs"])
+    kw["n_trees"] = 6
+
+    def fit(cls, seed=5):
+        m = cls(**kw)
+        np.random.seed(seed)
+        random.seed(seed)
+        m.fit(g["frame"].copy(), disable_progress_bar=True)
+        return m
+
+    yield dict(fit=fit, Mine=Mine, Ref=Ref, kw=kw, enc=json_encoder, frame=g["frame"].drop(columns=[kw["target_col"]]))
+    mp.undo()
+
+
+def _normalised(d):
+    for t in d["Forest"]:
+        t["used_features"] = sorted(t["used_features"])
+    return d
+
+
+def test_model2dict_json_md5_and_cross_loading(ctx):
+    a, b = ctx["fit"](ctx["Mine"]), ctx["fit"](ctx["Ref"])
+    ja = json.dumps(_normalised(a.model2dict()), default=ctx["enc"])
+    jb = json.dumps(_normalised(b.model2dict()), default=ctx["enc"])
+    assert ja == jb  # same wire format, byte for byte
+    assert [t.md5hexdigest for t in a.data] == [t.md5hexdigest for t in b.data]
+    assert repr(a) == repr(b) and a.Forest_size == b.Forest_size and a.trees2depths == b.trees2depths
+    mine_from_ref, ref_from_mine = ctx["Mine"](**ctx["kw"]), ctx["Ref"](**ctx["kw"])
+    mine_from_ref.dict2model(json.loads(jb))
+    ref_from_mine.dict2model(json.loads(ja))
+    fr = ctx["frame"].head(60)
+    for soft in (False, True):
+        for weighted in (False, True):
+            for m in (mine_from_ref, ref_from_mine):
+                m.setSoftVoting(soft)
+                m.setWeightedTrees(weighted)
+            assert probs_equal(mine_from_ref.testForestProbs(fr), ref_from_mine.testForestProbs(fr))
+            assert mine_from_ref.testForest(fr) == ref_from_mine.testForest(fr)
+    assert (a == mine_from_ref) == (b == ref_from_mine)
+
+
+def test_merge_and_drop_duplicates(ctx):
+    fit, Mine, Ref = ctx["fit"], ctx["Mine"], ctx["Ref"]
+    for by, n in (("add", -1), ("score", 4), ("random", 5)):
+        a, b = fit(Mine, 7), fit(Ref, 7)
+        random.seed(99)
+        a.mergeForest(fit(Mine, 8), n, by)
+        random.seed(99)
+        b.mergeForest(fit(Ref, 8), n, by)
+        assert [t.md5hexdigest for t in a.data] == [t.md5hexdigest for t in b.data], by
+        assert [float(s) for s in a.survived_scores] == [float(s) for s in b.survived_scores], by
+    a, b = fit(Mine, 7), fit(Ref, 7)
+    a.mergeForest(fit(Mine, 7))
+    b.mergeForest(fit(Ref, 7))
+    assert a.drop_duplicated_trees() == b.drop_duplicated_trees() and len(a.data) == len(b.data)
+
+
+def _call(fn, *args, **kw):
+    try:
+        return fn(*args, **kw)
+    except Exception as e:
+        return ("raised", type(e).__name__)
+
+
+def _equal(x, y):
+    if hasattr(x, "equals"):
+        return x.equals(y)
+    if isinstance(x, tuple) and isinstance(y, tuple) and len(x) == 2 and isinstance(x[1], list):
+        return x[0] == y[0] and x[1] == y[1]
+    return x == y  # dicts: equal whatever the key order
+
+
+def test_explainability_helpers(ctx):
+    a, b = ctx["fit"](ctx["Mine"]), ctx["fit"](ctx["Ref"])
+    for name in ("featCount", "featImportance", "featScoreMean", "featCorrDataFrame"):
+        assert _equal(_call(getattr(a, name)), _call(getattr(b, name))), name
+    assert a.featPairImportance(disable_progress_bar=True) == b.featPairImportance(disable_progress_bar=True)
+    row = ctx["frame"].iloc[2]
+    for Class in a.class_vals:
+        assert [t.md5hexdigest for t in a.sampleClass2trees(row, Class)] == [t.md5hexdigest for t in b.sampleClass2trees(row, Class)]
+        for name in ("sampleClassFeatCount", "sampleClassFeatImportance", "sampleClassFeatScoreMean",
+                     "sampleClassFeatPairImportance", "sampleClassFeatCorrDataFrame"):
+            assert _equal(_call(getattr(a, name), row, Class), _call(getattr(b, name), row, Class)), (name, Class)
