@@ -435,6 +435,11 @@ class RandomForestMC(BaseRandomForestMC):
                         # off-stream; continue the slot from the state right after its last draw
                         resume, extend = (p, spec), (p, judge)
                         break
+                    if judge.choice is None:
+                        # every candidate of the slot scored 0.0: the reference dies on Tree.survived_score
+                        # (model.py:345) with both streams where this slot left them
+                        self._rewind_into_slot(p, judge.used)
+                        raise AttributeError("'NoneType' object has no attribute 'survived_score'")
                     chosen.append((judge.choice, judge.best_score))
                     stats["candidates_used"] += judge.used
                     recent_used.append(judge.used)
@@ -559,6 +564,7 @@ class RandomForestMC(BaseRandomForestMC):
                     continue
                 choice = judge.choice
                 if choice is None:
+                    self._rewind_into_slot(ext, stop + 1, fresh_rows=False)
                     raise AttributeError("'NoneType' object has no attribute 'survived_score'")  # model.py:345
                 soa = kept.get(choice)
                 if soa is None:
