@@ -186,6 +186,11 @@ class RandomForestMC(BaseRandomForestMC):
         if self._dev_dataset is not None:
             self._dev_dataset.close()
             self._dev_dataset = None
+        self.encoded = None
+        if len(dataset) == 0 or len(feature_cols) == 0:
+            # Nothing to encode.  The reference accepts such a frame here and only trips inside its first
+            # tree slot; _reference_preflight reproduces where and how.
+            return
         self.encoded, self._dev_dataset = engine.encode_dataset_device(
             self.dataset_numpy, feature_cols, numeric_cols, self.target_col, self.class_vals, self.device
         )
@@ -227,6 +232,34 @@ class RandomForestMC(BaseRandomForestMC):
     # ---------------------------------------------------------------------------------------------
     # single-candidate API (model.py:264-314), one launch each
     # ---------------------------------------------------------------------------------------------
+    def _reference_preflight(self):
+        """Configurations the reference only trips over inside its first tree slot (model.py:318-326:
+        split_train_val -> sampleFeats -> plantTree -> validationTree).  Same exception, raised after
+        the same draws, so both RNG streams end where the reference leaves them:
+          * min_feature > max_feature (e.g. a frame with a single feature column and the default
+            min_feature = 2): np.random.randint raises ValueError inside sampleFeats, after the row draw;
+          * no training rows (batch_train_pclass <= 0, or a frame with no rows left after dropna) or no
+            hold-out rows (batch_val_pclass == 0, or a class smaller than batch_train_pclass):
+            split_train_val returns np.array([]) -- float64 -- and plantTree / validationTree die
+            indexing with it (model.py:210, 267, 306): IndexError."""
+        if self.dataset_numpy is None:
+            return
+        no_rows = self.encoded is None and self.n_samples == 0
+        lo, hi = int(self.min_feature), int(self.max_feature) + 1
+        no_train = no_rows or int(self.batch_train_pclass) <= 0
+        no_val = not no_rows and int(self._N) <= int(self.batch_train_pclass)
+        if not (lo >= hi or no_train or no_val or self.encoded is None):
+            return
+        if self.encoded is not None:
+            self.split_train_val()
+        elif not no_rows:  # rows but no feature columns: the row draw still happens (on the label column only)
+            st = self._np_rng()
+            target = self.dataset_numpy[self.target_col]
+            for val in self.class_vals:
+                st.choice(np.flatnonzero(target == val), int(self._N), replace=False)
+        self.sampleFeats(self.feature_cols[:])  # numpy's own ValueError when min_feature > max_feature
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
+
     def _require_dataset(self):
         if self.dataset_numpy is None or self._dev_dataset is None:
             raise DatasetNotFound
@@ -386,15 +419,9 @@ class RandomForestMC(BaseRandomForestMC):
 
     def _fit_slots(self, n_slots: int, stream=None):
         """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's."""
+        if n_slots > 0:
+            self._reference_preflight()
         self._require_dataset()
-        if n_slots > 0 and int(self._N) <= int(self.batch_train_pclass):
-            # Empty hold-out set (a class smaller than batch_train_pclass, or batch_val_pclass == 0): the
-            # reference's split_train_val returns np.array([]) -- float64 -- for idx_val (model.py:199-210)
-            # and its first validationTree dies indexing with it (model.py:306), after the slot's row draw,
-            # one sampleFeats and one plantTree.  Same exception, same RNG streams consumed.
-            self.split_train_val()
-            self.sampleFeats(self.feature_cols[:])
-            raise IndexError("arrays used as indices must be of integer (or boolean) type")
         trees: List[DecisionTreeMC] = []
         stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0,
                      t_draw=0.0, t_launch=0.0, t_wait=0.0, t_fetch=0.0)
