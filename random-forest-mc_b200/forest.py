@@ -25,6 +25,29 @@ from .flat import ForestTables, encode_frame, forest_tables_from_dicts
 from .tree import DecisionTreeMC
 
 
+def _reaches_marked(t: ForestTables, row_codes, absent, marked) -> bool:
+    """Does any tree's evaluation of this row touch a node that tests one of the ``marked`` features,
+    given that nodes testing an absent column are evaluated on both sides (tree.py:166-175)?"""
+    ff, thr, child = t.pnodes["feat_flags"], t.pnodes["thr"], t.pnodes["child"]
+    marked = set(int(j) for j in marked)
+    for root in t.roots:
+        todo = [int(root)]
+        while todo:
+            i = todo.pop()
+            if ff[i] & engine.PNODE_LEAF:
+                continue
+            f = int(ff[i] & 0xFFFF)
+            if absent[f]:
+                todo += [int(child[i]), int(child[i]) + 1]
+                continue
+            if f in marked:
+                return True
+            c = int(row_codes[f])
+            go = (c == thr[i]) if (ff[i] & engine.PNODE_CATEGORICAL) else (c >= thr[i])
+            todo.append(int(child[i]) + (0 if go else 1))
+    return False
+
+
 class BaseRandomForestMC(UserList):
     typer_error_msg = "Both objects must be instances of 'RandomForestMC' class."
 
@@ -189,7 +212,51 @@ class BaseRandomForestMC(UserList):
 
     def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool):
         dev = self._device_forest()
+        self._raise_for_unorderable_cells(dev, frame)
         return dev.predict_frame(frame, self.soft_voting, self.weighted_tree, want_probs, want_labels)
+
+    def _raise_for_unorderable_cells(self, dev, frame: pd.DataFrame) -> None:
+        """tree.py:177-180 tests ``val == split_val or (numeric and val > split_val)``: a cell of a numeric
+        feature that is neither a number nor NaN (None, pd.NA, a string) makes ``>`` raise TypeError -- but
+        only when some tree's walk reaches a node that tests it.  Such cells can only live in object /
+        string / nullable columns; the rows that hold one are walked once more through the leaf-export
+        kernel with those features marked: a walk that crosses a marked feature is a walk the reference
+        would have died on (up to its first marked node the walk is the true one)."""
+        t = self._forest_tables
+        marks = {}
+        for j, name in enumerate(t.feature_cols):
+            if t.thresholds[j] is None or name not in frame.columns:
+                continue
+            col = frame[name]
+            if isinstance(col.dtype, np.dtype) and col.dtype != object:
+                continue  # plain numeric / bool columns hold numbers only
+            cells = col.astype(object).to_numpy()  # what ds.iterrows() hands to the comparison, cell by cell
+            bad = np.fromiter((not isinstance(v, (int, float, np.number, np.bool_)) for v in cells), dtype=bool, count=len(cells))
+            if bad.any():
+                marks[j] = bad
+        if not marks:
+            return
+        feats = sorted(marks)
+        pattern = np.stack([marks[j] for j in feats], axis=1)  # [rows, marked features]
+        rows = np.flatnonzero(pattern.any(axis=1))
+        codes, absent = encode_frame(t, frame.iloc[rows])
+        groups = {}
+        for k, r in enumerate(rows):
+            groups.setdefault(pattern[r].tobytes(), []).append(k)
+        message = "'>' not supported between a non-numeric cell and a numeric split value (tree.py:177-180)"
+        for key, members in groups.items():
+            marked = [j for j, hit in zip(feats, np.frombuffer(key, dtype=bool)) if hit]
+            if absent.any():
+                # a column missing from the frame makes the reference evaluate BOTH subtrees (tree.py:166-175),
+                # so a marked node anywhere below counts; rare enough to walk on the host, row by row
+                if any(_reaches_marked(t, codes[k], absent, marked) for k in members):
+                    raise TypeError(message)
+                continue
+            ab = absent.copy()
+            ab[marked] = 1
+            _, crossed = dev.leaves(codes[members], ab)
+            if np.any(crossed):
+                raise TypeError(message)
 
     # -- inference API (forest.py:100-112, 204-274) ----------------------------------------------
     def useForest(self, row) -> dict:
