@@ -66,3 +66,35 @@ def test_fit_parallel_host_streams_contract():
     from tests.test_host_model import test_fit_parallel_host_streams_contract as check
 
     check()
+
+
+def test_non_numeric_cells_raise_only_when_reached():
+    """A None / string cell in a numeric column makes the reference's `val > split_val` raise TypeError, but only for
+    rows whose walk reaches a node testing it (tree.py:177-180); the engine finds those walks with the leaf-export
+    kernel.  Checked row by row against the oracle, which raises from the same Python comparison."""
+    from oracle import rfmc_oracle as orc
+
+    g, m = model_checks.fitted_model("mixed_default")
+    fr = g["frame"].drop(columns=["target"]).head(60)
+    numeric = [c for c in fr.columns if fr[c].dtype.kind in "fiu"]
+    trees, scores = [t.data for t in m.data], list(m.survived_scores)
+    raised = voted = 0
+    for k, c in enumerate(numeric * 6):
+        r = (7 * k) % len(fr)
+        one = fr.iloc[[r]].astype({c: object})
+        one.iloc[0, one.columns.get_loc(c)] = None if k % 2 else "oops"
+        if k % 5 == 0:
+            one = one.drop(columns=[numeric[(k + 1) % len(numeric)]]) if numeric[(k + 1) % len(numeric)] != c else one
+        try:
+            want = orc.forest_probs(trees, scores, g["class_vals"], one, False, False)
+        except TypeError:
+            want = None
+        if want is None:
+            with pytest.raises(TypeError):
+                m.testForestProbs(one)
+            raised += 1
+        else:
+            got = m.testForestProbs(one)
+            assert [float(got[0][c]) for c in g["class_vals"]] == [float(want[0][c]) for c in g["class_vals"]]
+            voted += 1
+    assert raised > 0 and voted > 0
