@@ -153,9 +153,20 @@ def leaf_payload(leaf: dict, class_vals, cidx):
     return best, besta, tuple(probs), tuple(pa)
 
 
-def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestTables:
-    """Flatten nested tree dicts (fitted here, merged, or loaded through dict2model)."""
+def weak_float32(v) -> float:
+    """A Python-number split value as a float32 cell sees it: numpy compares a np.float32 with a Python
+    scalar in float32 (NEP 50), i.e. against the split value rounded to float32."""
+    with np.errstate(over="ignore"):
+        return float(np.float32(v))
+
+
+def forest_tables_from_dicts(trees, scores, class_vals, feature_cols, f32_feats=frozenset()) -> ForestTables:
+    """Flatten nested tree dicts (fitted here, merged, or loaded through dict2model).  ``f32_feats``:
+    features whose cells the frame hands over as np.float32 scalars (see forest._float32_features)."""
     from math import fsum
+
+    def eff(v, j):
+        return weak_float32(v) if (j in f32_feats and type(v) in (float, int)) else float(v)
 
     from .encode import odd_word_stride
 
@@ -180,7 +191,7 @@ def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestT
                 if s["split_val"] not in cat_vals[j]:
                     cat_vals[j][s["split_val"]] = len(cat_vals[j]) + 1
             else:
-                num_vals[j].add(float(s["split_val"]))
+                num_vals[j].add(eff(s["split_val"], j))
             todo.append(s[">="])
             todo.append(s["<"])
     thresholds, categories = [], []
@@ -223,7 +234,7 @@ def forest_tables_from_dicts(trees, scores, class_vals, feature_cols) -> ForestT
                 thr[at] = cat_vals[j][s["split_val"]]
             else:
                 feat_flags[at] = j
-                sv = float(s["split_val"])
+                sv = eff(s["split_val"], j)
                 # a NaN split value matches nothing: an unreachable code sends every row to '<'
                 thr[at] = int(np.searchsorted(thresholds[j], sv, "left")) + 1 if sv == sv else 0xFFFFFFFF
             c = len(feat_flags)
@@ -293,7 +304,7 @@ def encode_frame(tables: ForestTables, frame):
     return codes, absent
 
 
-def forest_tables_from_soa(trees, scores, enc: EncodedDataset, class_vals, feature_cols) -> ForestTables:
+def forest_tables_from_soa(trees, scores, enc: EncodedDataset, class_vals, feature_cols, f32_feats=frozenset()) -> ForestTables:
     """Same tables as ``forest_tables_from_dicts`` but straight from the grower's SoA output,
     vectorised over all nodes of all trees (no nested dict is ever materialised)."""
     from math import fsum
@@ -330,7 +341,11 @@ def forest_tables_from_soa(trees, scores, enc: EncodedDataset, class_vals, featu
             categories[j] = {col.uniq[int(c) - 1]: k + 1 for k, c in enumerate(present)}
             top = max(top, len(present))
         else:
-            vals = np.where(two_row[m], col.table[np.clip(thr_ds[m] - 1, 0, len(col.table) - 1)], nodes["sval"][m])
+            sval = nodes["sval"][m]
+            if j in f32_feats:  # Python-float split values (model.py:237) as a np.float32 cell sees them
+                with np.errstate(over="ignore"):
+                    sval = sval.astype(np.float32).astype(np.float64)
+            vals = np.where(two_row[m], col.table[np.clip(thr_ds[m] - 1, 0, len(col.table) - 1)], sval)
             ok = vals == vals
             t = np.unique(vals[ok])
             code = np.full(len(vals), 0xFFFFFFFF, dtype=np.int64)

@@ -93,6 +93,7 @@ class BaseRandomForestMC(UserList):
         self._forest_key = None
         self._forest_dev: Optional[engine.DeviceForest] = None
         self._forest_tables: Optional[ForestTables] = None
+        self._forest_f32 = None  # ((forest key, float32 features), DeviceForest, ForestTables): see _device_forest
 
     def __repr__(self) -> str:
         return "{}(len(Forest)={},n_trees={},model_version={},module_version={})".format(
@@ -185,10 +186,22 @@ class BaseRandomForestMC(UserList):
         return sum(keep)
 
     # -- the GPU forest ------------------------------------------------------------------------------
-    def _device_forest(self) -> engine.DeviceForest:
+    def _device_forest(self, f32_feats=frozenset()) -> engine.DeviceForest:
+        """The forest resident on the device.  ``f32_feats`` (normally empty) selects the variant whose
+        Python-float split values of those features are rounded to float32, for frames that hand over
+        np.float32 cells (``_float32_features``); it is flattened on first use and cached beside the
+        default one."""
         if len(self.data) == 0:
             raise ZeroDivisionError("the forest is empty")
         key = (tuple(id(t) for t in self.data), tuple(float(s) for s in self.survived_scores), tuple(self.class_vals))
+        if f32_feats:
+            hit = self._forest_f32
+            if hit is None or hit[0] != (key, f32_feats):
+                if hit is not None:
+                    hit[1].close()
+                tables = self._flatten(f32_feats)
+                hit = self._forest_f32 = ((key, f32_feats), engine.DeviceForest(tables, self.device), tables)
+            return hit[1]
         if key != self._forest_key or self._forest_dev is None:
             if self._forest_dev is not None:
                 self._forest_dev.close()
@@ -198,7 +211,7 @@ class BaseRandomForestMC(UserList):
             self._forest_key = key
         return self._forest_dev
 
-    def _flatten(self) -> ForestTables:
+    def _flatten(self, f32_feats=frozenset()) -> ForestTables:
         from .flat import forest_tables_from_soa
 
         scores = list(self.survived_scores)
@@ -207,11 +220,25 @@ class BaseRandomForestMC(UserList):
         if all(getattr(t, "soa", None) is not None and t._data is None for t in self.data):
             enc = self.data[0]._enc
             if all(t._enc is enc for t in self.data):
-                return forest_tables_from_soa([t.soa for t in self.data], scores, enc, self.class_vals, self.feature_cols)
-        return forest_tables_from_dicts([t.data for t in self.data], scores, self.class_vals, self.feature_cols)
+                return forest_tables_from_soa([t.soa for t in self.data], scores, enc, self.class_vals, self.feature_cols, f32_feats)
+        return forest_tables_from_dicts([t.data for t in self.data], scores, self.class_vals, self.feature_cols, f32_feats)
 
-    def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool):
-        dev = self._device_forest()
+    def _float32_features(self, frame: pd.DataFrame, cells=None) -> frozenset:
+        """Features whose cells reach the comparison of tree.py:177-180 as np.float32 scalars.  The
+        reference walks ``ds.iterrows()``: a frame whose columns are all plain numbers with a float32
+        common dtype yields float32 rows (mixed frames yield object rows of Python numbers, wider frames
+        float64 rows).  A np.float32 cell meets a Python-float split value in float32 (NEP 50).
+        ``cells``: the row itself when a single Series / dict row is voted (its cells keep their types)."""
+        if cells is not None:
+            return frozenset(j for j, name in enumerate(self.feature_cols) if type(cells.get(name)) is np.float32)
+        kinds = [getattr(dt, "kind", "O") for dt in frame.dtypes]
+        if len(kinds) == 0 or any(k not in "fiu" for k in kinds) or np.result_type(*frame.dtypes) != np.float32:
+            return frozenset()
+        return frozenset(j for j, name in enumerate(self.feature_cols) if name in frame.columns)
+
+    def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool, cells=None):
+        f32 = self._float32_features(frame, cells)
+        dev = self._device_forest(f32)
         self._raise_for_unorderable_cells(dev, frame)
         return dev.predict_frame(frame, self.soft_voting, self.weighted_tree, want_probs, want_labels)
 
@@ -222,7 +249,7 @@ class BaseRandomForestMC(UserList):
         string / nullable columns; the rows that hold one are walked once more through the leaf-export
         kernel with those features marked: a walk that crosses a marked feature is a walk the reference
         would have died on (up to its first marked node the walk is the true one)."""
-        t = self._forest_tables
+        t = dev.tables
         marks = {}
         for j, name in enumerate(t.feature_cols):
             if t.thresholds[j] is None or name not in frame.columns:
@@ -263,7 +290,8 @@ class BaseRandomForestMC(UserList):
         if isinstance(row, dict):
             row = pd.Series(row)
         frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
-        probs, _ = self._vote_frame(frame, True, False)
+        cells = row if row.dtype == object else ({k: row.dtype.type() for k in row.index} if row.dtype == np.float32 else {})
+        probs, _ = self._vote_frame(frame, True, False, cells=cells)
         return {c: float(p) for c, p in zip(self.class_vals, probs[0])}
 
     def testForest(self, ds: pd.DataFrame) -> list:
@@ -311,11 +339,22 @@ def _single_tree_output(tree: DecisionTreeMC, row) -> dict:
     feats = tree.features
     if feats is None:
         feats = sorted(_features_of(tree.data))
-    tables = forest_tables_from_dicts([tree.data], [1.0], tree.class_vals, feats)
+    # cells that arrive as np.float32 meet Python-float split values in float32 (see _float32_features)
+    if row.dtype == np.float32:
+        f32 = frozenset(j for j, name in enumerate(feats) if name in row.index)
+    elif row.dtype == object:
+        f32 = frozenset(j for j, name in enumerate(feats) if name in row.index and type(row[name]) is np.float32)
+    else:
+        f32 = frozenset()
+    tables = forest_tables_from_dicts([tree.data], [1.0], tree.class_vals, feats, f32)
+    frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
+    codes, absent = encode_frame(tables, frame)
+    marked = [j for j, name in enumerate(feats) if tables.thresholds[j] is not None and name in row.index
+              and not isinstance(row[name], (int, float, np.number, np.bool_))]
+    if marked and _reaches_marked(tables, codes[0], absent, marked):
+        raise TypeError("'>' not supported between a non-numeric cell and a numeric split value (tree.py:177-180)")
     dev = engine.DeviceForest(tables)
     try:
-        frame = pd.DataFrame([row.to_numpy(dtype=object)], columns=list(row.index))
-        codes, absent = encode_frame(tables, frame)
         payload, seen = dev.leaves(codes, absent)
     finally:
         dev.close()

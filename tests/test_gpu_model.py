@@ -98,3 +98,41 @@ def test_non_numeric_cells_raise_only_when_reached():
             assert [float(got[0][c]) for c in g["class_vals"]] == [float(want[0][c]) for c in g["class_vals"]]
             voted += 1
     assert raised > 0 and voted > 0
+
+
+def test_float32_frames_on_a_float64_trained_forest_match_the_oracle():
+    """np.float32 cells meet Python-float split values in float32 (NEP 50): the engine flattens a float32 variant of
+    the forest for frames that hand over float32 rows.  The oracle walks real pandas rows with numpy comparisons, so
+    it follows the same promotion rules as the reference (pinned live in tests/test_predict_cells_live_reference.py)."""
+    import logging
+    import random
+
+    import pandas as pd
+
+    from oracle import rfmc_oracle as orc
+    from random_forest_mc_b200.model import RandomForestMC
+    from tests.helpers import probs_equal
+
+    logging.disable(logging.WARNING)
+    g = np.random.default_rng(0)
+    n = 300
+    frame = pd.DataFrame({"a_1": g.normal(size=n).round(2), "b_2": g.normal(size=n).round(1), "c_3": g.normal(size=n).round(3),
+                          "d_4": g.integers(-300, 300, size=n).astype(np.int16)})
+    frame["target"] = np.where(frame.a_1 + frame.b_2 + g.normal(size=n) * 0.3 > 0, "p", "q")
+    m = RandomForestMC(n_trees=6, target_col="target", max_discard_trees=3, batch_train_pclass=40, batch_val_pclass=20)
+    np.random.seed(1)
+    random.seed(1)
+    m.fit(frame.copy(), disable_progress_bar=True)
+    trees, scores = [t.data for t in m.data], list(m.survived_scores)
+    X = frame.drop(columns=["target"])
+    f32 = X.astype({"a_1": "float32", "b_2": "float32", "c_3": "float32"})  # float32 + int16 -> float32 rows
+    for soft in (False, True):
+        m.setSoftVoting(soft)
+        m.setWeightedTrees(soft)
+        for f in (f32, X.astype("float32"), X):
+            assert probs_equal(m.testForestProbs(f), orc.forest_probs(trees, scores, m.class_vals, f, soft, soft))
+        row = f32.iloc[3]
+        assert m.useForest(row) == orc.forest_row(trees, scores, m.class_vals, row, soft, soft)
+    m.setSoftVoting(False)
+    m.setWeightedTrees(False)
+    assert m.testForestProbs(f32) != m.testForestProbs(f32.astype("float64"))  # not vacuous
