@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .flat import NODE_DTYPE, TreeSoA
+from .flat import NODE_DTYPE, TreeSoA, reference_used_features
 
 
 def _td():
@@ -228,7 +228,10 @@ def _gather_forest(model, local, recorder=None):
     for soa, score, mask in gathered:
         t = model._wrap(soa, score)
         t.features = model.feature_cols
-        t.used_features = [model.feature_cols[j] for j in np.flatnonzero(mask)]
+        # model.py:413-417 semantics (flat.reference_used_features); every class of the balanced bootstrap
+        # ends up in some leaf, so the leaf labels of a fitted tree are the class labels
+        split_names = [model.feature_cols[j] for j in np.flatnonzero(mask)]
+        t.used_features = reference_used_features(model.feature_cols, split_names, model.class_vals, len(split_names) > 0)
         forest.append(t)
     return forest
 

@@ -82,6 +82,48 @@ def used_feature_ids(tree: TreeSoA) -> List[int]:
     return sorted(set(int(x) for x in np.unique(f[f >= 0])))
 
 
+_RE_QUOTED_KEY = __import__("re").compile(r"[\w\s]+")
+
+
+def reference_used_features(feature_cols, split_names, leaf_labels, has_split: bool) -> list:
+    """What the reference's ``tree2feats`` (model.py:413-417) reports for a tree: it greps ``str(tree)`` for
+    quoted keys (``'[\\w\\s]+':``) and intersects them with ``"'{f}':"`` of every feature column.  So a feature counts
+    as used when its name -- formatted into a string -- equals ANY string key of the nested dict made of word
+    characters and blanks: a feature it really splits on, but also the structural keys ('leaf', 'depth' in every tree;
+    'split', 'feat_type', 'split_val' when there is a split) and the class labels of its leaves; a feature whose name is
+    not a string, or holds other characters, is never found.  Returned in ``feature_cols`` order (the reference's order
+    is that of a hash set)."""
+    keys = {"leaf", "depth"}
+    if has_split:
+        keys.update(("split", "feat_type", "split_val"))
+    keys.update(k for k in split_names if isinstance(k, str))
+    keys.update(k for k in leaf_labels if isinstance(k, str))
+    keys = {k for k in keys if _RE_QUOTED_KEY.fullmatch(k)}
+    return [f"{f}" for f in feature_cols if f"{f}" in keys]
+
+
+def reference_used_features_of_dict(feature_cols, tree: dict) -> list:
+    split_names, labels, todo = set(), set(), [tree]
+    while todo:
+        node = todo.pop()
+        name = next(iter(node))
+        if name == "leaf":
+            labels.update(node["leaf"].keys())
+        else:
+            split_names.add(name)
+            todo.append(node[name]["split"][">="])
+            todo.append(node[name]["split"]["<"])
+    return reference_used_features(feature_cols, split_names, labels, bool(split_names))
+
+
+def reference_used_features_of_soa(feature_cols, tree: TreeSoA, class_sorted) -> list:
+    feat = tree.nodes["feat"]
+    leaf = feat < 0
+    present = np.flatnonzero(tree.counts[leaf].sum(axis=0) > 0)
+    ids = used_feature_ids(tree)
+    return reference_used_features(feature_cols, [feature_cols[j] for j in ids], [class_sorted[k] for k in present], len(ids) > 0)
+
+
 # --------------------------------------------------------------------------------------------
 # Forest flattening for the voting kernel
 # --------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ import pandas as pd
 
 from . import engine
 from .encode import EncodedDataset, LazyColumns
-from .flat import encode_frame, forest_tables_from_dicts, used_feature_ids
+from .flat import encode_frame, forest_tables_from_dicts
 from .forest import BaseRandomForestMC
 from .tree import DecisionTreeMC
 
@@ -337,18 +337,13 @@ class RandomForestMC(BaseRandomForestMC):
         return np.mean(y_val == y_pred)
 
     def tree2feats(self, Tree) -> List[str]:
+        """model.py:413-417, quirks included: see flat.reference_used_features."""
+        from .flat import reference_used_features_of_dict, reference_used_features_of_soa
+
         soa = getattr(Tree, "soa", None)
-        if soa is not None and Tree._data is None:
-            return [self.feature_cols[j] for j in used_feature_ids(soa)]
-        found, todo = set(), [Tree.data]
-        while todo:
-            node = todo.pop()
-            name = next(iter(node))
-            if name != "leaf":
-                found.add(name)
-                todo.append(node[name]["split"][">="])
-                todo.append(node[name]["split"]["<"])
-        return [f for f in self.feature_cols if f in found]
+        if soa is not None and Tree._data is None and Tree._enc is not None:
+            return reference_used_features_of_soa(self.feature_cols, soa, Tree._enc.class_sorted)
+        return reference_used_features_of_dict(self.feature_cols, Tree.data)
 
     # ---------------------------------------------------------------------------------------------
     # the batched, speculative fit loop

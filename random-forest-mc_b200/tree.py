@@ -81,10 +81,9 @@ class DecisionTreeMC(UserDict):
         """Features the tree splits on (model.py:413-417).  For a tree that came from the grower the
         list is read off the node table on first access."""
         if self._used_features is None and self._soa is not None and self._enc is not None:
-            from .flat import used_feature_ids
+            from .flat import reference_used_features_of_soa
 
-            names = self._enc.feature_cols
-            self._used_features = [names[j] for j in used_feature_ids(self._soa)]
+            self._used_features = reference_used_features_of_soa(self._enc.feature_cols, self._soa, self._enc.class_sorted)
         return self._used_features
 
     @used_features.setter

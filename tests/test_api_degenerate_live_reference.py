@@ -46,6 +46,19 @@ CASES = {
     "temporal features, unorderable names": (BASE.rename(columns={"x_1": "x"}), dict(temporal_features=True)),
     "duplicated rows": (pd.concat([BASE.head(5)] * 12), {}),
     "empty frame": (BASE.iloc[:0], {}),
+    # column names the reference's tree2feats regex (model.py:40, 413-417) treats in its own way
+    "int column names": (BASE.rename(columns={"x_1": 1, "y_2": 2, "c_3": 3}), {}),
+    "names with quotes": (BASE.rename(columns={"x_1": "it's", "y_2": 'say "hi"'}), {}),
+    "names with blanks and a colon": (BASE.rename(columns={"x_1": "a b", "y_2": "k: v"}), {}),
+    "feature named split / depth": (BASE.rename(columns={"y_2": "split", "c_3": "depth"}), {}),
+    "feature named like a class label": (BASE.rename(columns={"y_2": "u"}), {}),
+    "unicode names and labels": (BASE.rename(columns={"x_1": "größe", "c_3": "名前"}).assign(target=_g.choice(["ä", "β", "字"], size=_n)), {}),
+    "string index": (BASE.set_index(np.array([f"r{i}" for i in range(_n)])), {}),
+    "datetime feature": (BASE.assign(d_4=pd.to_datetime("2020-01-01") + pd.to_timedelta(_g.integers(0, 50, size=_n), unit="D")), {}),
+    "category dtype features": (BASE.astype({"c_3": "category", "y_2": "category"}), {}),
+    "nullable Int64 / Float64 features": (BASE.astype({"y_2": "Int64", "x_1": "Float64"}), {}),
+    "object-typed integers": (BASE.astype({"y_2": object}), {}),
+    "bytes feature": (BASE.assign(b_6=[b"a", b"bb"] * (_n // 2)), {}),
 }
 
 
@@ -88,6 +101,8 @@ def test_degenerate_case(name):
             assert len(a.data) == len(b.data) and all(tree_diff(x.data, y.data) is None for x, y in zip(a.data, b.data))
             assert [repr(float(s)) for s in a.survived_scores] == [repr(float(s)) for s in b.survived_scores]
             assert a.class_vals == b.class_vals and a.feature_cols == b.feature_cols and a._N == b._N
+            assert [sorted(map(str, t.used_features)) for t in a.data] == [sorted(map(str, t.used_features)) for t in b.data]
+            assert a.trees2depths == b.trees2depths and a.featImportance() == b.featImportance()
             pf = frame.drop(columns=["target"], errors="ignore").head(10)
             pa, pb = _call(a.testForestProbs, pf), _call(b.testForestProbs, pf)
             assert pa[0] == pb[0] and (pa[0] != "ok" or probs_equal(pa[1], pb[1]))
