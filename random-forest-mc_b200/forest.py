@@ -217,11 +217,20 @@ class BaseRandomForestMC(UserList):
         scores = list(self.survived_scores)
         if len(scores) != len(self.data):  # dict2model(add=True) leaves them out of step (forest.py:177-184)
             scores = scores[: len(self.data)] + [0.0] * max(0, len(self.data) - len(scores))
+        tables = None
         if all(getattr(t, "soa", None) is not None and t._data is None for t in self.data):
             enc = self.data[0]._enc
             if all(t._enc is enc for t in self.data):
-                return forest_tables_from_soa([t.soa for t in self.data], scores, enc, self.class_vals, self.feature_cols, f32_feats)
-        return forest_tables_from_dicts([t.data for t in self.data], scores, self.class_vals, self.feature_cols, f32_feats)
+                tables = forest_tables_from_soa([t.soa for t in self.data], scores, enc, self.class_vals, self.feature_cols, f32_feats)
+        if tables is None:
+            tables = forest_tables_from_dicts([t.data for t in self.data], scores, self.class_vals, self.feature_cols, f32_feats)
+        if len(self.survived_scores) != len(self.data):
+            # weighted votes pair trees with scores by zip() but divide by fsum(self.survived_scores) -- ALL of
+            # them, also the ones without a tree (forest.py:208-212, 224-231)
+            from math import fsum
+
+            tables.score_fsum = fsum(float(s) for s in self.survived_scores)
+        return tables
 
     def _float32_features(self, frame: pd.DataFrame, cells=None) -> frozenset:
         """Features whose cells reach the comparison of tree.py:177-180 as np.float32 scalars.  The

@@ -114,3 +114,24 @@ def test_explainability_helpers(ctx):
         for name in ("sampleClassFeatCount", "sampleClassFeatImportance", "sampleClassFeatScoreMean",
                      "sampleClassFeatPairImportance", "sampleClassFeatCorrDataFrame"):
             assert _equal(_call(getattr(a, name), row, Class), _call(getattr(b, name), row, Class)), (name, Class)
+
+
+def test_scores_out_of_step_with_trees(ctx):
+    """dict2model aliases the dict's score list (forest.py:177-184), so scores and trees can get out of step; weighted
+    votes then pair them by zip() but divide by fsum of ALL scores (forest.py:208-212, 224-231)."""
+    a, b = ctx["fit"](ctx["Mine"]), ctx["fit"](ctx["Ref"])
+    fr = ctx["frame"].head(40)
+    for change in ("one score too many", "one score too few"):
+        for m in (a, b):
+            m.survived_scores = [float(s) for s in m.survived_scores]
+            if change == "one score too many":
+                m.survived_scores.append(0.123)
+            else:
+                del m.survived_scores[-2:]
+        for soft in (False, True):
+            for weighted in (False, True):
+                for m in (a, b):
+                    m.setSoftVoting(soft)
+                    m.setWeightedTrees(weighted)
+                assert probs_equal(a.testForestProbs(fr), b.testForestProbs(fr)), (change, soft, weighted)
+                assert a.useForest(fr.iloc[1]) == b.useForest(fr.iloc[1]), (change, soft, weighted)
