@@ -246,6 +246,16 @@ class BaseRandomForestMC(UserList):
         return frozenset(j for j, name in enumerate(self.feature_cols) if name in frame.columns)
 
     def _vote_frame(self, frame: pd.DataFrame, want_probs: bool, want_labels: bool, cells=None):
+        if len(self.data) == 0:
+            # no tree votes (forest.py:204-233): the unweighted modes divide by len([]) -> ZeroDivisionError; the
+            # weighted ones divide an empty sum by fsum(self.survived_scores), which may still hold scores
+            from math import fsum
+
+            if not self.weighted_tree:
+                raise ZeroDivisionError("division by zero")
+            share = 0.0 / fsum(float(s) for s in self.survived_scores)
+            n, C = len(frame), len(self.class_vals)
+            return (np.full((n, C), share) if want_probs else None), (np.zeros(n, dtype=np.int64) if want_labels else None)
         f32 = self._float32_features(frame, cells)
         dev = self._device_forest(f32)
         self._raise_for_unorderable_cells(dev, frame)

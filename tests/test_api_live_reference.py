@@ -135,3 +135,45 @@ def test_scores_out_of_step_with_trees(ctx):
                     m.setWeightedTrees(weighted)
                 assert probs_equal(a.testForestProbs(fr), b.testForestProbs(fr)), (change, soft, weighted)
                 assert a.useForest(fr.iloc[1]) == b.useForest(fr.iloc[1]), (change, soft, weighted)
+
+
+def test_pathological_scores_and_an_emptied_forest(ctx):
+    """Weighted votes with score lists a user can produce by hand: all zero / zero sum (ZeroDivisionError), NaN, negative,
+    integers, no scores at all, denormals, 1e308 (OverflowError from fsum); and a forest emptied of its trees but not
+    of its scores (weighted modes return zeros, unweighted ones ZeroDivisionError)."""
+    fr = ctx["frame"].head(20)
+    cases = {"all zero": [0.0] * 6, "zero sum": [0.5, -0.5, 0.25, -0.25, 1.0, -1.0], "nan": [0.5, float("nan"), 0.5, 0.5, 0.5, 0.5],
+             "negative": [-0.5, -0.25, -1.0, -0.1, -0.2, -0.3], "numpy zeros": [np.float64(0.0)] * 6, "integers": [1, 2, 3, 4, 5, 6],
+             "no scores": [], "denormal": [1e-320] * 6, "huge": [1e308] * 6}
+    a, b = ctx["fit"](ctx["Mine"]), ctx["fit"](ctx["Ref"])
+
+    def same(x, y):
+        if x[0] == "raised" or y[0] == "raised":
+            return x == y
+        return all(all(p[k] == q[k] or (p[k] != p[k] and q[k] != q[k]) for k in p) and list(p) == list(q) for p, q in zip(x[1], y[1]))
+
+    def call(fn, *args):
+        try:
+            return ("ok", fn(*args))
+        except Exception as e:
+            return ("raised", type(e).__name__)
+
+    for name, scores in cases.items():
+        a.survived_scores, b.survived_scores = list(scores), list(scores)
+        for soft in (False, True):
+            for m in (a, b):
+                m.setSoftVoting(soft)
+                m.setWeightedTrees(True)
+            assert same(call(a.testForestProbs, fr), call(b.testForestProbs, fr)), (name, soft)
+            if name != "nan":  # the label of an all-NaN vote depends on sorted()'s handling of NaN
+                assert call(a.testForest, fr) == call(b.testForest, fr), (name, soft)
+    a.survived_scores, b.survived_scores = [0.5] * 6, [0.5] * 6
+    a.data, b.data = [], []
+    for soft in (False, True):
+        for weighted in (False, True):
+            for m in (a, b):
+                m.setSoftVoting(soft)
+                m.setWeightedTrees(weighted)
+            assert same(call(a.testForestProbs, fr), call(b.testForestProbs, fr)), (soft, weighted)
+            assert call(a.testForest, fr) == call(b.testForest, fr), (soft, weighted)
+            assert call(a.useForest, fr.iloc[0]) == call(b.useForest, fr.iloc[0]), (soft, weighted)
