@@ -86,6 +86,11 @@ class EncodedDataset:
         self.sorted_to_classvals = sorted_to_classvals
         self.class_rows = class_rows if class_rows is not None else []
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_fetch_codes"] = None  # a closure over a device handle: a copy keeps the description, not the matrix
+        return state
+
     @property
     def codes(self) -> np.ndarray:
         if self._codes is None:

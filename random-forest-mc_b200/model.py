@@ -261,8 +261,29 @@ class RandomForestMC(BaseRandomForestMC):
         raise IndexError("arrays used as indices must be of integer (or boolean) type")
 
     def _require_dataset(self):
+        if self.dataset_numpy is not None and self._dev_dataset is None and self.n_samples and self.feature_cols:
+            # a model that was pickled / deep-copied travels without its device handles: encode again
+            self.encoded, self._dev_dataset = engine.encode_dataset_device(
+                self.dataset_numpy, self.feature_cols, self.numeric_cols, self.target_col, self.class_vals, self.device
+            )
         if self.dataset_numpy is None or self._dev_dataset is None:
             raise DatasetNotFound
+
+    # -- pickling / copy.deepcopy (the reference model is a plain picklable object; joblib.dump(model) is common) --
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for key in ("_tls", "_dev_dataset", "_forest_dev", "_forest_f32", "_stream_hooks"):
+            state.pop(key, None)
+        state["_forest_key"] = None
+        state["_forest_tables"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._tls = threading.local()
+        self._dev_dataset = None
+        self._forest_dev = None
+        self._forest_f32 = None
 
     def _feat_ids(self, feature_list: List[str]) -> List[int]:
         pos = {name: j for j, name in enumerate(self.feature_cols)}

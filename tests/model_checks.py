@@ -121,3 +121,39 @@ def check_predict_missing_values():
         m.predictMissingValues(g["frame"].loc[0], g["dict_values"])
     with pytest.raises(DictValuesAllFeaturesMissing):
         m.predictMissingValues(g["holes"], {"Not Feature": [1, 2], "Not Feature 2": [3]})
+
+
+def check_pickle_and_deepcopy():
+    """The reference model is a plain picklable object (its fitParallel pickles it; users joblib.dump it).  A copy
+    travels without device handles: it votes at once (the forest is re-flattened) and re-encodes its dataset on the
+    device when it is fitted again, continuing exactly as the original would."""
+    import copy
+    import pickle
+    import random
+
+    from random_forest_mc_b200.model import RandomForestMC
+
+    g = load_golden("mixed_default")
+    kw = dict(g["kwargs"])
+    kw["n_trees"] = 3
+    m = RandomForestMC(**kw)
+    np.random.seed(1)
+    random.seed(1)
+    m.fit(g["frame"].copy(), disable_progress_bar=True)
+    fr = g["frame"].drop(columns=[kw["target_col"]]).head(20)
+    m.setSoftVoting(True)
+    want = m.testForestProbs(fr)
+    copies = [copy.deepcopy(m), pickle.loads(pickle.dumps(m))]
+    for c in copies:
+        assert c.testForestProbs(fr) == want and c.soft_voting
+        assert all(tree_diff(a.data, b.data) is None for a, b in zip(c.data, m.data))
+        np.random.seed(2)
+        random.seed(2)
+        c.fit(disable_progress_bar=True)
+    np.random.seed(2)
+    random.seed(2)
+    m.fit(disable_progress_bar=True)
+    for c in copies:
+        assert len(c.data) == len(m.data) == 6
+        assert all(tree_diff(a.data, b.data) is None for a, b in zip(c.data, m.data))
+        assert [float(s) for s in c.survived_scores] == [float(s) for s in m.survived_scores]

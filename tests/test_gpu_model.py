@@ -136,3 +136,7 @@ def test_float32_frames_on_a_float64_trained_forest_match_the_oracle():
     m.setSoftVoting(False)
     m.setWeightedTrees(False)
     assert m.testForestProbs(f32) != m.testForestProbs(f32.astype("float64"))  # not vacuous
+
+
+def test_pickle_and_deepcopy():
+    model_checks.check_pickle_and_deepcopy()

@@ -121,3 +121,7 @@ def test_fit_parallel_host_streams_contract():
         m2.fitParallel(g["frame"].copy(), disable_progress_bar=True, max_workers=3)
         outs.append([float(s) for s in m2.survived_scores])
     assert outs[0] == outs[1] and len(outs[0]) == 5
+
+
+def test_pickle_and_deepcopy():
+    model_checks.check_pickle_and_deepcopy()
