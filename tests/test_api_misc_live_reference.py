@@ -72,3 +72,39 @@ def test_single_candidate_api_tree_objects_and_parallel_votes(seed):
         assert probs_equal(a.testForestProbsParallel(fr, max_workers=2), b.testForestProbsParallel(fr, max_workers=2))
     finally:
         mp.undo()
+
+
+def test_hand_built_tree_called_on_awkward_rows():
+    """A DecisionTreeMC built directly from a nested dict (as the reference's own unit tests do), called on Series and
+    dict rows: equal values, missing features (both subtrees evaluated, first leaf renormalised), NaN / None cells, a
+    string in a numeric feature (TypeError only when reached), a float32 cell, bools, an empty row."""
+    import pandas as pd
+
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    from random_forest_mc.tree import DecisionTreeMC as Ref
+
+    from random_forest_mc_b200.tree import DecisionTreeMC as Mine
+
+    mp = pytest.MonkeyPatch()
+    fake_engine.install(mp)
+    try:
+        leaf = lambda d: {"leaf": d, "depth": "3#"}  # noqa: E731
+        tree = {"feat1": {"split": {"feat_type": "numeric", "split_val": 5,
+                                    ">=": {"feat2": {"split": {"feat_type": "categorical", "split_val": "A",
+                                                               ">=": leaf({"0": 0.8, "1": 0.2}), "<": leaf({"0": 0.3, "1": 0.7})}}},
+                                    "<": {"feat3": {"split": {"feat_type": "numeric", "split_val": 2.5,
+                                                              ">=": leaf({"1": 1.0}), "<": leaf({"0": 0.5, "1": 0.5})}}}}}}
+        a, b = Mine(tree, ["0", "1"]), Ref(tree, ["0", "1"])
+        rows = [{"feat1": 6, "feat2": "A", "feat3": 1}, {"feat1": 5, "feat2": "B", "feat3": 1}, {"feat1": 4, "feat2": "A", "feat3": 2.5},
+                {"feat1": 4, "feat2": "A", "feat3": 2.4}, {"feat2": "A", "feat3": 3}, {"feat1": 7, "feat3": 3}, {"feat1": 1},
+                {"feat1": np.nan, "feat2": "A", "feat3": 9}, {"feat1": 7, "feat2": None, "feat3": 9}, {},
+                {"feat1": "x", "feat2": "A", "feat3": 1}, {"feat1": 7, "feat2": "A", "feat3": "x"},
+                {"feat1": 5.0, "feat2": "A", "feat3": np.float32(2.5)}, {"feat1": True, "feat2": "A", "feat3": False}]
+        for r in rows:
+            for form in (pd.Series(r, dtype=object), r):
+                assert _call(a, form) == _call(b, form), r
+        assert a.depths == b.depths and str(a) == str(b) and a.md5hexdigest == b.md5hexdigest
+        assert a.tree2dict().keys() == b.tree2dict().keys()
+    finally:
+        mp.undo()
