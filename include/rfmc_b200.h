@@ -65,6 +65,7 @@ typedef struct rfmc_pnode {
 typedef struct rfmc_dataset rfmc_dataset;
 typedef struct rfmc_batch rfmc_batch;
 typedef struct rfmc_forest rfmc_forest;
+typedef struct rfmc_drawplan rfmc_drawplan;
 
 int rfmc_abi_version(void);
 /* A non-blocking CUDA stream on `device` as an opaque pointer for the `stream` arguments below
@@ -215,6 +216,50 @@ int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos, int32_t n_slots, int32_t 
                           const int64_t* class_off, int64_t per_class, int64_t n_train_pclass, int32_t n_cands,
                           int64_t randint_low, int64_t randint_high, int32_t* idx_train, int32_t* idx_val,
                           int32_t* feat_counts, uint32_t* key_snap, int32_t* pos_snap, int32_t n_threads);
+
+/* ---- split_train_val / sampleFeats on the device (model.py:198-219) -----------------
+ * The same draws as rfmc_legacy_draw_plan, walked on the GPU: numpy's legacy MT19937 stream is
+ * generated in HBM (GF(2) jump-ahead, one CTA per chunk of the stream), the masked rejection of
+ * random_interval is decided exactly in chunks of 8,192 words, the first per_class entries of every
+ * class's permutation are resolved, and idx_train / idx_val stay in HBM as the inputs of
+ * rfmc_batch_create_from_plan.  Same row ids, same feature counts, same end state as numpy.
+ *
+ * rfmc_dataset_set_class_rows  once per dataset: class_rows = every class's ascending row ids back to
+ *                       back (class c = [class_off[c], class_off[c+1])), in class_vals order.
+ * rfmc_draw_plan_device launches the plan on `stream` (asynchronous).  key[624] / pos are
+ *                       np.random.get_state()[1:3]; per_class <= RFMC_DRAW_MAX_PER_CLASS.
+ * rfmc_drawplan_finish  waits; feat_counts [n_slots][n_cands] = the randint values; key_end / pos_end
+ *                       = the stream state after the plan (what np.random.set_state takes).
+ * rfmc_drawplan_state_at  the stream state BEFORE slot `slot` (slot == n_slots: after the plan), for the
+ *                       exact rewind of a mis-speculated plan.
+ * rfmc_drawplan_indices device -> host copy of the row ids of slots [slot0, slot0 + n_slots).
+ * rfmc_drawplan_info    words generated / consumed, chunks that fell back to the exact warp path,
+ *                       kernel launches.  rfmc_drawplan_timing(1) makes every later plan bracket its
+ *                       kernels with CUDA events; rfmc_drawplan_kernel_ms returns {fill, walk, resolve
+ *                       scan, resolve prefix} in milliseconds (measurement hooks of bench.py).      */
+#define RFMC_DRAW_MAX_PER_CLASS 4096
+/* t^(offset-1) mod phi (the characteristic polynomial of MT19937) as 624 words, bit i = coefficient
+ * of t^i; and its host evaluation: the untempered window x[offset .. offset+623] of the stream whose
+ * window at 0 is key[624] (tests; the device evaluates the same correlation in mt_fill_kernel).   */
+int rfmc_mt_jump_poly(int64_t offset, uint32_t* out624);
+int rfmc_mt_jump_window_host(const uint32_t* key, int64_t offset, uint32_t* out624);
+int rfmc_dataset_set_class_rows(rfmc_dataset* ds, int32_t n_classes, const int64_t* class_rows, const int64_t* class_off);
+int rfmc_draw_plan_device(rfmc_dataset* ds, const uint32_t* key, int32_t pos, int32_t n_slots, int64_t per_class,
+                          int64_t n_train_pclass, int32_t n_cands, int64_t randint_low, int64_t randint_high, void* stream,
+                          rfmc_drawplan** out);
+int rfmc_drawplan_finish(rfmc_drawplan* pl, int32_t* feat_counts, uint32_t* key_end, int32_t* pos_end);
+int rfmc_drawplan_state_at(rfmc_drawplan* pl, int32_t slot, uint32_t* key, int32_t* pos);
+int rfmc_drawplan_indices(rfmc_drawplan* pl, int32_t slot0, int32_t n_slots, int32_t* idx_train, int32_t* idx_val);
+int rfmc_drawplan_info(rfmc_drawplan* pl, int64_t* words_generated, int64_t* words_consumed, int32_t* chunk_fallbacks,
+                       int32_t* launches);
+int rfmc_drawplan_timing(int enabled);
+int rfmc_drawplan_kernel_ms(rfmc_drawplan* pl, float* ms4);
+int rfmc_drawplan_destroy(rfmc_drawplan* pl);
+/* rfmc_batch_create with the row ids of a finished or in-flight draw plan (same stream): nothing but
+ * the feature lists crosses the bus.  The plan must outlive the batch. */
+int rfmc_batch_create_from_plan(rfmc_dataset* ds, rfmc_drawplan* pl, int32_t n_cand, const int32_t* cand_slot,
+                                const int32_t* feat_off, const uint16_t* feat_list, int32_t max_depth,
+                                int32_t min_samples_split, void* stream, rfmc_batch** out);
 
 #ifdef __cplusplus
 }

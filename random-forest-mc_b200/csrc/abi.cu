@@ -39,7 +39,7 @@ static void flush_cache_locked(DevCache& dc) {
     dc.cached = 0;
 }
 
-static cudaError_t dev_alloc(void** p, size_t bytes) {
+cudaError_t dev_alloc(void** p, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
     bytes = size_class(bytes);
@@ -67,7 +67,7 @@ static cudaError_t dev_alloc(void** p, size_t bytes) {
     return e;
 }
 
-static void release(void* p) {
+void release(void* p) {
     if (!p) return;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -558,14 +558,18 @@ int rfmc_dataset_destroy(rfmc_dataset* ds) {
     release(ds->d_nuniq);
     release(ds->d_taboff);
     release(ds->d_tables);
+    release(ds->d_class_n);
+    release(ds->d_class_aoff);
+    release(ds->d_class_rows);
+    release(ds->d_class_roff);
     delete ds;
     return 0;
 }
 
-int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_t n_val, const int32_t* idx_train,
-                      const int32_t* idx_val, int32_t n_cand, const int32_t* cand_slot, const int32_t* feat_off,
-                      const uint16_t* feat_list, int32_t max_depth, int32_t min_samples_split, void* stream,
-                      rfmc_batch** out) {
+static int batch_create_impl(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_t n_val, const int32_t* idx_train,
+                             const int32_t* idx_val, bool idx_on_device, int32_t n_cand, const int32_t* cand_slot,
+                             const int32_t* feat_off, const uint16_t* feat_list, int32_t max_depth, int32_t min_samples_split,
+                             void* stream, rfmc_batch** out) {
     RFMC_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     RFMC_REQUIRE(ds != nullptr, "dataset is NULL");
@@ -598,8 +602,14 @@ int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_
     b->stream = st;
     const size_t g = (size_t)b->grid, ntp = (size_t)b->nt_pad, C = (size_t)ds->n_classes;
     int rc = 0;
-    rc |= upload(&b->d_idx_train, idx_train, (size_t)n_slots * n_train, st);
-    rc |= upload(&b->d_idx_val, idx_val, (size_t)n_slots * n_val, st);
+    if (idx_on_device) {
+        b->own_idx = false;
+        b->d_idx_train = const_cast<int32_t*>(idx_train);
+        b->d_idx_val = const_cast<int32_t*>(idx_val);
+    } else {
+        rc |= upload(&b->d_idx_train, idx_train, (size_t)n_slots * n_train, st);
+        rc |= upload(&b->d_idx_val, idx_val, (size_t)n_slots * n_val, st);
+    }
     rc |= upload(&b->d_cand_slot, cand_slot, (size_t)n_cand, st);
     rc |= upload(&b->d_feat_off, feat_off, (size_t)n_cand + 1, st);
     rc |= upload(&b->d_feat_list, feat_list, (size_t)feat_off[n_cand], st);
@@ -621,6 +631,26 @@ int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_
     }
     *out = b;
     return 0;
+}
+
+int rfmc_batch_create(rfmc_dataset* ds, int32_t n_slots, int32_t n_train, int32_t n_val, const int32_t* idx_train,
+                      const int32_t* idx_val, int32_t n_cand, const int32_t* cand_slot, const int32_t* feat_off,
+                      const uint16_t* feat_list, int32_t max_depth, int32_t min_samples_split, void* stream,
+                      rfmc_batch** out) {
+    return batch_create_impl(ds, n_slots, n_train, n_val, idx_train, idx_val, false, n_cand, cand_slot, feat_off, feat_list,
+                             max_depth, min_samples_split, stream, out);
+}
+
+int rfmc_batch_create_from_plan(rfmc_dataset* ds, rfmc_drawplan* pl, int32_t n_cand, const int32_t* cand_slot,
+                                const int32_t* feat_off, const uint16_t* feat_list, int32_t max_depth,
+                                int32_t min_samples_split, void* stream, rfmc_batch** out) {
+    RFMC_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RFMC_REQUIRE(pl != nullptr && pl->ds == ds, "plan is NULL or belongs to another dataset");
+    RFMC_REQUIRE((cudaStream_t)stream == pl->stream, "the batch must run on the plan's stream");
+    return batch_create_impl(ds, pl->n_slots, (int32_t)(pl->n_classes * pl->n_tr), (int32_t)(pl->n_classes * pl->n_va),
+                             pl->d_idx_train, pl->d_idx_val, true, n_cand, cand_slot, feat_off, feat_list, max_depth,
+                             min_samples_split, stream, out);
 }
 
 int rfmc_batch_run(rfmc_batch* b, void* stream) {
@@ -730,8 +760,13 @@ int rfmc_batch_pack(rfmc_batch* b, const int32_t* cand_ids, int32_t n_sel, rfmc_
 int rfmc_batch_destroy(rfmc_batch* b) {
     if (!b) return 0;
     cudaSetDevice(b->ds->device);
-    release(b->d_idx_train);
-    release(b->d_idx_val);
+    // blocks go back to a process-wide pool: nothing of this batch may still be in flight (error paths,
+    // a close() before results())
+    cudaStreamSynchronize(b->stream);
+    if (b->own_idx) {
+        release(b->d_idx_train);
+        release(b->d_idx_val);
+    }
     release(b->d_cand_slot);
     release(b->d_feat_off);
     release(b->d_feat_list);

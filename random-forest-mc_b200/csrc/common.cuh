@@ -58,6 +58,13 @@ struct rfmc_dataset {
     std::vector<int32_t> h_nuniq;
     std::vector<int64_t> h_taboff;
     std::vector<double> h_tables;
+    // per-class row lists for the device draws (rfmc_dataset_set_class_rows)
+    int32_t n_draw_classes = 0;
+    int32_t* d_class_n = nullptr;     // [C] rows per class
+    int64_t* d_class_aoff = nullptr;  // [C+1] offsets of each class's n-1 shuffle draws inside one slot
+    int32_t* d_class_rows = nullptr;  // ascending row ids of every class back to back
+    int64_t* d_class_roff = nullptr;  // [C+1]
+    std::vector<int64_t> h_class_n;
 };
 
 struct rfmc_batch {
@@ -65,6 +72,7 @@ struct rfmc_batch {
     int32_t n_slots = 0, n_train = 0, n_val = 0, n_cand = 0, max_depth = 0, mss = 1;
     int32_t nt_pad = 0, max_nodes = 0, fmax = 0, grid = 0;
     int launches = 0;
+    bool own_idx = true;  // false: idx_train / idx_val belong to a draw plan (rfmc_batch_create_from_plan)
     // inputs
     int32_t* d_idx_train = nullptr;
     int32_t* d_idx_val = nullptr;
@@ -93,6 +101,37 @@ struct rfmc_batch {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
+// One plan of tree slots drawn on the device (csrc/rng_walk.cu): numpy's legacy stream walked in HBM.
+struct rfmc_drawplan {
+    rfmc_dataset* ds = nullptr;
+    cudaStream_t stream = nullptr;
+    int32_t n_slots = 0, n_classes = 0, n_cands = 0, pos0 = 0;
+    int64_t size = 0, n_tr = 0, n_va = 0;  // per class: drawn, training part, hold-out part
+    int64_t randint_low = 0;
+    uint32_t rmask = 0, rrange = 0;
+    int cap_log2 = 10;
+    int attempt = 0;
+    int64_t n_blocks = 0, n_chunks = 0;
+    int blocks_per_chunk = 0;
+    int launches = 0;
+    bool finished = false;
+    uint32_t h_key[624];
+    uint32_t* d_key = nullptr;
+    const uint32_t* d_polys = nullptr;  // borrowed from the per-device table
+    uint32_t* d_W = nullptr;
+    uint32_t* d_A = nullptr;
+    uint32_t* d_heads = nullptr;
+    int32_t* d_idx_train = nullptr;
+    int32_t* d_idx_val = nullptr;
+    int32_t* d_randv = nullptr;
+    int64_t* d_slot_pos = nullptr;
+    int32_t* d_status = nullptr;
+    std::vector<int64_t> h_slot_pos;
+    int32_t h_status[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // measurement hook
+    bool timing = false;
+};
+
 struct PredictPipe;
 
 struct rfmc_forest {
@@ -118,6 +157,13 @@ struct rfmc_forest {
 };
 
 namespace rfmc {
+cudaError_t dev_alloc(void** p, size_t bytes);
+void release(void* p);
+int drawplan_launch(rfmc_drawplan* pl);
+int64_t drawplan_words_needed(const std::vector<int64_t>& class_n, int n_slots, int n_cands, uint32_t rmask, uint32_t rrange,
+                              int attempt);
+int drawplan_geometry(rfmc_drawplan* pl, int64_t words);
+int64_t drawplan_chunk_words(const rfmc_drawplan* pl);
 int launch_grow(rfmc_batch* b, cudaStream_t stream);
 int grow_grid_size(const rfmc_dataset* ds, int n_cand, int n_train);
 int debug_read(unsigned long long* out, int n);

@@ -76,7 +76,21 @@ _SIGNATURES = {
                                             C.c_int, C.c_int, _p, _p]),
     "rfmc_legacy_draw_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p, C.c_int64, C.c_int64,
                                         C.c_int32, C.c_int64, C.c_int64, _p, _p, _p, _p, _p, C.c_int32]),
+    "rfmc_mt_jump_poly": (C.c_int, [C.c_int64, _p]),
+    "rfmc_mt_jump_window_host": (C.c_int, [_p, C.c_int64, _p]),
+    "rfmc_dataset_set_class_rows": (C.c_int, [_p, C.c_int32, _p, _p]),
+    "rfmc_draw_plan_device": (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _p,
+                                        C.POINTER(_p)]),
+    "rfmc_drawplan_finish": (C.c_int, [_p, _p, _p, C.POINTER(C.c_int32)]),
+    "rfmc_drawplan_state_at": (C.c_int, [_p, C.c_int32, _p, C.POINTER(C.c_int32)]),
+    "rfmc_drawplan_indices": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p]),
+    "rfmc_drawplan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rfmc_drawplan_timing": (C.c_int, [C.c_int]),
+    "rfmc_drawplan_kernel_ms": (C.c_int, [_p, _p]),
+    "rfmc_drawplan_destroy": (C.c_int, [_p]),
+    "rfmc_batch_create_from_plan": (C.c_int, [_p, _p, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
 }
+DRAW_MAX_PER_CLASS = 4096  # RFMC_DRAW_MAX_PER_CLASS
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
@@ -266,6 +280,14 @@ class DeviceDataset:
         self._h = handle
         return self
 
+    def set_class_rows(self, class_rows: Sequence[np.ndarray]) -> None:
+        """Per-class row lists (class_vals order) for the device draws; uploaded once."""
+        if getattr(self, "_class_rows_id", None) is class_rows:
+            return
+        rows, off = _flat_class_rows(class_rows)
+        _check(load_library().rfmc_dataset_set_class_rows(self._h, len(class_rows), _ptr(rows), _ptr(off)))
+        self._class_rows_id = class_rows
+
     def close(self):
         if getattr(self, "_h", None):
             load_library().rfmc_dataset_destroy(self._h)
@@ -276,6 +298,83 @@ class DeviceDataset:
             self.close()
         except Exception:
             pass
+
+
+class DrawPlan:
+    """rfmc_drawplan handle: the numpy-stream draws of a plan of tree slots, walked on the GPU
+    (split_train_val / sampleFeats, model.py:198-219).  Row ids stay in HBM for the grower."""
+
+    def __init__(self, ds: DeviceDataset, class_rows: Sequence[np.ndarray], key: np.ndarray, pos: int, n_slots: int,
+                 per_class: int, n_train_pclass: int, n_cands: int, low: int, high: int, stream=None):
+        self.ds = ds
+        ds.set_class_rows(class_rows)
+        self.n_slots, self.n_cands = int(n_slots), int(n_cands)
+        self.n_classes = len(class_rows)
+        self.n_tr = min(int(per_class), int(n_train_pclass))
+        self.n_va = int(per_class) - self.n_tr
+        self._stream = _stream_ptr(stream)
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        h = _p()
+        _check(load_library().rfmc_draw_plan_device(ds._h, _ptr(key), int(pos), self.n_slots, int(per_class), int(n_train_pclass),
+                                                     self.n_cands, int(low), int(high), self._stream, C.byref(h)))
+        self._h = h
+
+    def finish(self):
+        """Wait for the plan.  Returns (feat_counts [n_slots, n_cands], key_end, pos_end)."""
+        counts = np.zeros((self.n_slots, self.n_cands), dtype=np.int32)
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32(0)
+        _check(load_library().rfmc_drawplan_finish(self._h, _ptr(counts), _ptr(key), C.byref(pos)))
+        return counts, key, pos.value
+
+    def state_at(self, slot: int):
+        """numpy's stream state (key, pos) before slot ``slot`` (``n_slots``: after the plan)."""
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32(0)
+        _check(load_library().rfmc_drawplan_state_at(self._h, int(slot), _ptr(key), C.byref(pos)))
+        return key, pos.value
+
+    def indices(self, slot0: int = 0, n_slots: Optional[int] = None):
+        n = self.n_slots - slot0 if n_slots is None else int(n_slots)
+        T = np.empty((n, self.n_classes * self.n_tr), dtype=np.int32)
+        V = np.empty((n, self.n_classes * self.n_va), dtype=np.int32)
+        _check(load_library().rfmc_drawplan_indices(self._h, int(slot0), n, _ptr(T), _ptr(V)))
+        return T, V
+
+    def info(self):
+        g, c, f, l = C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        _check(load_library().rfmc_drawplan_info(self._h, C.byref(g), C.byref(c), C.byref(f), C.byref(l)))
+        return dict(words_generated=g.value, words_consumed=c.value, chunk_fallbacks=f.value, launches=l.value)
+
+    def kernel_ms(self):
+        """(fill, walk, resolve scan, resolve prefix) in ms; needs engine.drawplan_timing(True) before creation."""
+        ms = (C.c_float * 4)()
+        _check(load_library().rfmc_drawplan_kernel_ms(self._h, C.cast(ms, _p)))
+        return tuple(float(x) for x in ms)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().rfmc_drawplan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def drawplan_timing(enabled: bool) -> None:
+    _check(load_library().rfmc_drawplan_timing(int(bool(enabled))))
+
+
+def mt_jump_window_host(key: np.ndarray, offset: int) -> np.ndarray:
+    """Host evaluation of the MT19937 jump: the untempered window x[offset .. offset+623]."""
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(624, dtype=np.uint32)
+    if load_library().rfmc_mt_jump_window_host(_ptr(key), int(offset), _ptr(out)) != 0:
+        raise EngineError("rfmc_mt_jump_window_host: bad arguments")
+    return out
 
 
 # numpy dtype -> RFMC_DT_* (include/rfmc_b200.h)
@@ -387,21 +486,18 @@ class GrowBatch:
     def __init__(
         self,
         ds: DeviceDataset,
-        idx_train: np.ndarray,
-        idx_val: np.ndarray,
+        idx_train,
+        idx_val,
         cand_slot: Sequence[int],
         feat_lists: Sequence[Sequence[int]],
         max_depth: int,
         min_samples_split: int,
         stream=None,
+        plan: Optional["DrawPlan"] = None,
     ):
+        """Row ids either as host arrays ``idx_train`` / ``idx_val`` [n_slots, n], or -- ``plan`` given --
+        the device-resident output of a DrawPlan on the same stream (both arrays None)."""
         self.ds = ds
-        idx_train = np.ascontiguousarray(idx_train, dtype=np.int32)
-        idx_val = np.ascontiguousarray(idx_val, dtype=np.int32)
-        if idx_train.ndim != 2 or idx_val.ndim != 2 or idx_train.shape[0] != idx_val.shape[0]:
-            raise ValueError("idx_train / idx_val must be [n_slots, n] arrays")
-        self.n_slots, self.n_train = idx_train.shape
-        self.n_val = idx_val.shape[1]
         cand_slot = np.ascontiguousarray(cand_slot, dtype=np.int32)
         self.n_cand = len(cand_slot)
         off = np.zeros(self.n_cand + 1, dtype=np.int32)
@@ -409,13 +505,29 @@ class GrowBatch:
         flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint16) for f in feat_lists]), dtype=np.uint16)
         self._stream = _stream_ptr(stream)
         h = _p()
-        _check(
-            load_library().rfmc_batch_create(
-                ds._h, self.n_slots, self.n_train, self.n_val, _ptr(idx_train), _ptr(idx_val), self.n_cand,
-                _ptr(cand_slot), _ptr(off), _ptr(flat), int(min(max_depth, 2**31 - 1)), int(min_samples_split),
-                self._stream, C.byref(h),
+        if plan is not None:
+            self._plan = plan  # the plan owns the row ids: keep it alive
+            self.n_slots, self.n_train, self.n_val = plan.n_slots, plan.n_classes * plan.n_tr, plan.n_classes * plan.n_va
+            _check(
+                load_library().rfmc_batch_create_from_plan(
+                    ds._h, plan._h, self.n_cand, _ptr(cand_slot), _ptr(off), _ptr(flat), int(min(max_depth, 2**31 - 1)),
+                    int(min_samples_split), self._stream, C.byref(h),
+                )
             )
-        )
+        else:
+            idx_train = np.ascontiguousarray(idx_train, dtype=np.int32)
+            idx_val = np.ascontiguousarray(idx_val, dtype=np.int32)
+            if idx_train.ndim != 2 or idx_val.ndim != 2 or idx_train.shape[0] != idx_val.shape[0]:
+                raise ValueError("idx_train / idx_val must be [n_slots, n] arrays")
+            self.n_slots, self.n_train = idx_train.shape
+            self.n_val = idx_val.shape[1]
+            _check(
+                load_library().rfmc_batch_create(
+                    ds._h, self.n_slots, self.n_train, self.n_val, _ptr(idx_train), _ptr(idx_val), self.n_cand,
+                    _ptr(cand_slot), _ptr(off), _ptr(flat), int(min(max_depth, 2**31 - 1)), int(min_samples_split),
+                    self._stream, C.byref(h),
+                )
+            )
         self._h = h
         self.correct = None
         self.n_nodes = None
