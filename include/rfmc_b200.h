@@ -220,9 +220,11 @@ int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos, int32_t n_slots, int32_t 
 /* ---- split_train_val / sampleFeats on the device (model.py:198-219) -----------------
  * The same draws as rfmc_legacy_draw_plan, walked on the GPU: numpy's legacy MT19937 stream is
  * generated in HBM (GF(2) jump-ahead, one CTA per chunk of the stream), the masked rejection of
- * random_interval is decided exactly in chunks of 8,192 words, the first per_class entries of every
- * class's permutation are resolved, and idx_train / idx_val stay in HBM as the inputs of
- * rfmc_batch_create_from_plan.  Same row ids, same feature counts, same end state as numpy.
+ * random_interval is decided in chunks of 4,096 words (GPU-wide against a band around the expected
+ * accept count, the undecided words settled exactly by one CTA per stream, every decision verified by
+ * a final pass), the first per_class entries of every class's permutation are resolved, and idx_train
+ * / idx_val stay in HBM as the inputs of rfmc_batch_create_from_plan.  Same row ids, same feature
+ * counts, same end state as numpy.
  *
  * rfmc_dataset_set_class_rows  once per dataset: class_rows = every class's ascending row ids back to
  *                       back (class c = [class_off[c], class_off[c+1])), in class_vals order.
@@ -233,10 +235,11 @@ int rfmc_legacy_draw_plan(uint32_t* key, int32_t* pos, int32_t n_slots, int32_t 
  * rfmc_drawplan_state_at  the stream state BEFORE slot `slot` (slot == n_slots: after the plan), for the
  *                       exact rewind of a mis-speculated plan.
  * rfmc_drawplan_indices device -> host copy of the row ids of slots [slot0, slot0 + n_slots).
- * rfmc_drawplan_info    words generated / consumed, chunks that fell back to the exact warp path,
- *                       kernel launches.  rfmc_drawplan_timing(1) makes every later plan bracket its
- *                       kernels with CUDA events; rfmc_drawplan_kernel_ms returns {fill, walk, resolve
- *                       scan, resolve prefix} in milliseconds (measurement hooks of bench.py).      */
+ * rfmc_drawplan_info    words generated / consumed / left pending for the chain (thousands, rounded
+ *                       down), chunks the final pass redid with every word pending, kernel launches.
+ *                       rfmc_drawplan_timing(1) makes every later plan bracket its kernels with CUDA
+ *                       events; rfmc_drawplan_kernel_ms returns {fill, classify + chain rounds, final
+ *                       pass, resolve} in milliseconds (measurement hooks of bench.py).               */
 #define RFMC_DRAW_MAX_PER_CLASS 4096
 /* t^(offset-1) mod phi (the characteristic polynomial of MT19937) as 624 words, bit i = coefficient
  * of t^i; and its host evaluation: the untempered window x[offset .. offset+623] of the stream whose
@@ -250,8 +253,8 @@ int rfmc_draw_plan_device(rfmc_dataset* ds, const uint32_t* key, int32_t pos, in
 int rfmc_drawplan_finish(rfmc_drawplan* pl, int32_t* feat_counts, uint32_t* key_end, int32_t* pos_end);
 int rfmc_drawplan_state_at(rfmc_drawplan* pl, int32_t slot, uint32_t* key, int32_t* pos);
 int rfmc_drawplan_indices(rfmc_drawplan* pl, int32_t slot0, int32_t n_slots, int32_t* idx_train, int32_t* idx_val);
-int rfmc_drawplan_info(rfmc_drawplan* pl, int64_t* words_generated, int64_t* words_consumed, int32_t* chunk_fallbacks,
-                       int32_t* launches);
+int rfmc_drawplan_info(rfmc_drawplan* pl, int64_t* words_generated, int64_t* words_consumed, int64_t* words_pending,
+                       int32_t* chunk_fallbacks, int32_t* launches);
 int rfmc_drawplan_timing(int enabled);
 int rfmc_drawplan_kernel_ms(rfmc_drawplan* pl, float* ms4);
 int rfmc_drawplan_destroy(rfmc_drawplan* pl);

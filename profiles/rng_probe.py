@@ -37,5 +37,5 @@ for per_class, n_train in ((20, 10), (2500, 2000)):
         gT, gV = plan.indices()
         ok = np.array_equal(gT, T) and np.array_equal(gV, V) and np.array_equal(counts, K) and np.array_equal(key_end, key) and pos_end == pos
         plan.close()
-        print(f"rows/class {per} per_class {per_class} slots {n_slots}: fill {ms[0]:.3f} walk {ms[1]:.3f} scan {ms[2]:.3f} prefix {ms[3]:.3f} ms"
-              f" | wall {wall*1e3:.2f} ms | host walk {host*1e3:.1f} ms | words {info['words_consumed']/1e6:.1f}M fallbacks {info['chunk_fallbacks']} | parity {ok}", flush=True)
+        print(f"rows/class {per} per_class {per_class} slots {n_slots}: fill {ms[0]:.3f} rounds {ms[1]:.3f} final {ms[2]:.3f} resolve {ms[3]:.3f} ms"
+              f" | wall {wall*1e3:.2f} ms | host walk {host*1e3:.1f} ms | words {info['words_consumed']/1e6:.1f}M pending {info['words_pending']/1e6:.1f}M launches {info['launches']} redone {info['chunk_fallbacks']} | parity {ok}", flush=True)

@@ -81,6 +81,14 @@ void plan_free_buffers(rfmc_drawplan* pl) {
     release(pl->d_slot_pos);
     release(pl->d_status);
     release(pl->d_key);
+    release(pl->d_k0);
+    release(pl->d_kpred);
+    release(pl->d_eband);
+    release(pl->d_hdr);
+    release(pl->d_pend);
+    pl->d_k0 = pl->d_kpred = nullptr;
+    pl->d_eband = nullptr;
+    pl->d_hdr = pl->d_pend = nullptr;
     pl->d_W = pl->d_A = pl->d_heads = nullptr;
     pl->d_idx_train = pl->d_idx_val = pl->d_randv = nullptr;
     pl->d_slot_pos = nullptr;
@@ -94,9 +102,17 @@ int plan_start(rfmc_drawplan* pl) {
     const int64_t words = drawplan_words_needed(ds->h_class_n, pl->n_slots, pl->n_cands, pl->rmask, pl->rrange, pl->attempt);
     drawplan_geometry(pl, words);
     RFMC_REQUIRE(poly_table(ds->device, drawplan_chunk_words(pl), pl->n_chunks, pl->stream, &pl->d_polys) == 0, "jump table failed");
-    int64_t a_per_slot = 0;
+    int64_t a_per_slot = 0;  // ordinals per slot: every class's shuffle steps, then the randint block
     for (int c = 0; c < C; ++c) a_per_slot += ds->h_class_n[c] > 1 ? ds->h_class_n[c] - 1 : 0;
+    if (pl->n_cands > 0 && pl->rrange != 0u) a_per_slot += pl->n_cands;
+    RFMC_REQUIRE(a_per_slot < 0x7fffffffll, "too many draws per slot");
     const size_t S = (size_t)pl->n_slots;
+    const size_t G = (size_t)pl->chunks_per_round;
+    RFMC_CUDA(dev_alloc((void**)&pl->d_k0, ((size_t)pl->n_walk_chunks + 1) * 8));
+    RFMC_CUDA(dev_alloc((void**)&pl->d_kpred, (G + 1) * 8));
+    RFMC_CUDA(dev_alloc((void**)&pl->d_eband, G * 4));
+    RFMC_CUDA(dev_alloc(&pl->d_hdr, G * 8));
+    RFMC_CUDA(dev_alloc(&pl->d_pend, G * 4096 * 8));
     RFMC_CUDA(dev_alloc((void**)&pl->d_key, MT_N * 4));
     RFMC_CUDA(dev_alloc((void**)&pl->d_W, (size_t)pl->n_blocks * MT_N * 4));
     RFMC_CUDA(dev_alloc((void**)&pl->d_A, (S * (size_t)a_per_slot + 1) * 4));
@@ -200,12 +216,13 @@ int rfmc_drawplan_finish(rfmc_drawplan* pl, int32_t* feat_counts, uint32_t* key_
     RFMC_REQUIRE(pl != nullptr, "plan is NULL");
     RFMC_CUDA(cudaSetDevice(pl->ds->device));
     for (;;) {
-        RFMC_CUDA(cudaMemcpyAsync(pl->h_status, pl->d_status, 16, cudaMemcpyDeviceToHost, pl->stream));
+        RFMC_CUDA(cudaMemcpyAsync(pl->h_status, pl->d_status, 32, cudaMemcpyDeviceToHost, pl->stream));
         pl->h_slot_pos.resize((size_t)pl->n_slots + 1);
         RFMC_CUDA(cudaMemcpyAsync(pl->h_slot_pos.data(), pl->d_slot_pos, ((size_t)pl->n_slots + 1) * 8, cudaMemcpyDeviceToHost, pl->stream));
         RFMC_CUDA(cudaStreamSynchronize(pl->stream));
-        RFMC_REQUIRE(pl->h_status[2] == 0, "device draw: late list overflow");
-        if (pl->h_status[0] == 0) break;
+        RFMC_REQUIRE(pl->h_status[2] == 0, "device draw: resolve scratch overflow");
+        RFMC_REQUIRE(pl->h_status[3] == 0, "device draw: the final pass and the chain disagree on a chunk's accept count");
+        if (pl->h_slot_pos[(size_t)pl->n_slots] >= 0) break;
         // the generated stretch of the stream was too short (beyond 8 sigma): redo the plan with a longer one
         RFMC_REQUIRE(pl->attempt < 3, "device draw: stream words exhausted");
         pl->attempt += 1;
@@ -215,8 +232,15 @@ int rfmc_drawplan_finish(rfmc_drawplan* pl, int32_t* feat_counts, uint32_t* key_
     pl->finished = true;
     if (feat_counts && pl->n_cands > 0) {
         const size_t n = (size_t)pl->n_slots * pl->n_cands;
-        RFMC_CUDA(cudaMemcpy(feat_counts, pl->d_randv, n * 4, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; ++i) feat_counts[i] = (int32_t)(pl->randint_low + (int64_t)feat_counts[i]);
+        if (pl->rrange == 0u) {
+            for (size_t i = 0; i < n; ++i) feat_counts[i] = (int32_t)pl->randint_low;  // randint over one value draws nothing
+        } else {
+            // the randint block closes every slot's stretch of A
+            const size_t stride = (size_t)pl->steps_per_slot;
+            RFMC_CUDA(cudaMemcpy2D(feat_counts, (size_t)pl->n_cands * 4, pl->d_A + (stride - (size_t)pl->n_cands), stride * 4,
+                                   (size_t)pl->n_cands * 4, (size_t)pl->n_slots, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) feat_counts[i] = (int32_t)(pl->randint_low + (int64_t)feat_counts[i]);
+        }
     }
     if (key_end && pos_end) return rfmc_drawplan_state_at(pl, pl->n_slots, key_end, pos_end);
     return 0;
@@ -264,28 +288,22 @@ int rfmc_drawplan_draws(rfmc_drawplan* pl, int32_t slot, int32_t cls, uint32_t* 
     RFMC_REQUIRE(pl != nullptr && pl->finished && out != nullptr, "plan is NULL or not finished");
     RFMC_REQUIRE(slot >= 0 && slot < pl->n_slots && cls >= 0 && cls < pl->n_classes, "out of range");
     RFMC_CUDA(cudaSetDevice(pl->ds->device));
-    int64_t per_slot = 0, off = 0;
-    for (int c = 0; c < pl->n_classes; ++c) {
-        const int64_t m = pl->ds->h_class_n[c] > 1 ? pl->ds->h_class_n[c] - 1 : 0;
-        if (c < cls) off += m;
-        per_slot += m;
-    }
+    int64_t off = 0;
+    const int64_t per_slot = pl->steps_per_slot;
+    for (int c = 0; c < cls; ++c) off += pl->ds->h_class_n[c] > 1 ? pl->ds->h_class_n[c] - 1 : 0;
     const int64_t m = pl->ds->h_class_n[cls] > 1 ? pl->ds->h_class_n[cls] - 1 : 0;
     if (m) RFMC_CUDA(cudaMemcpy(out, pl->d_A + (size_t)slot * per_slot + off, (size_t)m * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
-int rfmc_drawplan_info(rfmc_drawplan* pl, int64_t* words_generated, int64_t* words_consumed, int32_t* chunk_fallbacks,
-                       int32_t* launches) {
+int rfmc_drawplan_info(rfmc_drawplan* pl, int64_t* words_generated, int64_t* words_consumed, int64_t* words_pending,
+                       int32_t* chunk_fallbacks, int32_t* launches) {
+    // chunk_fallbacks: chunks the final pass redid with every word pending (its tight band missed)
     RFMC_REQUIRE(pl != nullptr && pl->finished, "plan is NULL or not finished");
     if (words_generated) *words_generated = pl->n_blocks * MT_N;
     if (words_consumed) *words_consumed = pl->h_slot_pos[(size_t)pl->n_slots] - pl->pos0;
+    if (words_pending) *words_pending = (int64_t)pl->h_status[4] << 10;
     if (chunk_fallbacks) *chunk_fallbacks = pl->h_status[1];
-    if (getenv("RFMC_DBG_STATUS")) {
-        int dbg[64];
-        cudaMemcpy(dbg, pl->d_status, 256, cudaMemcpyDeviceToHost);
-        for (int i = 8; i < 16; ++i) fprintf(stderr, "status[%d]=%d\n", i, dbg[i]);
-    }
     if (launches) *launches = pl->launches * (pl->attempt + 1);
     return 0;
 }

@@ -111,8 +111,11 @@ struct rfmc_drawplan {
     uint32_t rmask = 0, rrange = 0;
     int cap_log2 = 10;
     int attempt = 0;
-    int64_t n_blocks = 0, n_chunks = 0;
+    int64_t n_blocks = 0, n_chunks = 0;  // MT19937 blocks generated, fill CTAs
     int blocks_per_chunk = 0;
+    int64_t n_walk_chunks = 0;           // 4,096-word chunks of the walk
+    int chunks_per_round = 128;
+    int64_t steps_per_slot = 0;
     int launches = 0;
     bool finished = false;
     uint32_t h_key[624];
@@ -124,10 +127,15 @@ struct rfmc_drawplan {
     int32_t* d_idx_train = nullptr;
     int32_t* d_idx_val = nullptr;
     int32_t* d_randv = nullptr;
+    int64_t* d_k0 = nullptr;
+    int64_t* d_kpred = nullptr;
+    int32_t* d_eband = nullptr;
+    void* d_hdr = nullptr;
+    void* d_pend = nullptr;
     int64_t* d_slot_pos = nullptr;
     int32_t* d_status = nullptr;
     std::vector<int64_t> h_slot_pos;
-    int32_t h_status[4] = {0, 0, 0, 0};
+    int32_t h_status[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // measurement hook
     bool timing = false;
 };

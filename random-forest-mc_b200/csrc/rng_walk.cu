@@ -8,23 +8,21 @@
 //   shuffle: for i = n-1 .. 1: j_i = random_interval(i); swap(x[i], x[j_i])
 //   random_interval(i): mask = smallest 2^k - 1 >= i; draw 32-bit words until (word & mask) <= i
 //
-// Four kernels per plan of slots, all on one CUDA stream:
+// The kernels of one plan of slots, all on one CUDA stream:
 //
 //   mt_fill_kernel      the stream's tempered words W[0 .. L) into HBM.  One CTA per chunk of
 //                       1680 blocks of 624 words; chunk c jumps straight to word c*J: the window
 //                       x[cJ .. cJ+623] is a GF(2) correlation of the first 19936+624 words of the
 //                       sequence with the polynomial t^(cJ-1) mod phi (mt_jump.cpp), then blocks are
 //                       regenerated in three dependent phases of 227 / 227 / 170 lanes.
-//   walk_kernel         the masked rejection walk: which word feeds which Fisher-Yates step.  This is
-//                       the sequential chain of the stream (a word is accepted iff (w & mask) <= i, and
-//                       i falls by one per accept), executed by ONE CTA in chunks of up to 8,192 words:
-//                       every thread decides its words against the EXPECTED number of earlier accepts
-//                       +- a 7.5 sigma band; words outside the band are certain, the few inside
-//                       (~0.2 % at the top level) are resolved exactly by one warp with a ballot
-//                       fix-point over the exact prefix counts; every certain decision is then verified
-//                       against the exact count (a violated band reruns the chunk on the exact warp
-//                       path), so the result is exact, never statistical.  Accepted draws are
-//                       written compacted: A[k] = j_(n-1-k).
+//   classify / chain / final   the masked rejection walk: which word feeds which Fisher-Yates step.  A
+//                       word is accepted iff (w & mask) <= i, and i falls by one per accept: sequential
+//                       only through the running count of accepts.  All per-word work runs GPU-wide in
+//                       chunks of 4,096 words decided against a band around the EXPECTED count; one warp
+//                       per stream settles the few undecided words exactly, in order; a last pass with
+//                       exact counts at both ends of every chunk writes the draws A[k] = j_(n-1-k) and
+//                       verifies every decision (see the section comment below): exact, never
+//                       statistical.
 //   resolve_scan_kernel one CTA per (slot, class): only the first N entries of the permutation are
 //                       needed.  Steps i >= N touch prefix position p only through chains
 //                       p -> (first i with j_i == p) -> ...; one ascending scan over the draws with the
@@ -141,118 +139,178 @@ __global__ void __launch_bounds__(FILL_THREADS) mt_fill_kernel(const uint32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// walk_kernel
+// The rejection walk: which word of the stream feeds which draw.
+//
+// Every accepted word gets an ORDINAL k (0, 1, 2, ... over the whole plan); what an ordinal needs is
+// fixed in advance (the schedule below: per slot the classes' shuffle steps i = n-1 .. 1, then the
+// randint draws), so the walk is the recurrence  k(p+1) = k(p) + [word p is accepted at ordinal k(p)].
+// It is sequential only through k.  The stream is cut into chunks of 4,096 words and worked in rounds:
+//
+//   classify_kernel  one CTA per chunk, a whole round of chunks at once.  The chain (below) predicts
+//                    the ordinal of every chunk boundary from the schedule (expected acceptance rates)
+//                    with a 7.5 sigma band.  A word whose verdict is the same for every ordinal of its
+//                    band is CERTAIN (counted with ballots); the rest are PENDING and leave as
+//                    (word, position, certain accepts before it).
+//   chain_kernel     one warp per stream: walks the round's chunks in order and settles the pending
+//                    words exactly (32 at a time, ballot fix-point over the exact ordinals) -> the exact
+//                    ordinal at every chunk boundary; then predicts the next round's boundaries.
+//   final_kernel     one CTA per chunk, all chunks at once: with the exact ordinal at both ends of its
+//                    chunk it decides every word again against a tight band, settles its own pending
+//                    words, checks EVERY word's exact ordinal against the band it was decided with (a
+//                    miss redoes the chunk with all words pending), writes the accepted draws
+//                    A[k] = word & mask and the stream position of every slot boundary, and compares its
+//                    count with the chain's.  A chunk whose count differs from the chain's fails the
+//                    plan loudly (status), so a band that was too narrow in classify_kernel can cost
+//                    time but never a wrong draw.
 // ------------------------------------------------------------------------------------------------
-constexpr int WK_THREADS = 1024;
-constexpr int WK_ROWS = 8;        // words per thread of the widest chunk
-constexpr int WK_AMB_MAX = 3072;  // undecided words one chunk may hold before it falls to the warp path
+constexpr int CH_WORDS = 4096;   // words per chunk
+constexpr int CH_THREADS = 512;  // 8 words per thread
+constexpr int CH_ROWS = CH_WORDS / CH_THREADS;
+constexpr int CH_SEGS = CH_WORDS / 32;
+constexpr int SCHED_MAX_ENT = RFMC_MAX_CLASSES + 1;
 
-struct WalkArgs {
-    const uint32_t* W;
-    int64_t n_words;
-    int32_t pos0;
-    int32_t n_slots, n_classes, n_cands;
-    const int32_t* class_n;     // [n_classes]
-    const int64_t* class_aoff;  // [n_classes + 1] offsets of each class's draws inside a slot's segment of A
-    uint32_t rmask, rrange;     // randint: accept iff (w & rmask) <= rrange; rrange == 0: no draw
-    uint32_t* A;
-    int32_t* randv;     // [n_slots][n_cands] accepted randint offsets
-    int64_t* slot_pos;  // [n_slots + 1] stream position before each slot; [n_slots] = after the plan
-    int32_t* status;    // 0 ok, 1 words exhausted; status[1] = chunks that fell back to the warp path
+struct Sched {
+    int32_t n_ent;                   // draws-with-steps per slot: classes with n >= 2, then the randint block
+    int32_t steps;                   // ordinals per slot
+    int32_t ks[SCHED_MAX_ENT + 1];   // first ordinal of entity e inside a slot; ks[n_ent] = steps
+    int32_t nn[SCHED_MAX_ENT];       // class size n of a shuffle entity; 0 = the randint block
+    uint32_t rmask, rrange;
+    int64_t k_total;                 // n_slots * steps
 };
 
-struct WalkShared {
-    uint32_t seg[32 * WK_ROWS];  // per 32-word segment: certain accepts | undecided << 16, then their exclusive prefix
-    uint32_t amb_u[WK_AMB_MAX];
-    uint16_t amb_s[WK_AMB_MAX];    // certain accepts before the undecided word
-    uint16_t amb_res[WK_AMB_MAX];  // undecided accepts before it | its own decision << 15
-    uint32_t tot, amb_acc;
-    int32_t cut;
-    // state hand-off of the warp path
-    int64_t p;
-    int32_t i;
-    int32_t done;
-};
-
-// Exact warp path: 32 words per round.  thr falls by `dec` per accept (1: shuffle step, 0: randint).
-// Stops when `need` draws are accepted, `max_words` are consumed or the words run out.
-__device__ void warp_walk(const uint32_t* __restrict__ W, int64_t n_words, int64_t& p, uint32_t M, int32_t& thr, int dec,
-                          int32_t& need, uint32_t* __restrict__ out, int64_t max_words, bool& exhausted) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt = lanemask_lt();
-    while (need > 0 && max_words > 0) {
-        if (p + 32 > n_words) {
-            exhausted = true;
-            return;
-        }
-        const uint32_t u = __ldg(&W[p + lane]) & M;
-        uint32_t b = __ballot_sync(FULL, (int32_t)u <= thr);
-        if (dec) {
-            for (;;) {  // lane l is exact once lanes < l are: at most 32 rounds, usually 2
-                const int c = __popc(b & lt);
-                const uint32_t nb = __ballot_sync(FULL, (int32_t)u <= thr - c);
-                if (nb == b) break;
-                b = nb;
-            }
-        }
-        int consumed = 32;
-        if (max_words < 32) {
-            consumed = (int)max_words;
-            b &= (1u << consumed) - 1u;
-        }
-        int n_acc = __popc(b);
-        if (n_acc >= need) {
-            const int cutl = (int)__fns(b, 0, need);  // lane of the need-th accept
-            b &= (2u << cutl) - 1u;
-            consumed = cutl + 1;
-            n_acc = need;
-        }
-        if ((b >> lane) & 1u) out[__popc(b & lt)] = u;
-        out += n_acc;
-        p += consumed;
-        max_words -= consumed;
-        thr -= dec * n_acc;
-        need -= n_acc;
-    }
+__device__ __forceinline__ int ent_of(const Sched& sc, int32_t kr, int e) {
+    while (kr >= sc.ks[e + 1]) ++e;
+    while (kr < sc.ks[e]) --e;
+    return e;
 }
 
-// One chunk of V * 1024 words inside one mask level.  Returns false when the chunk has to be redone
-// on the warp path (band violated or too many undecided words); then nothing may be committed.
-template <int V>
-__device__ __forceinline__ bool chunk_step(WalkShared& sh, const uint32_t (&w)[WK_ROWS], uint32_t M, int32_t i, int32_t need,
-                                           uint32_t* __restrict__ out, int& accepted, int& consumed) {
+__device__ __forceinline__ int32_t wrap_slot(const Sched& sc, int32_t kr) {
+    while (kr >= sc.steps) kr -= sc.steps;
+    while (kr < 0) kr += sc.steps;
+    return kr;
+}
+
+// Is word w accepted at slot-relative ordinal kr?  u = the draw it would deliver.
+__device__ __forceinline__ bool accept_at(const Sched& sc, uint32_t w, int32_t kr, int& e, uint32_t& u) {
+    e = ent_of(sc, kr, e);
+    const int32_t n = sc.nn[e];
+    if (n == 0) {
+        u = w & sc.rmask;
+        return u <= sc.rrange;
+    }
+    const int32_t i = n - 1 - (kr - sc.ks[e]);  // >= 1
+    const uint32_t M = 0xFFFFFFFFu >> __clz(i);
+    u = w & M;
+    return u <= (uint32_t)i;
+}
+
+// Verdict of word w over every ordinal of [klo, klo + span] (slot-relative, periodic in the slot):
+// bit 0 = accepted at all of them, bit 1 = rejected at all of them.  Inside one mask level the test
+// u <= i is monotone in the ordinal, so a level segment is settled by its two ends.
+__device__ __forceinline__ int band_verdict(const Sched& sc, uint32_t w, int32_t klo, int32_t span, int e_hint) {
+    int32_t k = wrap_slot(sc, klo);
+    int e = ent_of(sc, k, e_hint);
+    int32_t rem = span + 1;
+    bool all_acc = true, all_rej = true;
+    for (int it = 0; it < 40; ++it) {
+        const int32_t n = sc.nn[e];
+        int32_t cnt;
+        if (n == 0) {
+            cnt = sc.ks[e + 1] - k;
+            const bool acc = (w & sc.rmask) <= sc.rrange;
+            all_acc &= acc;
+            all_rej &= !acc;
+        } else {
+            const int32_t i_hi = n - 1 - (k - sc.ks[e]);
+            const uint32_t M = 0xFFFFFFFFu >> __clz(i_hi);
+            cnt = i_hi - (int32_t)(M >> 1);  // ordinals left in this level
+            cnt = cnt < rem ? cnt : rem;
+            const uint32_t u = w & M;
+            all_acc &= u <= (uint32_t)(i_hi - (cnt - 1));
+            all_rej &= u > (uint32_t)i_hi;
+        }
+        cnt = cnt < rem ? cnt : rem;
+        rem -= cnt;
+        if (rem <= 0) return (all_acc ? 1 : 0) | (all_rej ? 2 : 0);
+        if (!(all_acc || all_rej)) return 0;
+        k += cnt;
+        if (k >= sc.ks[e + 1]) {
+            ++e;
+            if (e == sc.n_ent) {
+                e = 0;
+                k = 0;
+            }
+        }
+    }
+    return 0;  // a band across more than 40 level segments: leave the word pending
+}
+
+struct ChunkHdr {
+    int32_t n_sure, n_pend;
+};
+
+struct WalkBuffers {
+    const uint32_t* W;     // tempered words; chunk c = W[pos0 + c * 4096 ...]
+    int64_t n_words;
+    int32_t pos0;
+    int32_t chunks_per_round;
+    int64_t n_chunks;      // chunks of the whole plan
+    int64_t* k0;           // [n_chunks + 1] exact ordinal at every chunk boundary (chain_kernel)
+    int64_t* kpred;        // [chunks_per_round + 1] predicted boundaries of the round being classified
+    int32_t* eband;        // [chunks_per_round] half-width of the band
+    ChunkHdr* hdr;         // [chunks_per_round]
+    uint2* pend;           // [chunks_per_round][4096] {word, position | certain accepts before << 16}
+    uint32_t* A;           // accepted draws by ordinal
+    int64_t* slot_pos;     // [n_slots + 1]
+    int32_t* status;       // [3] != 0: a chunk's count differed from the chain's; [1] chunks redone all-pending
+};
+
+// Decide the CTA's 4,096 words against bands [kr0 + dk(q) - E(q), .. + E(q)], dk linear from 0 to dk_end.
+// Certain accepts are counted, pending words compacted in stream order.  Leaves per-thread ballots and
+// the segments' exclusive prefixes in shared memory for the caller.
+struct ChunkShared {
+    uint32_t seg[CH_SEGS];
+    uint32_t tot;
+};
+
+template <bool TIGHT>
+__device__ __forceinline__ void classify_words(const Sched& sc, ChunkShared& sh, const uint32_t (&w)[CH_ROWS], int32_t kr0,
+                                               int32_t dk_end, int32_t e_band, bool all_pending, int e_hint,
+                                               uint32_t (&bs)[CH_ROWS], uint32_t (&ba)[CH_ROWS], int32_t (&klo)[CH_ROWS],
+                                               int32_t (&khi)[CH_ROWS]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = lanemask_lt();
-    const float invM = 1.0f / ((float)M + 1.0f);
-    const float ip1 = (float)i + 1.0f;
-    float re = (ip1 - (float)(V * WK_THREADS)) * invM;  // acceptance probability at the chunk's end (>= 1/2 inside a level)
-    re = fminf(fmaxf(re, 0.5f), 1.0f);
-    const float vr = re * (1.0f - re);
-    uint32_t u[V], bs[V], ba[V];
-    int klo[V], khi[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const int q = v * WK_THREADS + tid;
-        u[v] = w[v] & M;
-        const float kp = ip1 * (-expm1f(-(float)q * invM));  // expected accepts before word q
-        const float E = 6.0f + 7.5f * sqrtf((float)q * vr + 1.0f);
-        int lo_k = (int)floorf(kp - E), hi_k = (int)ceilf(kp + E);
-        lo_k = lo_k < 0 ? 0 : lo_k;
-        hi_k = hi_k > q ? q : hi_k;
+    for (int v = 0; v < CH_ROWS; ++v) {
+        const int q = v * CH_THREADS + tid;
+        const int32_t dk = (int32_t)(((int64_t)dk_end * q) >> 12);
+        int32_t E = e_band;
+        if (TIGHT) {  // both ends of the chunk are exact: the walk is a bridge, widest in the middle
+            const int m = q < CH_WORDS - q ? q : CH_WORDS - q;
+            E += (int32_t)(7.5f * 0.5f * sqrtf((float)m)) + 1;
+        }
+        int32_t lo_k = dk - E, hi_k = dk + E;
+        if (TIGHT) {  // exact start: between none and q accepts before word q, at most dk_end in the whole chunk
+            lo_k = lo_k < 0 ? 0 : lo_k;
+            hi_k = hi_k > q ? q : hi_k;
+            hi_k = hi_k > dk_end ? dk_end : hi_k;
+            const int32_t floor_k = dk_end - (CH_WORDS - q);
+            lo_k = lo_k < floor_k ? floor_k : lo_k;
+        }
         klo[v] = lo_k;
         khi[v] = hi_k;
-        const bool sure_acc = (int32_t)u[v] <= i - hi_k;
-        const bool sure_rej = (int32_t)u[v] > i - lo_k;
-        bs[v] = __ballot_sync(FULL, sure_acc);
-        ba[v] = __ballot_sync(FULL, !sure_acc && !sure_rej);
-        if (lane == 0) sh.seg[v * 32 + warp] = (uint32_t)__popc(bs[v]) | ((uint32_t)__popc(ba[v]) << 16);
+        int verdict = 0;
+        if (!all_pending && hi_k >= lo_k) verdict = band_verdict(sc, w[v], kr0 + lo_k, hi_k - lo_k, e_hint);
+        bs[v] = __ballot_sync(FULL, verdict == 1);
+        ba[v] = __ballot_sync(FULL, verdict == 0);
+        if (lane == 0) sh.seg[v * (CH_THREADS / 32) + warp] = (uint32_t)__popc(bs[v]) | ((uint32_t)__popc(ba[v]) << 16);
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan of the 32 * V segment counts (both 16-bit fields at once)
-        uint32_t x[V], s = 0;
+    if (warp == 0) {  // exclusive scan of the 128 segment counts (both 16-bit fields at once)
+        constexpr int PER = CH_SEGS / 32;
+        uint32_t x[PER], s = 0;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            x[e] = sh.seg[lane * V + e];
+        for (int e = 0; e < PER; ++e) {
+            x[e] = sh.seg[lane * PER + e];
             s += x[e];
         }
         uint32_t inc = s;
@@ -263,200 +321,405 @@ __device__ __forceinline__ bool chunk_step(WalkShared& sh, const uint32_t (&w)[W
         }
         uint32_t run = inc - s;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            sh.seg[lane * V + e] = run;
+        for (int e = 0; e < PER; ++e) {
+            sh.seg[lane * PER + e] = run;
             run += x[e];
         }
         if (lane == 31) sh.tot = inc;
     }
     __syncthreads();
-    const uint32_t tot = sh.tot;
-    const int n_amb = (int)(tot >> 16), n_sure = (int)(tot & 0xFFFFu);
-    const bool overflow = n_amb > WK_AMB_MAX;
-    if (!overflow) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if ((ba[v] >> lane) & 1u) {
-                const uint32_t pre = sh.seg[v * 32 + warp];
-                const int e = (int)(pre >> 16) + __popc(ba[v] & lt);
-                sh.amb_u[e] = u[v];
-                sh.amb_s[e] = (uint16_t)((pre & 0xFFFFu) + (uint32_t)__popc(bs[v] & lt));
-            }
-        }
-    }
-    __syncthreads();
-    if (warp == 0 && !overflow) {  // the undecided words, in stream order, against the exact counts
-        int D = 0;
-        for (int base = 0; base < n_amb; base += 32) {
-            const int e = base + lane;
-            const bool valid = e < n_amb;
-            const int32_t uu = valid ? (int32_t)sh.amb_u[e] : 0;
-            const int32_t ss = valid ? (int32_t)sh.amb_s[e] + D : 0;
-            uint32_t b = __ballot_sync(FULL, valid && uu <= i - ss);
-            for (;;) {
-                const int c = __popc(b & lt);
-                const uint32_t nb = __ballot_sync(FULL, valid && uu <= i - ss - c);
-                if (nb == b) break;
-                b = nb;
-            }
-            if (valid) sh.amb_res[e] = (uint16_t)((uint32_t)(D + __popc(b & lt)) | (((b >> lane) & 1u) << 15));
-            D += __popc(b);
-        }
-        if (lane == 0) sh.amb_acc = (uint32_t)D;
-    }
-    __syncthreads();
-    bool viol = overflow;
-    const int amb_acc = (int)sh.amb_acc;
-    if (!overflow) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const uint32_t pre = sh.seg[v * 32 + warp];
-            const int a_idx = (int)(pre >> 16) + __popc(ba[v] & lt);
-            const uint32_t res = a_idx < n_amb ? sh.amb_res[a_idx] : (uint32_t)amb_acc;
-            const int k = (int)(pre & 0xFFFFu) + __popc(bs[v] & lt) + (int)(res & 0x7FFFu);  // exact accepts before this word
-            const bool is_amb = (ba[v] >> lane) & 1u;
-            const bool acc = is_amb ? ((res >> 15) & 1u) : ((bs[v] >> lane) & 1u);
-            if (k < need) {
-                if (k < klo[v] || k > khi[v]) viol = true;
-                if (acc) {
-                    out[k] = u[v];
-                    if (k == need - 1) sh.cut = v * WK_THREADS + tid;
-                }
-            }
-        }
-    }
-    if (__syncthreads_or(viol)) return false;
-    const int total = n_sure + amb_acc;
-    if (total >= need) {
-        accepted = need;
-        consumed = sh.cut + 1;
-    } else {
-        accepted = total;
-        consumed = V * WK_THREADS;
-    }
-    return true;
 }
 
-__global__ void __launch_bounds__(WK_THREADS, 1) walk_kernel(WalkArgs a) {
-    __shared__ WalkShared sh;
-    const int tid = threadIdx.x;
-    const uint32_t* __restrict__ W = a.W;
-    int64_t p = a.pos0;
-    int fallbacks = 0;
-    // one chunk of prefetched words: pf[v] = W[pf_p + v * 1024 + tid]
-    uint32_t pf[WK_ROWS];
-    int64_t pf_p = -1;
-    auto prefetch = [&](int64_t at) {
-        pf_p = at;
+__device__ __forceinline__ void load_chunk(const WalkBuffers& b, int64_t chunk, uint32_t (&w)[CH_ROWS]) {
+    const int64_t base = b.pos0 + chunk * CH_WORDS;
 #pragma unroll
-        for (int v = 0; v < WK_ROWS; ++v) {
-            const int64_t q = at + v * WK_THREADS + tid;
-            pf[v] = q < a.n_words ? __ldg(&W[q]) : 0u;
-        }
-    };
-    const int64_t slot_stride = a.class_aoff[a.n_classes];
-    for (int s = 0; s < a.n_slots; ++s) {
-        if (tid == 0) a.slot_pos[s] = p;
-        for (int c = 0; c < a.n_classes; ++c) {
-            const int32_t n = a.class_n[c];
-            if (n < 2) continue;
-            uint32_t* out = a.A + (size_t)s * slot_stride + a.class_aoff[c];
-            uint32_t M = (uint32_t)(n - 1);
-            M |= M >> 1;
-            M |= M >> 2;
-            M |= M >> 4;
-            M |= M >> 8;
-            M |= M >> 16;
-            int32_t i = n - 1;
-            while (i >= 1) {
-                const int32_t lo = (int32_t)(M >> 1);
-                while (i > lo) {
-                    const int need = i - lo;
-                    const int V = M >= 32767u ? 8 : (M >= 16383u ? 4 : (M >= 8191u ? 2 : (M >= 1023u ? 1 : 0)));
-                    bool done = false;
-                    if (V > 0 && p + V * WK_THREADS <= a.n_words) {
-                        uint32_t w[WK_ROWS];
-                        if (pf_p != p) prefetch(p);
+    for (int v = 0; v < CH_ROWS; ++v) {
+        const int64_t p = base + v * CH_THREADS + threadIdx.x;
+        w[v] = p < b.n_words ? __ldg(&b.W[p]) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS) classify_kernel(const __grid_constant__ Sched sc, WalkBuffers b, int64_t chunk0) {
+    __shared__ ChunkShared sh;
+    const int g = blockIdx.x;
+    const int64_t chunk = chunk0 + g;
+    if (chunk >= b.n_chunks) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t w[CH_ROWS], bs[CH_ROWS], ba[CH_ROWS];
+    int32_t klo[CH_ROWS], khi[CH_ROWS];
+    load_chunk(b, chunk, w);
+    const int64_t ks = b.kpred[g], ke = b.kpred[g + 1];
+    const int32_t kr0 = (int32_t)(ks % sc.steps);
+    const int e_hint = ent_of(sc, kr0, 0);
+    classify_words<false>(sc, sh, w, kr0, (int32_t)(ke - ks), b.eband[g], false, e_hint, bs, ba, klo, khi);
+    const uint32_t tot = sh.tot;
+    if (tid == 0) b.hdr[g] = ChunkHdr{(int32_t)(tot & 0xFFFFu), (int32_t)(tot >> 16)};
+    uint2* out = b.pend + (size_t)g * CH_WORDS;
 #pragma unroll
-                        for (int v = 0; v < WK_ROWS; ++v) w[v] = pf[v];
-                        prefetch(p + V * WK_THREADS);
-                        int accepted = 0, consumed = 0;
-                        bool ok;
-                        if (V == 8)
-                            ok = chunk_step<8>(sh, w, M, i, need, out, accepted, consumed);
-                        else if (V == 4)
-                            ok = chunk_step<4>(sh, w, M, i, need, out, accepted, consumed);
-                        else if (V == 2)
-                            ok = chunk_step<2>(sh, w, M, i, need, out, accepted, consumed);
-                        else
-                            ok = chunk_step<1>(sh, w, M, i, need, out, accepted, consumed);
-                        if (ok) {
-                            p += consumed;
-                            i -= accepted;
-                            out += accepted;
-                            done = true;
-                        } else {
-                            ++fallbacks;
-                        }
-                    }
-                    if (!done) {
-                        // exact warp path: the low levels, the tail of the words, and chunks whose band failed
-                        if (tid < 32) {
-                            int64_t pp = p;
-                            int32_t thr = i, nd = need;
-                            bool ex = false;
-                            warp_walk(W, a.n_words, pp, M, thr, 1, nd, out, V > 0 ? (int64_t)V * WK_THREADS : (int64_t)1 << 40, ex);
-                            if (tid == 0) {
-                                sh.p = pp;
-                                sh.i = thr;
-                                sh.done = ex ? 1 : 0;
-                            }
-                        }
-                        __syncthreads();
-                        const int64_t np_ = sh.p;
-                        const int32_t ni = sh.i;
-                        const int ex = sh.done;
-                        __syncthreads();
-                        out += i - ni;
-                        p = np_;
-                        i = ni;
-                        if (ex) {
-                            if (tid == 0) a.status[0] = 1;
-                            return;
-                        }
-                    }
-                }
-                M >>= 1;
-            }
-        }
-        if (a.n_cands > 0) {
-            if (a.rrange == 0u) {
-                for (int k = tid; k < a.n_cands; k += WK_THREADS) a.randv[(size_t)s * a.n_cands + k] = 0;
-            } else {
-                if (tid < 32) {
-                    int64_t pp = p;
-                    int32_t thr = (int32_t)a.rrange, nd = a.n_cands;
-                    bool ex = false;
-                    warp_walk(W, a.n_words, pp, a.rmask, thr, 0, nd, (uint32_t*)(a.randv + (size_t)s * a.n_cands), (int64_t)1 << 40, ex);
-                    if (tid == 0) {
-                        sh.p = pp;
-                        sh.done = ex ? 1 : 0;
-                    }
-                }
-                __syncthreads();
-                p = sh.p;
-                const int ex = sh.done;
-                __syncthreads();
-                if (ex) {
-                    if (tid == 0) a.status[0] = 1;
-                    return;
-                }
-            }
+    for (int v = 0; v < CH_ROWS; ++v) {
+        if ((ba[v] >> lane) & 1u) {
+            const uint32_t pre = sh.seg[v * (CH_THREADS / 32) + warp];
+            const uint32_t e = (pre >> 16) + (uint32_t)__popc(ba[v] & lt);
+            const uint32_t sure_before = (pre & 0xFFFFu) + (uint32_t)__popc(bs[v] & lt);
+            // first guess for the chain: the verdict at the predicted ordinal itself
+            const int q = v * CH_THREADS + tid;
+            int ent = e_hint;
+            uint32_t u;
+            const uint32_t guess = accept_at(sc, w[v], wrap_slot(sc, kr0 + (int32_t)(((int64_t)(ke - ks) * q) >> 12)), ent, u) ? 1u : 0u;
+            out[e] = make_uint2(w[v], (uint32_t)q | (sure_before << 16) | (guess << 31));
         }
     }
-    if (tid == 0) {
-        a.slot_pos[a.n_slots] = p;
-        a.status[1] = fallbacks;
+}
+
+// Settle a list of pending words in stream order, one warp, 32 at a time.  fetch(e) -> {word, certain
+// accepts before it}; kr0 = slot-relative ordinal at the chunk's start.  Returns the accepts among them;
+// res(e, accepted pending before e, own verdict) is told every word's outcome.
+template <typename Fetch, typename Store>
+__device__ __forceinline__ int settle_pending(const Sched& sc, int n_pend, int32_t kr0, int e_hint, Fetch fetch, Store store) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    int D = 0;
+    uint2 nxt = lane < n_pend ? fetch(lane) : make_uint2(0u, 0u);
+    for (int base = 0; base < n_pend; base += 32) {
+        const int e = base + lane;
+        const bool valid = e < n_pend;
+        const uint2 cur = nxt;
+        if (e + 32 < n_pend) nxt = fetch(e + 32);
+        const int32_t k_base = kr0 + (int32_t)cur.y + D;  // ordinal if no pending word of this group before it is accepted
+        int ent = e_hint;
+        uint32_t u;
+        uint32_t bits = __ballot_sync(FULL, valid && accept_at(sc, cur.x, wrap_slot(sc, k_base), ent, u));
+        for (;;) {  // lane l is final once the lanes below it are: at most 32 rounds, usually 2
+            const int c = __popc(bits & lt);
+            const uint32_t nb = __ballot_sync(FULL, valid && accept_at(sc, cur.x, wrap_slot(sc, k_base + c), ent, u));
+            if (nb == bits) break;
+            bits = nb;
+        }
+        if (valid) store(e, D + __popc(bits & lt), (bits >> lane) & 1u);
+        D += __popc(bits);
+    }
+    return D;
+}
+
+// Expected walk from slot-relative ordinal kr0 over `words` words (the words may run through several
+// mask levels, classes and slots): the expected number of accepts, and the variance of that count.
+// Single precision is enough: the band built from it only decides how many words stay pending.
+__device__ void predict_span(const Sched& sc, int32_t kr0, float words, double& dk_out, float& var_out) {
+    double kr = (double)kr0, dk = 0.0;
+    float var = 0.0f;
+    int e = ent_of(sc, kr0, 0);
+    for (int guard = 0; guard < 4096 && words > 0.0f; ++guard) {
+        if (kr >= (double)sc.steps) {
+            kr -= (double)sc.steps;
+            e = 0;
+        }
+        const int32_t ki = (int32_t)kr;
+        e = ent_of(sc, ki, e);
+        const int32_t n = sc.nn[e];
+        if (n == 0) {
+            const float p = ((float)sc.rrange + 1.0f) / ((float)sc.rmask + 1.0f);
+            const float left = (float)((double)sc.ks[e + 1] - kr);
+            const float need = left / p;
+            const bool stays = words < need;
+            const float use = stays ? words : need;
+            const double adv = stays ? (double)(use * p) : (double)sc.ks[e + 1] - kr;
+            kr += adv;
+            dk += adv;
+            var += use * p * (1.0f - p);
+            words -= use;
+            continue;
+        }
+        int32_t i_int = n - 1 - (ki - sc.ks[e]);
+        i_int = i_int < 1 ? 1 : i_int;
+        const uint32_t M = 0xFFFFFFFFu >> __clz(i_int);
+        const float lo = (float)(M >> 1), Mp = (float)M + 1.0f;
+        const double level_end = (double)sc.ks[e] + (double)(n - 1) - (double)(M >> 1);  // ordinal where i reaches lo
+        const float i_f = (float)((double)(n - 1) - (kr - (double)sc.ks[e]));
+        const float togo = (float)(level_end - kr);
+        if (togo < 0.5f) {
+            dk += level_end - kr;
+            kr = level_end;
+            continue;
+        }
+        const float r_here = fminf(1.0f, (i_f + 1.0f) / Mp), r_end = (lo + 1.0f) / Mp;
+        const float need = Mp * __logf((i_f + 1.0f) / (lo + 1.0f));  // expected words to the end of this level
+        if (words < need) {
+            const float d = (i_f + 1.0f) * (1.0f - __expf(-words / Mp));
+            const float r_mid = 0.5f * (r_here + fminf(1.0f, (i_f + 1.0f - d) / Mp));
+            kr += (double)d;
+            dk += (double)d;
+            var += words * r_mid * (1.0f - r_mid);
+            words = 0.0f;
+        } else {
+            const float r_mid = 0.5f * (r_here + r_end);
+            dk += level_end - kr;
+            kr = level_end;
+            var += need * r_mid * (1.0f - r_mid);
+            words -= need;
+        }
+    }
+    dk_out = dk;
+    var_out = var;
+}
+
+// Acceptance rate at slot-relative ordinal kr, and an id of its (entity, mask level).
+__device__ __forceinline__ float rate_at(const Sched& sc, int32_t kr, int& level_id) {
+    kr = wrap_slot(sc, kr);
+    const int e = ent_of(sc, kr, 0);
+    const int32_t n = sc.nn[e];
+    if (n == 0) {
+        level_id = e << 6;
+        return ((float)sc.rrange + 1.0f) / ((float)sc.rmask + 1.0f);
+    }
+    const int32_t i = n - 1 - (kr - sc.ks[e]);
+    const int lz = __clz(i);
+    level_id = (e << 6) | lz;
+    return ((float)i + 1.0f) / ((float)(0xFFFFFFFFu >> lz) + 1.0f);
+}
+
+// How far the expected walk of one chunk may leave the chord between its ends: inside one level the rate
+// falls smoothly (words * dr / 8); across a level or class boundary it jumps (words * dr / 4).
+__device__ __forceinline__ int32_t chord_slack(const Sched& sc, int32_t kr_a, int32_t kr_b) {
+    int la, lb;
+    const float ra = rate_at(sc, kr_a, la), rb = rate_at(sc, kr_b, lb);
+    if (la == lb) return 4 + (int32_t)((float)CH_WORDS * 0.125f * fabsf(ra - rb));
+    const float r_lo = fminf(0.5f, fminf(ra, rb));
+    return 4 + (int32_t)((float)CH_WORDS * 0.25f * (1.0f - r_lo));
+}
+
+constexpr int CN_THREADS = 256;          // warp 0 settles, warps 1..7 stage the next unit's pending words
+constexpr int CN_MAX = 8192;             // pending words per unit (a unit = up to 8 chunks)
+constexpr int CN_UNIT_CHUNKS = 8;
+
+struct ChainUnit {
+    int first, count;  // chunks [first, first + count) of the round
+    int n;             // pending words in them
+    int ent0[CN_UNIT_CHUNKS + 1];  // entry index where each chunk starts
+    int sure0[CN_UNIT_CHUNKS + 1]; // certain accepts before each chunk's start, inside the unit
+};
+
+struct ChainShared {
+    uint2 ent[2][CN_MAX];  // {word, certain accepts before it inside the unit}
+    ChunkHdr hdr[256];
+    ChainUnit unit[2];
+    int64_t k;
+};
+
+// Greedy unit: chunks from `first` while the pending words fit.  A single chunk always fits (4,096).
+__device__ void plan_unit(const ChunkHdr* hdr, int n_here, int first, ChainUnit& u) {
+    u.first = first;
+    u.count = 0;
+    u.n = 0;
+    int sure = 0;
+    while (first + u.count < n_here && u.count < CN_UNIT_CHUNKS && u.n + hdr[first + u.count].n_pend <= CN_MAX) {
+        u.ent0[u.count] = u.n;
+        u.sure0[u.count] = sure;
+        u.n += hdr[first + u.count].n_pend;
+        sure += hdr[first + u.count].n_sure;
+        ++u.count;
+    }
+    u.ent0[u.count] = u.n;
+    u.sure0[u.count] = sure;
+}
+
+// global -> shared copy of a unit's pending lists by `n_thr` threads (rank `t`), the count of certain accepts
+// made relative to the unit on the way
+__device__ __forceinline__ void stage_unit(const WalkBuffers& b, const ChainUnit& u, uint2* dst, int t, int n_thr) {
+    for (int c = 0; c < u.count; ++c) {
+        const uint2* src = b.pend + (size_t)(u.first + c) * CH_WORDS;
+        const int n = u.ent0[c + 1] - u.ent0[c];
+        const uint32_t add = (uint32_t)u.sure0[c];
+        for (int e = t; e < n; e += n_thr) {
+            const uint2 x = __ldg(&src[e]);
+            dst[u.ent0[c] + e] = make_uint2(x.x, add + ((x.y >> 16) & 0x7FFFu));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CN_THREADS, 1) chain_kernel(const __grid_constant__ Sched sc, WalkBuffers b, int64_t chunk0,
+                                                              int n_here, int n_next) {
+    extern __shared__ __align__(16) unsigned char chain_dyn[];
+    ChainShared& sh = *reinterpret_cast<ChainShared*>(chain_dyn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    int64_t k = chunk0 == 0 ? 0 : b.k0[chunk0];
+    if (chunk0 == 0 && tid == 0) b.k0[0] = 0;
+    int pend_total = 0;
+    for (int g = tid; g < n_here; g += CN_THREADS) sh.hdr[g] = b.hdr[g];
+    __syncthreads();
+    if (n_here > 0) {
+        if (tid == 0) plan_unit(sh.hdr, n_here, 0, sh.unit[0]);
+        __syncthreads();
+        stage_unit(b, sh.unit[0], sh.ent[0], tid, CN_THREADS);
+        __syncthreads();
+    }
+    int buf = 0;
+    for (int first = 0; first < n_here;) {
+        const ChainUnit& u = sh.unit[buf];
+        const int next_first = first + u.count;
+        if (next_first < n_here && tid == 32) plan_unit(sh.hdr, n_here, next_first, sh.unit[buf ^ 1]);
+        if (warp != 0) {
+            // named barrier among the staging warps only: the plan of the next unit is theirs
+            asm volatile("bar.sync 1, %0;" ::"r"(CN_THREADS - 32));
+            if (next_first < n_here) stage_unit(b, sh.unit[buf ^ 1], sh.ent[buf ^ 1], tid - 32, CN_THREADS - 32);
+        } else {
+            // warp 0: the unit's pending words in stream order, 32 at a time, each at its exact ordinal
+            const uint2* ent = sh.ent[buf];
+            const int n = u.n;
+            const int32_t kr0 = (int32_t)(k % sc.steps);
+            const int e_hint = ent_of(sc, kr0, 0);
+            // the usual unit lies inside one class's shuffle: the step number is then i0 - (accepts before the word)
+            const bool one_class = sc.nn[e_hint] > 0 && kr0 + u.sure0[u.count] + n < sc.ks[e_hint + 1];
+            const int32_t i0 = sc.nn[e_hint] - 1 - (kr0 - sc.ks[e_hint]);
+            const int my_idx = lane < u.count ? u.ent0[lane + 1] : -1;  // lane c reports the boundary after chunk c
+            int my_D = 0, D = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int e = base + lane;
+                const bool valid = e < n;
+                const uint2 x = valid ? ent[e] : make_uint2(0u, 0u);
+                const int32_t before = (int32_t)x.y + D;
+                uint32_t bits;
+                if (one_class) {
+                    const int32_t i_a = i0 - before;
+                    bits = __ballot_sync(FULL, valid && (x.x & (0xFFFFFFFFu >> __clz(i_a))) <= (uint32_t)i_a);
+                    for (;;) {  // lane l is final once the lanes below it are: at most 32 rounds, usually 2
+                        const int32_t i = i_a - __popc(bits & lt);
+                        const uint32_t nb = __ballot_sync(FULL, valid && (x.x & (0xFFFFFFFFu >> __clz(i))) <= (uint32_t)i);
+                        if (nb == bits) break;
+                        bits = nb;
+                    }
+                } else {
+                    int en = e_hint;
+                    uint32_t uu;
+                    bits = __ballot_sync(FULL, valid && accept_at(sc, x.x, wrap_slot(sc, kr0 + before), en, uu));
+                    for (;;) {
+                        const uint32_t nb =
+                            __ballot_sync(FULL, valid && accept_at(sc, x.x, wrap_slot(sc, kr0 + before + __popc(bits & lt)), en, uu));
+                        if (nb == bits) break;
+                        bits = nb;
+                    }
+                }
+                if (my_idx >= base && my_idx < base + 32) my_D = D + __popc(bits & ((1u << (my_idx - base)) - 1u));
+                D += __popc(bits);
+            }
+            if (my_idx >= n) my_D = D;
+            if (lane < u.count) b.k0[chunk0 + u.first + lane + 1] = k + u.sure0[lane + 1] + my_D;
+            if (lane == 0) sh.k = k + u.sure0[u.count] + D;
+        }
+        __syncthreads();
+        k = sh.k;
+        pend_total += u.n;
+        first = next_first;
+        buf ^= 1;
+        __syncthreads();
+    }
+    // boundaries of the next round, from the exact ordinal reached: one thread per chunk
+    if (n_next > 0) {
+        const int32_t kr0 = (int32_t)(k % sc.steps);
+        if (tid == 0) b.kpred[0] = k;
+        float var = 0.0f;
+        if (tid < n_next) {
+            double dk;
+            predict_span(sc, kr0, (float)(tid + 1) * (float)CH_WORDS, dk, var);
+            b.kpred[tid + 1] = k + (int64_t)(dk + 0.5);
+        }
+        __syncthreads();
+        if (tid < n_next) {
+            const int32_t ka = (int32_t)((b.kpred[tid] - k + kr0) % sc.steps), kb = (int32_t)((b.kpred[tid + 1] - k + kr0) % sc.steps);
+            b.eband[tid] = 8 + (int32_t)(7.5f * sqrtf(var + 1.0f)) + chord_slack(sc, ka, kb);
+        }
+    }
+    if (tid == 0) atomicAdd(&b.status[4], pend_total >> 10);  // thousands of pending words the chain settled
+}
+
+struct FinalShared {
+    ChunkShared cs;
+    uint32_t pend_w[CH_WORDS];
+    uint16_t pend_s[CH_WORDS];
+    uint16_t pend_res[CH_WORDS];  // accepted pending words before it | own verdict << 15
+    int32_t pend_acc;
+};
+
+__global__ void __launch_bounds__(CH_THREADS) final_kernel(const __grid_constant__ Sched sc, WalkBuffers b) {
+    __shared__ FinalShared sh;
+    const int64_t chunk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    const int64_t ka = b.k0[chunk], kb = b.k0[chunk + 1];
+    if (ka >= sc.k_total) return;  // the plan ended before this chunk
+    const int64_t slot_a = ka / sc.steps;
+    const int32_t kr0 = (int32_t)(ka - slot_a * sc.steps);
+    const int32_t dk_end = (int32_t)(kb - ka);
+    const int e_hint = ent_of(sc, kr0, 0);
+    const int64_t next_slot_k = (slot_a + 1) * sc.steps;  // first slot boundary at or after this chunk's start
+    uint32_t w[CH_ROWS], bs[CH_ROWS], ba[CH_ROWS];
+    int32_t klo[CH_ROWS], khi[CH_ROWS];
+    load_chunk(b, chunk, w);
+    // how far the expected walk may bend away from the chord between the exact ends
+    const int32_t e_band = chord_slack(sc, kr0, kr0 + (dk_end > 0 && dk_end <= CH_WORDS ? dk_end : 0));
+    const bool sane = dk_end >= 0 && dk_end <= CH_WORDS;
+    bool counted = false;
+    for (int attempt = sane ? 0 : 1; attempt < 2 && !counted; ++attempt) {
+        const bool all_pending = attempt == 1;
+        classify_words<true>(sc, sh.cs, w, kr0, sane ? dk_end : 0, e_band, all_pending, e_hint, bs, ba, klo, khi);
+        const uint32_t tot = sh.cs.tot;
+        const int n_pend = (int)(tot >> 16), n_sure = (int)(tot & 0xFFFFu);
+#pragma unroll
+        for (int v = 0; v < CH_ROWS; ++v) {
+            if ((ba[v] >> lane) & 1u) {
+                const uint32_t pre = sh.cs.seg[v * (CH_THREADS / 32) + warp];
+                const uint32_t e = (pre >> 16) + (uint32_t)__popc(ba[v] & lt);
+                sh.pend_w[e] = w[v];
+                sh.pend_s[e] = (uint16_t)((pre & 0xFFFFu) + (uint32_t)__popc(bs[v] & lt));
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int D = settle_pending(
+                sc, n_pend, kr0, e_hint, [&](int e) { return make_uint2(sh.pend_w[e], (uint32_t)sh.pend_s[e]); },
+                [&](int e, int before, uint32_t acc) { sh.pend_res[e] = (uint16_t)((uint32_t)before | (acc << 15)); });
+            if (lane == 0) sh.pend_acc = D;
+        }
+        __syncthreads();
+        const int pend_acc = sh.pend_acc;
+        bool viol = false;
+#pragma unroll
+        for (int v = 0; v < CH_ROWS; ++v) {
+            const uint32_t pre = sh.cs.seg[v * (CH_THREADS / 32) + warp];
+            const int a_idx = (int)(pre >> 16) + __popc(ba[v] & lt);
+            const uint32_t res = a_idx < n_pend ? sh.pend_res[a_idx] : (uint32_t)pend_acc;
+            const int k = (int)(pre & 0xFFFFu) + __popc(bs[v] & lt) + (int)(res & 0x7FFFu);  // exact accepts before this word
+            if (!all_pending && (k < klo[v] || k > khi[v])) viol = true;
+        }
+        if (__syncthreads_or(viol)) {
+            if (tid == 0) atomicAdd(&b.status[1], 1);
+            continue;  // a word left its band: decide the chunk again with every word pending (exact by itself)
+        }
+        counted = true;
+        if (n_sure + pend_acc != dk_end) {
+            if (tid == 0) atomicExch(&b.status[3], 1);  // the chain counted this chunk differently: the plan is void
+            return;
+        }
+#pragma unroll
+        for (int v = 0; v < CH_ROWS; ++v) {
+            const uint32_t pre = sh.cs.seg[v * (CH_THREADS / 32) + warp];
+            const int a_idx = (int)(pre >> 16) + __popc(ba[v] & lt);
+            const uint32_t res = a_idx < n_pend ? sh.pend_res[a_idx] : (uint32_t)pend_acc;
+            const int k = (int)(pre & 0xFFFFu) + __popc(bs[v] & lt) + (int)(res & 0x7FFFu);
+            const bool is_pend = (ba[v] >> lane) & 1u;
+            const bool acc = is_pend ? ((res >> 15) & 1u) : ((bs[v] >> lane) & 1u);
+            const int64_t kg = ka + k;
+            if (acc && kg < sc.k_total) {
+                int ent = e_hint;
+                uint32_t u;
+                accept_at(sc, w[v], wrap_slot(sc, kr0 + k), ent, u);
+                b.A[kg] = u;
+                const int64_t after = kg + 1;  // a slot ends with its last draw
+                if (after >= next_slot_k && (after - next_slot_k) % sc.steps == 0)
+                    b.slot_pos[after / sc.steps] = b.pos0 + chunk * CH_WORDS + v * CH_THREADS + tid + 1;
+            }
+        }
     }
 }
 
@@ -474,6 +737,7 @@ struct ResolveArgs {
     const int32_t* class_n;
     const int64_t* class_aoff;
     int32_t n_classes;
+    int64_t slot_stride;  // draws per slot in A (all classes' shuffle steps + the randint block)
     int32_t size;      // entries of the permutation wanted per class
     int32_t cap_log2;  // hash capacity
     uint32_t* heads;   // [n_slots * n_classes][size]
@@ -537,7 +801,7 @@ __global__ void __launch_bounds__(RS_THREADS) resolve_scan_kernel(ResolveArgs a)
     h.own = reinterpret_cast<uint16_t*>(head + size);
     h.mask = cap - 1;
     h.shift = 32 - a.cap_log2;
-    const uint32_t* __restrict__ A = a.A + (size_t)s * a.class_aoff[a.n_classes] + a.class_aoff[c];
+    const uint32_t* __restrict__ A = a.A + (size_t)s * a.slot_stride + a.class_aoff[c];
     uint32_t* heads_out = a.heads + (size_t)draw * size;
 
     for (uint32_t t = tid; t < cap; t += RS_THREADS) {
@@ -692,6 +956,7 @@ struct PrefixArgs {
     const int32_t* class_rows;  // every class's ascending row ids back to back
     const int64_t* class_roff;  // [n_classes + 1]
     int32_t n_classes, n_draws;
+    int64_t slot_stride;
     int32_t size, n_tr, n_va;
     const uint32_t* heads;
     int32_t* idx_train;  // [n_slots][n_classes * n_tr]
@@ -708,7 +973,7 @@ __global__ void resolve_prefix_kernel(PrefixArgs a) {
     const int32_t size = a.size;
     uint32_t* head = pf_dyn + (size_t)warp * 2 * size;
     uint32_t* js = head + size;
-    const uint32_t* __restrict__ A = a.A + (size_t)s * a.class_aoff[a.n_classes] + a.class_aoff[c];
+    const uint32_t* __restrict__ A = a.A + (size_t)s * a.slot_stride + a.class_aoff[c];
     const uint32_t* hin = a.heads + (size_t)draw * size;
     for (int p = lane; p < size; p += 32) {
         head[p] = hin[p];
@@ -764,6 +1029,36 @@ static double expected_words(int64_t n) {
     return total;
 }
 
+static void build_schedule(const rfmc_drawplan* pl, Sched& sc) {
+    const rfmc_dataset* ds = pl->ds;
+    sc.n_ent = 0;
+    int32_t k = 0;
+    for (int c = 0; c < pl->n_classes; ++c) {
+        const int64_t n = ds->h_class_n[c];
+        if (n < 2) continue;
+        sc.ks[sc.n_ent] = k;
+        sc.nn[sc.n_ent] = (int32_t)n;
+        k += (int32_t)(n - 1);
+        ++sc.n_ent;
+    }
+    if (pl->n_cands > 0 && pl->rrange != 0u) {
+        sc.ks[sc.n_ent] = k;
+        sc.nn[sc.n_ent] = 0;
+        k += pl->n_cands;
+        ++sc.n_ent;
+    }
+    sc.ks[sc.n_ent] = k;
+    sc.steps = k;
+    sc.rmask = pl->rmask;
+    sc.rrange = pl->rrange;
+    sc.k_total = (int64_t)pl->n_slots * k;
+}
+
+__global__ void init_slot_pos_kernel(int64_t* slot_pos, int n, int64_t first, int64_t rest) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_pos[i] = i == 0 ? first : rest;
+}
+
 int drawplan_launch(rfmc_drawplan* pl) {
     rfmc_dataset* ds = pl->ds;
     cudaStream_t st = pl->stream;
@@ -771,43 +1066,67 @@ int drawplan_launch(rfmc_drawplan* pl) {
     auto mark = [&](int i) {
         if (pl->timing) cudaEventRecord(pl->ev[i], st);
     };
+    Sched sc;
+    build_schedule(pl, sc);
     mark(0);
-    // fill
+    int launches = 0;
     {
         const size_t smem = (size_t)(JUMP_SEQ + 1) * sizeof(uint32_t);
         RFMC_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mt_fill_kernel<<<(unsigned)pl->n_chunks, FILL_THREADS, smem, st>>>(pl->d_key, pl->d_polys, pl->blocks_per_chunk, pl->n_blocks,
                                                                            pl->d_W);
         RFMC_CUDA(cudaGetLastError());
+        ++launches;
     }
     mark(1);
-    // walk
-    {
-        WalkArgs w;
-        w.W = pl->d_W;
-        w.n_words = pl->n_blocks * MT_N;
-        w.pos0 = pl->pos0;
-        w.n_slots = pl->n_slots;
-        w.n_classes = C;
-        w.n_cands = pl->n_cands;
-        w.class_n = ds->d_class_n;
-        w.class_aoff = ds->d_class_aoff;
-        w.rmask = pl->rmask;
-        w.rrange = pl->rrange;
-        w.A = pl->d_A;
-        w.randv = pl->d_randv;
-        w.slot_pos = pl->d_slot_pos;
-        w.status = pl->d_status;
-        walk_kernel<<<1, WK_THREADS, 0, st>>>(w);
+    // a slot boundary that is never reached stays -1: the host then knows the words ran out
+    init_slot_pos_kernel<<<(pl->n_slots + 1 + 255) / 256, 256, 0, st>>>(pl->d_slot_pos, pl->n_slots + 1, (int64_t)pl->pos0,
+                                                                     sc.steps > 0 ? (int64_t)-1 : (int64_t)pl->pos0);
+    RFMC_CUDA(cudaGetLastError());
+    ++launches;
+    if (sc.steps > 0) {
+        WalkBuffers b;
+        b.W = pl->d_W;
+        b.n_words = pl->n_blocks * MT_N;
+        b.pos0 = pl->pos0;
+        b.chunks_per_round = pl->chunks_per_round;
+        b.n_chunks = pl->n_walk_chunks;
+        b.k0 = pl->d_k0;
+        b.kpred = pl->d_kpred;
+        b.eband = pl->d_eband;
+        b.hdr = (ChunkHdr*)pl->d_hdr;
+        b.pend = (uint2*)pl->d_pend;
+        b.A = pl->d_A;
+        b.slot_pos = pl->d_slot_pos;
+        b.status = pl->d_status;
+        const int G = pl->chunks_per_round;
+        const int64_t N = pl->n_walk_chunks;
+        RFMC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared)));
+        chain_kernel<<<1, CN_THREADS, sizeof(ChainShared), st>>>(sc, b, 0, 0, (int)(N < G ? N : G));
+        ++launches;
+        for (int64_t c0 = 0; c0 < N; c0 += G) {
+            const int here = (int)(N - c0 < G ? N - c0 : G);
+            const int64_t left = N - c0 - here;
+            classify_kernel<<<here, CH_THREADS, 0, st>>>(sc, b, c0);
+            chain_kernel<<<1, CN_THREADS, sizeof(ChainShared), st>>>(sc, b, c0, here, (int)(left < G ? left : G));
+            launches += 2;
+        }
         RFMC_CUDA(cudaGetLastError());
+        mark(2);
+        final_kernel<<<(unsigned)N, CH_THREADS, 0, st>>>(sc, b);
+        RFMC_CUDA(cudaGetLastError());
+        ++launches;
+    } else {
+        mark(2);
     }
-    mark(2);
+    mark(3);
     if (pl->size > 0) {
         ResolveArgs r;
         r.A = pl->d_A;
         r.class_n = ds->d_class_n;
         r.class_aoff = ds->d_class_aoff;
         r.n_classes = C;
+        r.slot_stride = sc.steps;
         r.size = (int32_t)pl->size;
         r.cap_log2 = pl->cap_log2;
         r.heads = pl->d_heads;
@@ -817,7 +1136,6 @@ int drawplan_launch(rfmc_drawplan* pl) {
         RFMC_CUDA(cudaFuncSetAttribute(resolve_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resolve_scan_kernel<<<(unsigned)(pl->n_slots * C), RS_THREADS, smem, st>>>(r);
         RFMC_CUDA(cudaGetLastError());
-        mark(3);
         PrefixArgs x;
         x.A = pl->d_A;
         x.class_n = ds->d_class_n;
@@ -826,6 +1144,7 @@ int drawplan_launch(rfmc_drawplan* pl) {
         x.class_roff = ds->d_class_roff;
         x.n_classes = C;
         x.n_draws = pl->n_slots * C;
+        x.slot_stride = sc.steps;
         x.size = (int32_t)pl->size;
         x.n_tr = (int32_t)pl->n_tr;
         x.n_va = (int32_t)pl->n_va;
@@ -838,11 +1157,11 @@ int drawplan_launch(rfmc_drawplan* pl) {
         RFMC_CUDA(cudaFuncSetAttribute(resolve_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         resolve_prefix_kernel<<<(unsigned)((x.n_draws + wpb - 1) / wpb), wpb * 32, psm, st>>>(x);
         RFMC_CUDA(cudaGetLastError());
+        launches += 2;
     }
-    else
-        mark(3);
     mark(4);
-    pl->launches = pl->size > 0 ? 4 : 2;
+    pl->launches = launches;
+    pl->steps_per_slot = sc.steps;
     return 0;
 }
 
@@ -856,13 +1175,18 @@ int64_t drawplan_words_needed(const std::vector<int64_t>& class_n, int n_slots, 
     if (rrange) per_slot += (double)n_cands * ((double)rmask + 1.0) / ((double)rrange + 1.0);
     const double mean = per_slot * n_slots;
     const double sigma = sqrt(2.0 * (steps + n_cands) * n_slots);
-    // the walk reads whole chunks of 8,192 words ahead of what it consumes
-    return (int64_t)(mean + (8.0 + 8.0 * attempt) * sigma) + 65536 + (int64_t)attempt * (1 << 20);
+    return (int64_t)(mean + (8.0 + 8.0 * attempt) * sigma) + 16384 + (int64_t)attempt * (1 << 20);
 }
 
 int drawplan_geometry(rfmc_drawplan* pl, int64_t words) {
-    pl->n_blocks = (pl->pos0 + words + MT_N - 1) / MT_N + 1;
-    pl->blocks_per_chunk = pl->n_blocks < RNG_BLOCKS_PER_CHUNK ? (int)pl->n_blocks : RNG_BLOCKS_PER_CHUNK;
+    const int64_t walk_chunks = (words + CH_WORDS - 1) / CH_WORDS + 1;
+    pl->n_walk_chunks = walk_chunks;
+    pl->chunks_per_round = 128;
+    pl->n_blocks = (pl->pos0 + walk_chunks * CH_WORDS + MT_N - 1) / MT_N + 1;
+    // fill CTAs: about two per SM; the chunk length is one of five sizes so that the jump polynomials are shared
+    int bpc = RNG_BLOCKS_PER_CHUNK;
+    while (bpc > 105 && pl->n_blocks / bpc < 296) bpc /= 2;
+    pl->blocks_per_chunk = pl->n_blocks < bpc ? (int)pl->n_blocks : bpc;
     pl->n_chunks = (pl->n_blocks + pl->blocks_per_chunk - 1) / pl->blocks_per_chunk;
     return 0;
 }

@@ -84,7 +84,8 @@ _SIGNATURES = {
     "rfmc_drawplan_finish": (C.c_int, [_p, _p, _p, C.POINTER(C.c_int32)]),
     "rfmc_drawplan_state_at": (C.c_int, [_p, C.c_int32, _p, C.POINTER(C.c_int32)]),
     "rfmc_drawplan_indices": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p]),
-    "rfmc_drawplan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rfmc_drawplan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32)]),
     "rfmc_drawplan_timing": (C.c_int, [C.c_int]),
     "rfmc_drawplan_kernel_ms": (C.c_int, [_p, _p]),
     "rfmc_drawplan_destroy": (C.c_int, [_p]),
@@ -342,12 +343,12 @@ class DrawPlan:
         return T, V
 
     def info(self):
-        g, c, f, l = C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
-        _check(load_library().rfmc_drawplan_info(self._h, C.byref(g), C.byref(c), C.byref(f), C.byref(l)))
-        return dict(words_generated=g.value, words_consumed=c.value, chunk_fallbacks=f.value, launches=l.value)
+        g, c, p, f, l = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        _check(load_library().rfmc_drawplan_info(self._h, C.byref(g), C.byref(c), C.byref(p), C.byref(f), C.byref(l)))
+        return dict(words_generated=g.value, words_consumed=c.value, words_pending=p.value, chunk_fallbacks=f.value, launches=l.value)
 
     def kernel_ms(self):
-        """(fill, walk, resolve scan, resolve prefix) in ms; needs engine.drawplan_timing(True) before creation."""
+        """(fill, classify + chain rounds, final pass, resolve) in ms; needs engine.drawplan_timing(True) before creation."""
         ms = (C.c_float * 4)()
         _check(load_library().rfmc_drawplan_kernel_ms(self._h, C.cast(ms, _p)))
         return tuple(float(x) for x in ms)

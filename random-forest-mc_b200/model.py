@@ -95,6 +95,25 @@ class _SlotJudge:
         return False
 
 
+class _DeviceSlotState:
+    """numpy's stream state before one slot of a device draw plan; read back (624 words) only when a
+    mis-speculated plan has to be rewound to that slot."""
+
+    def __init__(self, dev, slot, template):
+        self.dev, self.slot, self.template = dev, slot, template
+
+    def resolve(self):
+        key, pos = self.dev.state_at(self.slot)
+        t = self.template
+        return (t[0], key, pos, t[3], t[4])
+
+
+class _PlanList(list):
+    """The slots of one plan; ``dev`` is the device draw plan that owns their row ids (or None)."""
+
+    dev = None
+
+
 class RandomForestMC(BaseRandomForestMC):
     def __init__(
         self,
@@ -152,6 +171,12 @@ class RandomForestMC(BaseRandomForestMC):
         self.rng_threads = max(0, min(2, (os.cpu_count() or 1) - 1))
         self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"
         self.gil_switch_interval = float(os.environ.get("RFMC_GIL_SWITCH_INTERVAL", "1e-4"))  # seconds, host-stream fits only
+        # numpy's stream can be walked on the GPU (csrc/rng_walk.cu: same rows, counts and stream states, row
+        # ids never leave HBM).  Measured on a B200 next to 32 AVX-512 host cores the host walk
+        # (csrc/host_rng.cpp) is still the faster one, so the device walk is opt-in;
+        # replays, single-slot calls and draws wider than the device resolve always use the host walk.
+        self.device_draws = os.environ.get("RFMC_DEVICE_DRAWS", "0") == "1"
+        self.device_draw_min_slots = 2
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -289,19 +314,33 @@ class RandomForestMC(BaseRandomForestMC):
         pos = {name: j for j, name in enumerate(self.feature_cols)}
         return [pos[f] for f in feature_list]
 
-    def _draw_plan(self, n_plan: int, spec: int):
+    def _draw_plan(self, n_plan: int, spec: int, stream=None):
         """All draws of ``n_plan`` slots with ``spec`` candidates each, in the reference's order.
-        numpy's stream (rows per class, then one feature count per candidate) is walked by ONE host
-        call (``rfmc_legacy_draw_plan``); CPython's ``random.sample`` -- a separate stream --
-        then picks and orders the features.  Entry layout as ``_draw_slot``."""
+        numpy's stream (rows per class, then one feature count per candidate) is walked in ONE call:
+        on the GPU (``rfmc_draw_plan_device``; the row ids stay in HBM for the grower) or, for plans
+        the device resolve does not take, on the host (``rfmc_legacy_draw_plan``).  CPython's
+        ``random.sample`` -- a separate stream -- then picks and orders the features.  Entry layout as
+        ``_draw_slot``, plus the device plan and slot that hold the row ids."""
         if self.min_feature > self.max_feature:
             raise ValueError("low >= high")  # what np.random.randint raises in the reference
         st = self._np_rng().get_state()
-        key = st[1].copy()
-        T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
-            key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,
-            int(self.min_feature), int(self.max_feature) + 1, getattr(self._tls, "rng_flags", self.rng_threads | (0x100 if self.rng_producer else 0)),
-        )
+        dev = None
+        if (self.device_draws and n_plan >= self.device_draw_min_slots and int(self._N) <= engine.DRAW_MAX_PER_CLASS
+                and int(self.max_feature) - int(self.min_feature) < 2**31 - 2):
+            dev = engine.DrawPlan(self._dev_dataset, self.encoded.class_rows, st[1], int(st[2]), n_plan, int(self._N),
+                                  int(self.batch_train_pclass), spec, int(self.min_feature), int(self.max_feature) + 1, stream)
+            try:
+                K, key, pos = dev.finish()
+            except BaseException:
+                dev.close()
+                raise
+            T = V = ksnap = psnap = None
+        else:
+            key = st[1].copy()
+            T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
+                key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,
+                int(self.min_feature), int(self.max_feature) + 1, getattr(self._tls, "rng_flags", self.rng_threads | (0x100 if self.rng_producer else 0)),
+            )
         self._np_rng().set_state((st[0], key, pos, st[3], st[4]))
         cols = self.feature_cols
         py_rng = self._py_rng()
@@ -318,11 +357,25 @@ class RandomForestMC(BaseRandomForestMC):
             for k in ks.reshape(-1):
                 out = sorted(py_rng.sample(cols, int(k)), key=lambda x: int(x.split("_")[-1]))
                 per_cand.append(np.array([where[f] for f in out], dtype=np.int32))
-        plan = []
+        plan = _PlanList()
+        plan.dev = dev
         for s in range(n_plan):
-            start = ((st[0], ksnap[s], int(psnap[s]), st[3], st[4]), ("replay", py_state0, K, spec, s))
-            plan.append((T[s], V[s], per_cand[s * spec : (s + 1) * spec], (start, True)))
+            if dev is not None:
+                start = (_DeviceSlotState(dev, s, st), ("replay", py_state0, K, spec, s))
+                plan.append((None, None, per_cand[s * spec : (s + 1) * spec], (start, True), (dev, s)))
+            else:
+                start = ((st[0], ksnap[s], int(psnap[s]), st[3], st[4]), ("replay", py_state0, K, spec, s))
+                plan.append((T[s], V[s], per_cand[s * spec : (s + 1) * spec], (start, True), None))
         return plan
+
+    @staticmethod
+    def _slot_rows(p):
+        """(idx_T, idx_V) of a plan entry; a device plan's rows are copied to the host only here."""
+        if p[0] is None and len(p) > 4 and p[4] is not None:
+            dev, s = p[4]
+            T, V = dev.indices(s, 1)
+            return T[0], V[0]
+        return p[0], p[1]
 
     def _wrap(self, soa, score=None) -> DecisionTreeMC:
         t = DecisionTreeMC.from_soa(soa, self.encoded, self.type_of_cols, self.class_vals)
@@ -373,7 +426,8 @@ class RandomForestMC(BaseRandomForestMC):
         return self._np_rng().get_state(), self._py_rng().getstate()
 
     def _restore(self, snap):
-        self._np_rng().set_state(snap[0])
+        np_state = snap[0].resolve() if isinstance(snap[0], _DeviceSlotState) else snap[0]
+        self._np_rng().set_state(np_state)
         py_rng = self._py_rng()
         py = snap[1]
         if isinstance(py, tuple) and len(py) == 5 and py[0] == "replay":
@@ -416,15 +470,19 @@ class RandomForestMC(BaseRandomForestMC):
 
     def _grow_plan(self, plan, stream=None):
         """One launch for every (slot, candidate) of the plan.  Returns (batch, first cand id per slot)."""
-        idx_T = np.stack([p[0] for p in plan])
-        idx_V = np.stack([p[1] for p in plan])
         slot_of, feats, first = [], [], []
         for s, p in enumerate(plan):
             first.append(len(feats))
             for f in p[2]:
                 slot_of.append(s)
                 feats.append(f)
-        b = engine.GrowBatch(self._dev_dataset, idx_T, idx_V, slot_of, feats, self.max_depth, self.min_samples_split, stream)
+        dev = getattr(plan, "dev", None)
+        if dev is not None:  # the row ids are already in HBM
+            b = engine.GrowBatch(self._dev_dataset, None, None, slot_of, feats, self.max_depth, self.min_samples_split, stream, plan=dev)
+        else:
+            idx_T = np.stack([p[0] for p in plan])
+            idx_V = np.stack([p[1] for p in plan])
+            b = engine.GrowBatch(self._dev_dataset, idx_T, idx_V, slot_of, feats, self.max_depth, self.min_samples_split, stream)
         b.run()
         return b, first
 
@@ -454,7 +512,7 @@ class RandomForestMC(BaseRandomForestMC):
             if avg_commit != float("inf"):
                 n_plan = min(n_plan, max(4, int(4 * avg_commit) + 1))
             t0 = _now()
-            plan = self._draw_plan(n_plan, spec)
+            plan = self._draw_plan(n_plan, spec, stream)
             t1 = _now()
             batch, first = self._grow_plan(plan, stream)
             t2 = _now()
@@ -502,6 +560,8 @@ class RandomForestMC(BaseRandomForestMC):
                     committed += 1
             finally:
                 batch.close()
+                if getattr(plan, "dev", None) is not None:
+                    plan.dev.close()
             avg_commit = committed if avg_commit == float("inf") else 0.5 * avg_commit + 0.5 * committed
             if len(recent_used) >= 4:
                 tail = recent_used[-16:]
@@ -585,10 +645,11 @@ class RandomForestMC(BaseRandomForestMC):
         if judge.best is not None:
             kept[judge.best] = batch.fetch([judge.best])[0]
         it = 0
+        rows = self._slot_rows(p)
         while True:
             it += 1
-            _, _, feats, snap = self._draw_slot(K, idx=(p[0], p[1]))
-            ext = (p[0], p[1], feats, snap)
+            _, _, feats, snap = self._draw_slot(K, idx=rows)
+            ext = (rows[0], rows[1], feats, snap)
             b, _ = self._grow_plan([ext], stream)
             try:
                 correct, _ = b.results()

@@ -19,8 +19,11 @@ class FakeDataset:
 class FakeBatch:
     grown_total = 0
 
-    def __init__(self, ds, idx_train, idx_val, cand_slot, feat_lists, max_depth, min_samples_split, stream=None):
+    def __init__(self, ds, idx_train, idx_val, cand_slot, feat_lists, max_depth, min_samples_split, stream=None, plan=None):
         self.ds = ds
+        if plan is not None:  # rows of a (fake) device draw plan
+            assert idx_train is None and idx_val is None and not plan.closed
+            idx_train, idx_val = plan.T, plan.V
         self.idx_train = np.asarray(idx_train)
         self.idx_val = np.asarray(idx_val)
         self.cand_slot = list(cand_slot)
@@ -55,6 +58,38 @@ class FakeBatch:
 
     def close(self):
         pass
+
+
+class FakeDrawPlan:
+    """engine.DrawPlan's interface on top of the HOST walk of numpy's stream (product code,
+    csrc/host_rng.cpp): the device-plan branch of the fit loop -- row ids that never visit the host,
+    stream states read back only for a rewind -- runs on a machine without a GPU."""
+
+    created = 0
+
+    def __init__(self, ds, class_rows, key, pos, n_slots, per_class, n_train_pclass, n_cands, low, high, stream=None):
+        from random_forest_mc_b200 import engine
+
+        FakeDrawPlan.created += 1
+        self.n_slots, self.closed = n_slots, False
+        self.key = np.array(key, dtype=np.uint32).copy()
+        self.T, self.V, self.K, self.ksnap, self.psnap, self.pos = engine.legacy_draw_plan(
+            self.key, int(pos), n_slots, class_rows, per_class, n_train_pclass, n_cands, low, high, 0)
+
+    def finish(self):
+        return self.K, self.key, self.pos
+
+    def state_at(self, slot):
+        assert not self.closed, "stream state asked of a closed plan"
+        return (self.key, self.pos) if slot == self.n_slots else (self.ksnap[slot], int(self.psnap[slot]))
+
+    def indices(self, slot0=0, n_slots=None):
+        assert not self.closed, "rows asked of a closed plan"
+        n = self.n_slots - slot0 if n_slots is None else n_slots
+        return self.T[slot0 : slot0 + n], self.V[slot0 : slot0 + n]
+
+    def close(self):
+        self.closed = True
 
 
 class FakeForest:
@@ -111,6 +146,7 @@ def install(monkeypatch):
     monkeypatch.setattr(engine, "DeviceDataset", FakeDataset)
     monkeypatch.setattr(engine, "encode_dataset_device", fake_encode_dataset_device)
     monkeypatch.setattr(engine, "GrowBatch", FakeBatch)
+    monkeypatch.setattr(engine, "DrawPlan", FakeDrawPlan)
     monkeypatch.setattr(engine, "DeviceForest", FakeForest)
 
 
@@ -118,6 +154,7 @@ def install_plain():
     from random_forest_mc_b200 import engine
 
     engine.DeviceDataset, engine.GrowBatch, engine.DeviceForest = FakeDataset, FakeBatch, FakeForest
+    engine.DrawPlan = FakeDrawPlan
     engine.encode_dataset_device = fake_encode_dataset_device
     engine.stream_create = lambda device=0: 0
     engine.stream_destroy = lambda device, stream: None

@@ -129,7 +129,7 @@ def test_c4_shape_sharded_fit_contract():
     correct, _ = batch.results()
     for k in range(2):
         tree = m._wrap(batch.fetch([k])[0])
-        assert float(m.validationTree(tree, plan[0][1])) == correct[k] / batch.n_val
+        assert float(m.validationTree(tree, m._slot_rows(plan[0])[1])) == correct[k] / batch.n_val
     batch.close()
 
 

@@ -46,7 +46,7 @@ def test_conservation_and_purity(big):
         slot = ci // 2
         nodes, counts = t.nodes, t.counts
         leaf = nodes["feat"] < 0
-        want = np.bincount(labels[plan[slot][0]], minlength=4)
+        want = np.bincount(labels[m._slot_rows(plan[slot])[0]], minlength=4)
         assert np.array_equal(counts[leaf].sum(axis=0), want)          # rows conserved per class
         assert np.array_equal(counts[0], want)                         # root sees the whole bootstrap
         split = np.flatnonzero(~leaf)
@@ -57,7 +57,8 @@ def test_conservation_and_purity(big):
         assert pure.mean() > 0.999                                     # grown to purity
         assert 0 <= correct[ci] <= batch.n_val
     # batching independence: candidate 3 alone == candidate 3 inside the batch
-    solo = eng.GrowBatch(m._dev_dataset, plan[1][0][None, :], plan[1][1][None, :], [0], [plan[1][2][1]], m.max_depth, 1).run()
+    rows1 = m._slot_rows(plan[1])
+    solo = eng.GrowBatch(m._dev_dataset, rows1[0][None, :], rows1[1][None, :], [0], [plan[1][2][1]], m.max_depth, 1).run()
     c1, _ = solo.results()
     t1 = solo.fetch([0])[0]
     assert c1[0] == correct[3]
@@ -75,7 +76,7 @@ def test_fused_scorer_equals_vote_kernel(big):
     correct, _ = batch.results()
     for k in range(2):
         tree = m._wrap(batch.fetch([k])[0])
-        score = m.validationTree(tree, plan[0][1])                    # vote kernel on raw values
+        score = m.validationTree(tree, m._slot_rows(plan[0])[1])                    # vote kernel on raw values
         assert float(score) == correct[k] / batch.n_val                # fused scorer in the grower
     batch.close()
 

@@ -155,3 +155,36 @@ def test_plan_feeds_the_grower_without_a_host_copy():
         a.close(), b.close(), plan.close()
     finally:
         ds.close()
+
+
+def test_fit_with_device_draws_equals_fit_with_host_draws():
+    """fit() with numpy's stream walked on the GPU (device_draws) grows the forest of the host walk and
+    leaves both RNG streams in the same state; a plan that stops early exercises the rewind through the
+    device plan's stream states."""
+    import random
+
+    import pandas as pd
+
+    from random_forest_mc_b200.model import RandomForestMC
+    from tests.helpers import tree_diff
+
+    g = np.random.default_rng(8)
+    n = 6000
+    frame = pd.DataFrame({"a": np.round(g.normal(size=n), 2), "b": g.integers(0, 30, size=n), "c": g.choice(list("xyz"), size=n)})
+    frame["target"] = ((frame.a + frame.b / 15 + (frame.c == "x") + g.normal(size=n) * 0.7) > 1.3).astype(int).astype(str)
+    out = []
+    for device in (False, True):
+        for th in (1.0, 0.55):  # 0.55: most slots stop at their first candidate -> rewinds
+            m = RandomForestMC(n_trees=12, target_col="target", max_discard_trees=3, batch_train_pclass=40, batch_val_pclass=30, th_start=th)
+            m.device_draws = device
+            m.process_dataset(frame.copy())
+            np.random.seed(3), random.seed(3)
+            m.fit()
+            out.append((m, np.random.get_state(), random.getstate()))
+    for a, b in ((out[0], out[2]), (out[1], out[3])):
+        assert len(a[0].data) == len(b[0].data) == 12
+        for ta, tb in zip(a[0].data, b[0].data):
+            assert tree_diff(ta.data, tb.data) is None
+        assert a[0].survived_scores == b[0].survived_scores
+        assert np.array_equal(a[1][1], b[1][1]) and a[1][2] == b[1][2] and a[2] == b[2]
+    assert out[3][0].fit_stats["rewinds"] > 0

@@ -25,6 +25,17 @@ def test_fit_is_independent_of_batch_size(name, cap):
     model_checks.check_fit_matches_reference(name, max_candidates_per_launch=cap)
 
 
+@pytest.mark.parametrize("name", ["titanic_c1", "mixed_feat", "mixed_nobest", "mixed_default"])
+@pytest.mark.parametrize("cap", [3, 4096])
+def test_fit_through_device_draw_plans_matches_reference(name, cap):
+    """The device-draw branch of the fit loop (row ids owned by the plan, stream states read back only
+    for a rewind, plans closed after their batch) on the fake plan -- the host walk behind the device
+    plan's interface: same forest, same consumed candidates, same RNG end states as the reference."""
+    before = fake_engine.FakeDrawPlan.created
+    model_checks.check_fit_matches_reference(name, device_draws=True, max_candidates_per_launch=cap)
+    assert fake_engine.FakeDrawPlan.created > before
+
+
 def test_persistence_and_merge():
     g, m = model_checks.fitted_model("mixed_default")
     model_checks.check_persistence_and_merge(g, m)
