@@ -32,7 +32,7 @@ def test_fit_through_device_draw_plans_matches_reference(name, cap):
     for a rewind, plans closed after their batch) on the fake plan -- the host walk behind the device
     plan's interface: same forest, same consumed candidates, same RNG end states as the reference."""
     before = fake_engine.FakeDrawPlan.created
-    model_checks.check_fit_matches_reference(name, device_draws=True, max_candidates_per_launch=cap)
+    model_checks.check_fit_matches_reference(name, device_draws=True, device_draw_min_slots=1, max_candidates_per_launch=cap)
     assert fake_engine.FakeDrawPlan.created > before
 
 
