@@ -66,6 +66,7 @@ typedef struct rfmc_dataset rfmc_dataset;
 typedef struct rfmc_batch rfmc_batch;
 typedef struct rfmc_forest rfmc_forest;
 typedef struct rfmc_drawplan rfmc_drawplan;
+typedef struct rfmc_gathered rfmc_gathered;
 
 int rfmc_abi_version(void);
 /* A non-blocking CUDA stream on `device` as an opaque pointer for the `stream` arguments below
@@ -263,6 +264,31 @@ int rfmc_drawplan_destroy(rfmc_drawplan* pl);
 int rfmc_batch_create_from_plan(rfmc_dataset* ds, rfmc_drawplan* pl, int32_t n_cand, const int32_t* cand_slot,
                                 const int32_t* feat_off, const uint16_t* feat_list, int32_t max_depth,
                                 int32_t min_samples_split, void* stream, rfmc_batch** out);
+
+/* ---- multi-GPU: the survivor exchange of the rank-sharded fit ---------------------------
+ * `self.data.extend(Tree_list)` (model.py:403) when the tree slots were grown by one process per GPU:
+ * every rank contributes the node tables of its surviving trees (packed back to back on its device by
+ * rfmc_batch_pack, dst_on_device = 1) and receives everybody's, in rank order.  nccl_comm is an
+ * ncclComm_t passed as void* (torch: ProcessGroupNCCL._comm_ptr()); NCCL is resolved at run time from
+ * the library that created it.  Sizes travel first, then the per-tree records (size, survived score,
+ * used-feature mask of mask_bytes bytes), then the node and count tables padded to the largest rank:
+ * four all-gathers, device to device.  tree_sizes / scores / masks are host arrays of this rank's
+ * n_trees trees; d_nodes / d_counts device arrays of n_nodes = sum(tree_sizes) entries.
+ * rfmc_gathered_describe  world, rank, per-rank tree and node counts ([world] each).
+ * rfmc_gathered_meta      rank r's tree sizes, scores, masks (host).
+ * rfmc_gathered_fetch     device -> host copy of rank r's node and count tables (they stay in HBM
+ *                         until somebody asks).
+ * rfmc_gathered_checksum  FNV-1a over every rank's sizes, scores and node bytes: equal on all ranks
+ *                         after a correct exchange.                                                  */
+int rfmc_allgather_survivors(void* nccl_comm, int device, const rfmc_node* d_nodes, const int32_t* d_counts, int64_t n_nodes,
+                             int32_t n_trees, const int64_t* tree_sizes, const double* scores, const uint8_t* masks,
+                             int32_t mask_bytes, int32_t n_classes, void* stream, rfmc_gathered** out);
+int rfmc_gathered_describe(rfmc_gathered* g, int32_t* world, int32_t* rank, int64_t* max_trees, int64_t* max_nodes,
+                           int64_t* trees_per_rank, int64_t* nodes_per_rank);
+int rfmc_gathered_meta(rfmc_gathered* g, int32_t r, int64_t* tree_sizes, double* scores, uint8_t* masks);
+int rfmc_gathered_fetch(rfmc_gathered* g, int32_t r, rfmc_node* nodes_out, int32_t* counts_out);
+int rfmc_gathered_checksum(rfmc_gathered* g, uint64_t* out);
+int rfmc_gathered_destroy(rfmc_gathered* g);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,58 @@ class GatheredBlock:
         return self._host
 
 
+class AbiGatheredBlock:
+    """Same role as GatheredBlock, over the C ABI's handle (rfmc_allgather_survivors): rank r's tables
+    are copied to the host the first time one of its trees is read."""
+
+    def __init__(self, handle):
+        self.handle = handle
+        self._host = {}
+
+    def host(self):
+        return self
+
+    def __getitem__(self, r):
+        if r not in self._host:
+            self._host[r] = self.handle.tables(r)
+        return self._host[r]
+
+
+def nccl_comm_ptr() -> int:
+    """The default process group's ncclComm_t (what rfmc_allgather_survivors takes)."""
+    import torch
+
+    td = _td()
+    backend = td.distributed_c10d._get_default_group()._get_backend(torch.device("cuda", torch.cuda.current_device()))
+    try:
+        return int(backend._comm_ptr())
+    except Exception:
+        td.barrier()  # the communicator is created lazily by the first collective
+        return int(backend._comm_ptr())
+
+
+def all_gather_trees_abi(trees, scores, n_classes, used_masks, dev_payload, device: int, stream=None):
+    """The survivor exchange through the C ABI (NCCL path): same result layout as all_gather_trees."""
+    from . import engine
+
+    sizes = np.array([t.n_nodes for t in trees], dtype=np.int64)
+    sc = np.array([float(s) for s in scores], dtype=np.float64)
+    nodes_ptr = dev_payload[0].data_ptr() if dev_payload is not None and int(sizes.sum()) else 0
+    counts_ptr = dev_payload[1].data_ptr() if dev_payload is not None and int(sizes.sum()) else 0
+    g = engine.GatheredSurvivors(nccl_comm_ptr(), device, nodes_ptr, counts_ptr, sizes, sc, used_masks, n_classes, stream)
+    block = AbiGatheredBlock(g)
+    out = []
+    for r in range(g.world):
+        r_sizes, r_scores, r_masks = g.meta(r)
+        at = 0
+        for k in range(len(r_sizes)):
+            s = int(r_sizes[k])
+            soa = trees[k] if r == g.rank else LazyTreeSoA(block, r, at, s)
+            out.append((soa, np.float64(r_scores[k]), r_masks[k] if g.mask_bytes else None))
+            at += s
+    return out, g
+
+
 class LazyTreeSoA:
     """TreeSoA interface over a slice of a GatheredBlock (materialised on first read)."""
 
@@ -223,7 +275,23 @@ def _gather_forest(model, local, recorder=None):
         for i, t in enumerate(local):
             for f in t.used_features:
                 masks[i, pos[f]] = 1
-    gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks, payload)
+    if _td().get_backend() == "nccl":
+        # NCCL: the exchange is the C ABI's (rfmc_allgather_survivors), device to device.  Every rank takes
+        # this branch; a rank whose tables are only on the host uploads them first.
+        import torch
+
+        dev_id = int(getattr(model, "device", 0) or 0)
+        if payload is None and len(local):
+            where = torch.device("cuda", dev_id)
+            nodes = np.concatenate([t.soa.nodes for t in local])
+            counts = np.concatenate([t.soa.counts for t in local])
+            payload = (torch.from_numpy(np.ascontiguousarray(nodes).view(np.uint8).reshape(-1)).to(where),
+                       torch.from_numpy(np.ascontiguousarray(counts).view(np.uint8).reshape(-1)).to(where))
+        gathered, handle = all_gather_trees_abi([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals),
+                                                masks, payload, dev_id)
+        model._last_gather = handle
+    else:
+        gathered = all_gather_trees([t.soa for t in local], [t.survived_score for t in local], len(model.class_vals), masks, payload)
     forest = []
     for soa, score, mask in gathered:
         t = model._wrap(soa, score)
@@ -274,15 +342,39 @@ def _fit_local(model, n_local: int, host_streams: int, seeds):
     return local, _merge_recorders(model._stream_hooks)
 
 
+def _agree_or_raise(error: Optional[BaseException]):
+    """Every rank learns whether some rank failed before the collective: a rank that died in its local
+    fit must not leave the others blocked in the all-gather."""
+    import torch
+
+    td = _td()
+    flag = torch.tensor([1 if error is not None else 0], dtype=torch.int32, device=_comm_device())
+    td.all_reduce(flag, op=td.ReduceOp.MAX)
+    if error is not None:
+        raise error
+    if int(flag.item()):
+        raise RuntimeError("rank-sharded fit: another rank failed in its local fit")
+
+
 def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
-    """Rank-sharded fit; every rank returns the full forest (list of DecisionTreeMC, rank order)."""
+    """Rank-sharded fit; every rank returns the full forest (list of DecisionTreeMC, rank order).
+    Without explicit ``rank_seeds`` the ranks seed themselves ``base + rank`` with ``base`` drawn from the
+    global numpy stream (ranks started under one np.random.seed would otherwise grow R copies of the
+    same trees)."""
     rank, world = rank_world()
     lo, hi = shard_bounds(model.n_trees, rank, world)
     seeds = rank_seeds if rank_seeds is not None else getattr(model, "rank_seeds", None)
-    if seeds is not None:
-        np.random.seed(seeds[rank])
-        _pyrandom.seed(seeds[rank])
-    local, recorder = _fit_local(model, hi - lo, 1, None)
+    if seeds is None:
+        base = int(np.random.randint(0, 2**31 - 1 - world))
+        seeds = [base + r for r in range(world)]
+    np.random.seed(seeds[rank])
+    _pyrandom.seed(seeds[rank])
+    local, recorder, error = [], None, None
+    try:
+        local, recorder = _fit_local(model, hi - lo, 1, None)
+    except BaseException as e:  # reported to every rank below
+        error = e
+    _agree_or_raise(error)
     return _gather_forest(model, local, recorder)
 
 
@@ -294,7 +386,12 @@ def fit_sharded_local(model, n_local: int, host_streams: int = 1, seeds=None):
         if host_streams > 1:
             return model._fit_slots_streams(n_local, list(seeds))
         return model._fit_slots(n_local)
-    local, recorder = _fit_local(model, n_local, host_streams, seeds)
+    local, recorder, error = [], None, None
+    try:
+        local, recorder = _fit_local(model, n_local, host_streams, seeds)
+    except BaseException as e:
+        error = e
+    _agree_or_raise(error)
     from time import perf_counter
 
     t0 = perf_counter()

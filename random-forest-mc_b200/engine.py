@@ -90,6 +90,12 @@ _SIGNATURES = {
     "rfmc_drawplan_kernel_ms": (C.c_int, [_p, _p]),
     "rfmc_drawplan_destroy": (C.c_int, [_p]),
     "rfmc_batch_create_from_plan": (C.c_int, [_p, _p, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
+    "rfmc_allgather_survivors": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int32, C.c_int32, _p, C.POINTER(_p)]),
+    "rfmc_gathered_describe": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _p, _p]),
+    "rfmc_gathered_meta": (C.c_int, [_p, C.c_int32, _p, _p, _p]),
+    "rfmc_gathered_fetch": (C.c_int, [_p, C.c_int32, _p, _p]),
+    "rfmc_gathered_checksum": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
+    "rfmc_gathered_destroy": (C.c_int, [_p]),
 }
 DRAW_MAX_PER_CLASS = 4096  # RFMC_DRAW_MAX_PER_CLASS
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -588,6 +594,63 @@ class GrowBatch:
     def close(self):
         if getattr(self, "_h", None):
             load_library().rfmc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GatheredSurvivors:
+    """rfmc_gathered handle: every rank's surviving trees after the NCCL exchange (fitParallel across
+    GPUs, model.py:403).  The node tables stay in HBM until ``tables(r)`` is called."""
+
+    def __init__(self, comm_ptr: int, device: int, nodes_ptr: int, counts_ptr: int, sizes: np.ndarray, scores: np.ndarray,
+                 masks: Optional[np.ndarray], n_classes: int, stream=None):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+        scores = np.ascontiguousarray(scores, dtype=np.float64)
+        masks = None if masks is None else np.ascontiguousarray(masks, dtype=np.uint8)
+        self.n_classes = int(n_classes)
+        self.mask_bytes = 0 if masks is None else int(masks.shape[1]) if masks.ndim == 2 else 0
+        h = _p()
+        _check(load_library().rfmc_allgather_survivors(
+            _p(comm_ptr), int(device), _p(nodes_ptr) if nodes_ptr else None, _p(counts_ptr) if counts_ptr else None, int(sizes.sum()),
+            len(sizes), _ptr(sizes), _ptr(scores), _ptr(masks) if self.mask_bytes else None, self.mask_bytes, self.n_classes,
+            _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        w, r, mt, mn = C.c_int32(0), C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        _check(load_library().rfmc_gathered_describe(h, C.byref(w), C.byref(r), C.byref(mt), C.byref(mn), None, None))
+        self.world, self.rank = w.value, r.value
+        self.trees_per_rank = np.zeros(self.world, dtype=np.int64)
+        self.nodes_per_rank = np.zeros(self.world, dtype=np.int64)
+        _check(load_library().rfmc_gathered_describe(h, None, None, None, None, _ptr(self.trees_per_rank), _ptr(self.nodes_per_rank)))
+
+    def meta(self, r: int):
+        """(tree sizes, survived scores, used-feature masks) of rank ``r``."""
+        nt = int(self.trees_per_rank[r])
+        sizes, scores = np.zeros(nt, dtype=np.int64), np.zeros(nt, dtype=np.float64)
+        masks = np.zeros((nt, self.mask_bytes), dtype=np.uint8)
+        _check(load_library().rfmc_gathered_meta(self._h, int(r), _ptr(sizes), _ptr(scores), _ptr(masks) if self.mask_bytes and nt else None))
+        return sizes, scores, masks
+
+    def tables(self, r: int):
+        """Device -> host copy of rank ``r``'s node and class-count tables."""
+        n = int(self.nodes_per_rank[r])
+        nodes = np.empty(n, dtype=NODE_DTYPE)
+        counts = np.empty((n, self.n_classes), dtype=np.int32)
+        _check(load_library().rfmc_gathered_fetch(self._h, int(r), _ptr(nodes), _ptr(counts)))
+        return nodes, counts
+
+    def checksum(self) -> int:
+        out = C.c_uint64(0)
+        _check(load_library().rfmc_gathered_checksum(self._h, C.byref(out)))
+        return int(out.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().rfmc_gathered_destroy(self._h)
             self._h = None
 
     def __del__(self):

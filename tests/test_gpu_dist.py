@@ -32,7 +32,23 @@ m.rank_seeds = [1000, 1001]
 m.fitParallel(g["frame"].copy(), disable_progress_bar=True)
 (lo, hi), labels = dist.predict_sharded(m, g["frames"]["nan"], want_probs=False)
 used = [sorted(t.used_features) for t in m.data]  # from the gathered masks, before any table is materialised
-out = dict(used=used, trees=[t.data for t in m.data], scores=[float(s) for s in m.survived_scores], lo=lo, hi=hi, labels=labels)
+# the exchange went through the C ABI (rfmc_allgather_survivors): every rank holds the same gathered tables
+h = torch.tensor([m._last_gather.checksum() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+hs = [torch.zeros_like(h) for _ in range(td.get_world_size())]
+td.all_gather(hs, h)
+# one slot for two ranks: rank 1 contributes nothing
+m1 = RandomForestMC(**dict(kw, n_trees=1))
+m1.device = local
+m1.rank_seeds = [1000, 1001]
+m1.fitParallel(g["frame"].copy(), disable_progress_bar=True)
+# two host streams per rank (the bench's layout): worker order inside a rank, rank order across
+m2 = RandomForestMC(**dict(kw, n_trees=4))
+m2.device = local
+m2.process_dataset(g["frame"].copy())
+f2 = dist.fit_sharded_local(m2, 4, 2, [2000 + 10 * td.get_rank(), 2001 + 10 * td.get_rank()])
+out = dict(used=used, trees=[t.data for t in m.data], scores=[float(s) for s in m.survived_scores], lo=lo, hi=hi, labels=labels,
+           checksums=[int(x.item()) for x in hs], one=[t.data for t in m1.data], streams=[t.data for t in f2],
+           stream_scores=[float(t.survived_score) for t in f2])
 with open(os.path.join({tmp!r}, "rank%d.pkl" % td.get_rank()), "wb") as f:
     pickle.dump(out, f)
 td.destroy_process_group()
@@ -86,3 +102,18 @@ def test_sharded_fit_over_nccl_world2():
     fr = g["frames"]["nan"]
     want = orc.forest_labels(want_trees, want_scores, g["class_vals"], fr, False, False)
     assert out[0]["labels"] + out[1]["labels"] == want
+    for r in range(2):
+        assert out[r]["checksums"][0] == out[r]["checksums"][1]
+        assert len(out[r]["one"]) == 1 and tree_diff(out[r]["one"][0], want_trees[0]) is None
+    # host streams: rank r stream w == the serial algorithm on 2 slots under seed 2000 + 10 r + w
+    want_streams = []
+    for seed in (2000, 2001, 2010, 2011):
+        ds = orc.ingest(g["frame"].copy(), target_col=kw["target_col"])
+        np.random.seed(seed)
+        random.seed(seed)
+        t, s, _ = orc.fit(ds, 2, max_discard_trees=kw["max_discard_trees"])
+        want_streams += t
+    for r in range(2):
+        assert len(out[r]["streams"]) == 8
+        for a, b in zip(out[r]["streams"], want_streams):
+            assert tree_diff(a, b) is None
