@@ -12,7 +12,12 @@
  *   - the caller owns host buffers (contiguous, little-endian); the library owns device memory
  *     behind opaque handles; a handle is bound to one CUDA device;
  *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream);
- *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails;
+ *   - threads: handles may be used from any thread.  Host-buffer voting calls on ONE rfmc_forest
+ *     (rfmc_forest_predict with on_device = 0, rfmc_forest_predict_frame) share its pinned staging and
+ *     take turns under a per-forest lock; device-pointer calls run on the caller's stream and need
+ *     no lock.  A batch / draw plan belongs to the thread (and stream) that drives it; create and
+ *     destroy of different handles are safe concurrently (device blocks come from a locked pool).
  *
  * Encoding contract (random-forest-mc_b200/encode.py): feature values are dense rank codes, code 0 =
  * missing/unseen; numeric columns carry a sorted float64 value table; class labels are coded by

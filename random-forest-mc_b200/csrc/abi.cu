@@ -169,6 +169,18 @@ struct PredictPipe {
     long launches = 0;
 };
 
+// One pipe (streams, events, pinned staging) per forest: host-buffer voting calls on the same forest
+// from several threads take turns (ctypes releases the GIL); device-pointer calls do not use the pipe.
+struct PipeLease {
+    rfmc_forest* f;
+    explicit PipeLease(rfmc_forest* forest) : f(forest) {
+        f->pipe_mu.lock();
+        if (!f->pipe) f->pipe = new PredictPipe();
+    }
+    ~PipeLease() { f->pipe_mu.unlock(); }
+    PredictPipe* get() const { return f->pipe; }
+};
+
 static int pipe_reserve(PredictPipe* p, size_t in_bytes, size_t probs_bytes, size_t labels_bytes) {
     for (int i = 0; i < 2; ++i) {
         if (!p->st[i]) RFMC_CUDA(cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking));
@@ -887,8 +899,8 @@ int rfmc_forest_predict(rfmc_forest* f, const void* codes, int code_width, int64
         return rc;
     }
     cudaStreamSynchronize(st);
-    PredictPipe* pp = f->pipe;
-    if (!pp) pp = f->pipe = new PredictPipe();
+    PipeLease lease(f);
+    PredictPipe* pp = lease.get();
     const size_t row_bytes = (size_t)row_stride * code_width;
     const int64_t chunk_rows = 32768;
     if (pipe_reserve(pp, chunk_rows * row_bytes, probs_out ? chunk_rows * C * sizeof(double) : 0,
@@ -988,8 +1000,8 @@ int rfmc_forest_predict_frame(rfmc_forest* f, int64_t n_rows, int32_t n_features
         for (int i = 0; i < n_features; ++i) has_absent |= absent[i] != 0;
     const size_t C = (size_t)f->n_classes;
     const size_t row_bytes = (size_t)row_stride * code_width;
-    PredictPipe* pp = f->pipe;
-    if (!pp) pp = f->pipe = new PredictPipe();
+    PipeLease lease(f);
+    PredictPipe* pp = lease.get();
     if (pipe_reserve(pp, chunk_rows * row_bytes, probs_out ? chunk_rows * C * sizeof(double) : 0,
                      labels_out ? chunk_rows * sizeof(int32_t) : 0) ||
         pipe_reserve_raw(pp, raw_bytes))

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -156,6 +157,7 @@ struct rfmc_forest {
     double* d_scores = nullptr;
     int sm_count = 0;
     PredictPipe* pipe = nullptr;  // pinned staging + streams of the host-buffer voting path
+    std::mutex pipe_mu;           // one host-buffer voting call at a time per forest
     uint4* d_blocks = nullptr;       // blocked 8-byte-node layout for the vote kernel (nullptr: not eligible)
     uint32_t* d_root_b = nullptr;
     int64_t n_blocks = 0;

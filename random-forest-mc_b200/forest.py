@@ -48,6 +48,28 @@ def _reaches_marked(t: ForestTables, row_codes, absent, marked) -> bool:
     return False
 
 
+class _ForestKey:
+    """What the device copy of a forest was flattened from.  The trees themselves are held (an id() of a
+    collected tree can come back on a new one), together with the version of each tree's dict: a forest
+    rebuilt by reset_forest() + fit(), dict2model() or an assignment to ``tree.data`` is a different key."""
+
+    def __init__(self, trees, scores, class_vals):
+        self.trees = list(trees)
+        self.versions = [getattr(t, "_version", 0) for t in self.trees]
+        self.materialised = [getattr(t, "_data", True) is not None for t in self.trees]
+        self.scores = tuple(float(s) for s in scores)
+        self.class_vals = tuple(class_vals)
+
+    def same(self, other: "_ForestKey") -> bool:
+        return (
+            len(self.trees) == len(other.trees)
+            and all(a is b for a, b in zip(self.trees, other.trees))
+            and self.versions == other.versions
+            and self.scores == other.scores
+            and self.class_vals == other.class_vals
+        )
+
+
 class BaseRandomForestMC(UserList):
     typer_error_msg = "Both objects must be instances of 'RandomForestMC' class."
 
@@ -193,23 +215,32 @@ class BaseRandomForestMC(UserList):
         default one."""
         if len(self.data) == 0:
             raise ZeroDivisionError("the forest is empty")
-        key = (tuple(id(t) for t in self.data), tuple(float(s) for s in self.survived_scores), tuple(self.class_vals))
-        if f32_feats:
-            hit = self._forest_f32
-            if hit is None or hit[0] != (key, f32_feats):
-                if hit is not None:
-                    hit[1].close()
-                tables = self._flatten(f32_feats)
-                hit = self._forest_f32 = ((key, f32_feats), engine.DeviceForest(tables, self.device), tables)
-            return hit[1]
-        if key != self._forest_key or self._forest_dev is None:
-            if self._forest_dev is not None:
-                self._forest_dev.close()
-            tables = self._flatten()
-            self._forest_dev = engine.DeviceForest(tables, self.device)
-            self._forest_tables = tables
-            self._forest_key = key
-        return self._forest_dev
+        with self._forest_lock():
+            key = _ForestKey(self.data, self.survived_scores, self.class_vals)
+            if f32_feats:
+                hit = self._forest_f32
+                if hit is None or hit[0][1] != f32_feats or not key.same(hit[0][0]):
+                    if hit is not None:
+                        hit[1].close()
+                    tables = self._flatten(f32_feats)
+                    hit = self._forest_f32 = ((key, f32_feats), engine.DeviceForest(tables, self.device), tables)
+                return hit[1]
+            if self._forest_dev is None or self._forest_key is None or not key.same(self._forest_key):
+                if self._forest_dev is not None:
+                    self._forest_dev.close()
+                tables = self._flatten()
+                self._forest_dev = engine.DeviceForest(tables, self.device)
+                self._forest_tables = tables
+                self._forest_key = key
+            return self._forest_dev
+
+    def _forest_lock(self):
+        lock = self.__dict__.get("_forest_mutex")
+        if lock is None:
+            import threading
+
+            lock = self.__dict__.setdefault("_forest_mutex", threading.RLock())
+        return lock
 
     def _flatten(self, f32_feats=frozenset()) -> ForestTables:
         from .flat import forest_tables_from_soa

@@ -297,7 +297,7 @@ class RandomForestMC(BaseRandomForestMC):
     # -- pickling / copy.deepcopy (the reference model is a plain picklable object; joblib.dump(model) is common) --
     def __getstate__(self):
         state = self.__dict__.copy()
-        for key in ("_tls", "_dev_dataset", "_forest_dev", "_forest_f32", "_stream_hooks"):
+        for key in ("_tls", "_dev_dataset", "_forest_dev", "_forest_f32", "_stream_hooks", "_forest_mutex", "_last_gather"):
             state.pop(key, None)
         state["_forest_key"] = None
         state["_forest_tables"] = None

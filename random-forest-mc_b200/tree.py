@@ -71,6 +71,7 @@ class DecisionTreeMC(UserDict):
     def data(self, value) -> None:
         self._data = value
         self._soa = None
+        self._version = getattr(self, "_version", 0) + 1  # the device copy of a forest notices the new dict
 
     @property
     def soa(self) -> Optional[TreeSoA]:

@@ -136,3 +136,32 @@ def test_fit_parallel_host_streams_contract():
 
 def test_pickle_and_deepcopy():
     model_checks.check_pickle_and_deepcopy()
+
+
+def test_device_forest_follows_the_trees_not_their_ids():
+    """The cached device copy of the forest is keyed on the tree objects themselves (held, compared with
+    `is`) and on the version of each tree's dict: a forest rebuilt with equal scores, or a tree whose
+    dict was replaced, must vote with the new trees (a freed tree's id() can come back on a new one)."""
+    import gc
+
+    g, m = model_checks.fitted_model("titanic_c1")
+    frame = g["frames"]["clean"]
+    from random_forest_mc_b200.tree import DecisionTreeMC
+
+    def one_tree_model(tree_dict):
+        m.data = [DecisionTreeMC(tree_dict, m.class_vals, survived_score=1.0, features=m.feature_cols)]
+        m.survived_scores = [1.0]
+        return m.testForestProbs(frame)
+
+    seen = []
+    for ref in g["forest"][:4]:
+        seen.append(one_tree_model(ref))
+        gc.collect()  # the previous single tree is garbage now: its id is free to be reused
+    from oracle import rfmc_oracle as orc
+
+    for ref, got in zip(g["forest"][:4], seen):
+        want = orc.forest_probs([ref], [1.0], g["class_vals"], frame, False, False)
+        assert got == want
+    # replacing a tree's dict in place of the same object
+    m.data[0].data = g["forest"][0]
+    assert m.testForestProbs(frame) == orc.forest_probs([g["forest"][0]], [1.0], g["class_vals"], frame, False, False)
