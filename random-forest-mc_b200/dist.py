@@ -356,11 +356,17 @@ def _agree_or_raise(error: Optional[BaseException]):
         raise RuntimeError("rank-sharded fit: another rank failed in its local fit")
 
 
-def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
+def stream_seeds(rank_seed: int, host_streams: int):
+    """Seeds of the host RNG streams of one rank (worker w of rank r == the serial algorithm under it)."""
+    return [(int(rank_seed) * 1009 + 7919 * w) % (2**31 - 1) for w in range(host_streams)]
+
+
+def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None, host_streams: int = 1):
     """Rank-sharded fit; every rank returns the full forest (list of DecisionTreeMC, rank order).
     Without explicit ``rank_seeds`` the ranks seed themselves ``base + rank`` with ``base`` drawn from the
     global numpy stream (ranks started under one np.random.seed would otherwise grow R copies of the
-    same trees)."""
+    same trees).  ``host_streams`` > 1: the rank's slots are shared over that many independent host RNG
+    streams (seeds: ``stream_seeds``), worker order inside the rank."""
     rank, world = rank_world()
     lo, hi = shard_bounds(model.n_trees, rank, world)
     seeds = rank_seeds if rank_seeds is not None else getattr(model, "rank_seeds", None)
@@ -369,13 +375,20 @@ def fit_sharded(model, rank_seeds: Optional[Sequence[int]] = None):
         seeds = [base + r for r in range(world)]
     np.random.seed(seeds[rank])
     _pyrandom.seed(seeds[rank])
+    host_streams = max(1, min(int(host_streams or 1), hi - lo))
     local, recorder, error = [], None, None
     try:
-        local, recorder = _fit_local(model, hi - lo, 1, None)
+        local, recorder = _fit_local(model, hi - lo, host_streams, stream_seeds(seeds[rank], host_streams))
     except BaseException as e:  # reported to every rank below
         error = e
     _agree_or_raise(error)
-    return _gather_forest(model, local, recorder)
+    from time import perf_counter
+
+    t0 = perf_counter()
+    forest = _gather_forest(model, local, recorder)
+    if isinstance(getattr(model, "fit_stats", None), dict):
+        model.fit_stats["t_gather"] = perf_counter() - t0
+    return forest
 
 
 def fit_sharded_local(model, n_local: int, host_streams: int = 1, seeds=None):

@@ -717,7 +717,7 @@ class RandomForestMC(BaseRandomForestMC):
         from . import dist
 
         if dist.is_distributed():
-            Forest = dist.fit_sharded(self)
+            Forest = dist.fit_sharded(self, host_streams=max_workers or 1)
         else:
             k = max_workers or min(16, os.cpu_count() or 1)  # the reference's pool defaults to one worker per core
             k = max(1, min(int(k), self.n_trees))

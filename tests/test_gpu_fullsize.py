@@ -108,3 +108,24 @@ def test_fit_is_independent_of_launch_cap_and_frame_encoder_agrees(big):
     m.setWeightedTrees(False)
     acc = np.mean(np.array(m.testForest(part)) == frame["target"].to_numpy()[:50_000])
     assert acc > 0.27  # 4 trees of median splits on a noisy 4-class target: above chance (0.25)
+
+
+def test_benched_shape_candidates_equal_the_code_model(big):
+    """Two candidates of the bench's own shape (C2b: 8,000 bootstrap rows + 2,000 hold-out rows out of the
+    1M x 64 frame, up to 64 features) array-for-array against oracle/code_model.py, scores included."""
+    from oracle import code_model as cm
+
+    frame, m = big
+    np.random.seed(11)
+    random.seed(11)
+    plan = m._draw_plan(1, 2)
+    batch, first = m._grow_plan(plan)
+    correct, n_nodes = batch.results()
+    trees = batch.fetch([0, 1])
+    idx_T, idx_V = m._slot_rows(plan[0])
+    assert len(idx_T) == 8000 and len(idx_V) == 2000
+    for k in range(2):
+        nodes, counts = cm.grow_codes(m.encoded, idx_T, plan[0][2][k], m.max_depth, m.min_samples_split)
+        assert np.array_equal(trees[k].nodes, nodes) and np.array_equal(trees[k].counts, counts)
+        assert correct[k] == cm.score_codes(m.encoded, nodes, counts, idx_V)
+    batch.close()
