@@ -251,7 +251,8 @@ static void pipe_destroy(PredictPipe* p) {
 // `next` is the block of ITS '>=' child (the '<' child is the next block).  Returns false when the
 // forest is not eligible (codes or feature ids too wide), in which case the 16-byte nodes are used.
 static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t* roots, int32_t n_trees,
-                         std::vector<uint32_t>& out, std::vector<uint32_t>& root_b) {
+                         std::vector<uint32_t>& out, std::vector<uint32_t>& root_b, std::vector<uint32_t>& block_of) {
+    block_of.assign((size_t)n_nodes, 0xFFFFFFFFu);  // node -> the block that holds it in slot 0 (even depths only)
     for (int64_t i = 0; i < n_nodes; ++i) {
         const rfmc_pnode& n = nodes[i];
         if (n.feat_flags & RFMC_PNODE_LEAF) continue;
@@ -279,6 +280,7 @@ static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t
         for (size_t q = 0; q < queue.size(); ++q) {
             const uint32_t ni = queue[q].first, bi = queue[q].second;
             const rfmc_pnode& p = nodes[ni];
+            block_of[ni] = bi;
             out[(size_t)bi * 8 + 0] = rec_lo(p);
             if (p.feat_flags & RFMC_PNODE_LEAF) {
                 out[(size_t)bi * 8 + 1] = p.thr;  // payload
@@ -301,6 +303,39 @@ static bool build_blocks(const rfmc_pnode* nodes, int64_t n_nodes, const int64_t
         }
     }
     return true;
+}
+
+// The top `levels` levels (even) of every tree as an implicit heap of 8-byte records for
+// predict_top_kernel: slot 0 the root, children of slot i in 2i+1 ('>=') and 2i+2 ('<').  A leaf carries
+// its payload; a split of the LAST staged level carries the block of its '>=' child in the blocked
+// layout (the '<' child's block follows it), where the walk continues.
+static void build_tops(const rfmc_pnode* nodes, const int64_t* roots, int32_t n_trees, int levels,
+                       const std::vector<uint32_t>& block_of, std::vector<uint32_t>& out) {
+    const size_t heap_n = ((size_t)1 << levels) - 1, heap_pad = (heap_n + 2) & ~(size_t)1;
+    out.assign((size_t)n_trees * heap_pad * 2, 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> todo;  // (node, heap slot)
+    for (int32_t t = 0; t < n_trees; ++t) {
+        uint32_t* heap = out.data() + (size_t)t * heap_pad * 2;
+        todo.clear();
+        todo.emplace_back((uint32_t)roots[t], 0u);
+        for (size_t q = 0; q < todo.size(); ++q) {
+            const uint32_t ni = todo[q].first, hi = todo[q].second;
+            const rfmc_pnode& p = nodes[ni];
+            if (p.feat_flags & RFMC_PNODE_LEAF) {
+                heap[2 * hi] = 0x8000u;
+                heap[2 * hi + 1] = p.thr;
+                continue;
+            }
+            const uint32_t thr = p.thr == 0xFFFFFFFFu ? 0xFFFFu : p.thr;
+            heap[2 * hi] = (p.feat_flags & 0x3FFFu) | ((p.feat_flags & RFMC_PNODE_CATEGORICAL) ? 0x4000u : 0u) | (thr << 16);
+            if (2 * (size_t)hi + 2 < heap_n) {
+                todo.emplace_back(p.child, 2 * hi + 1);
+                todo.emplace_back(p.child + 1, 2 * hi + 2);
+            } else {
+                heap[2 * hi + 1] = block_of[p.child];
+            }
+        }
+    }
 }
 
 extern "C" {
@@ -827,11 +862,21 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
     rc |= upload(&f->d_probs, probs, (size_t)n_payloads * n_classes, 0);
     rc |= upload(&f->d_probs_absent, probs_absent, (size_t)n_payloads * n_classes, 0);
     rc |= upload(&f->d_scores, scores, (size_t)n_trees, 0);
-    std::vector<uint32_t> blocks, root_b;  // must outlive the asynchronous uploads below
-    if (!rc && build_blocks(nodes, n_nodes, tree_root, n_trees, blocks, root_b)) {
+    std::vector<uint32_t> blocks, root_b, block_of, tops;  // must outlive the asynchronous uploads below
+    if (!rc && build_blocks(nodes, n_nodes, tree_root, n_trees, blocks, root_b, block_of)) {
         f->n_blocks = (int64_t)(blocks.size() / 8);
         rc |= upload((uint32_t**)&f->d_blocks, blocks.data(), blocks.size(), 0);
         rc |= upload(&f->d_root_b, root_b.data(), root_b.size(), 0);
+        // staged levels: enough for the average tree, at most ten (8 KB per tree), always even
+        int levels = 2;
+        while (levels < 10 && ((int64_t)1 << levels) < 2 * (n_nodes / n_trees + 1)) levels += 2;
+        if (const char* e = getenv("RFMC_PRED_TOP_LEVELS")) {
+            const int want = atoi(e) & ~1;
+            if (want >= 2 && want <= 12) levels = want;
+        }
+        build_tops(nodes, tree_root, n_trees, levels, block_of, tops);
+        f->top_levels = levels;
+        rc |= upload((uint32_t**)&f->d_tops, tops.data(), tops.size(), 0);
     }
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) {
         set_error("forest upload failed");
@@ -858,6 +903,7 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     pipe_destroy(f->pipe);
     release(f->d_blocks);
     release(f->d_root_b);
+    release(f->d_tops);
     release(f->d_thresholds);
     release(f->d_thr_off);
     delete f;

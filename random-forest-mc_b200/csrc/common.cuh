@@ -161,6 +161,8 @@ struct rfmc_forest {
     uint4* d_blocks = nullptr;       // blocked 8-byte-node layout for the vote kernel (nullptr: not eligible)
     uint32_t* d_root_b = nullptr;
     int64_t n_blocks = 0;
+    uint2* d_tops = nullptr;  // per tree: the top `top_levels` levels as an implicit heap of 8-byte records
+    int32_t top_levels = 0;
     double* d_thresholds = nullptr;  // code book of the frame encoder (rfmc_forest_set_codebook)
     int64_t* d_thr_off = nullptr;
     int32_t n_features_book = 0;

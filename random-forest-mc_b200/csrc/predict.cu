@@ -15,6 +15,8 @@
 // Missing values (tree.py:166-181): a NaN / unseen cell is code 0 and fails both tests -> '<'.
 // A column absent from the frame takes '>=' and switches the leaf payload to the renormalised
 // variant the host precomputed (tree.py:201-210).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rfmc {
@@ -34,6 +36,8 @@ struct PredictArgs {
     const int64_t* root;
     const uint4* blocks;     // blocked layout (nullptr: walk `nodes`)
     const uint32_t* root_b;  // block of every tree's root
+    const uint2* tops;       // every tree's top `top_levels` levels as an implicit heap of 8-byte records
+    int32_t top_levels;      // even, >= 2 (0: no tops)
     int32_t n_trees;
     const uint8_t* vote;
     const uint8_t* vote_absent;
@@ -232,10 +236,231 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_kernel(PredictArgs a) {
     if (a.labels_out) a.labels_out[row] = best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vote kernel with the tree tops in shared memory (EXPERIMENT, opt-in with RFMC_PRED_TOPS=1: measured
+// 0.64x / 0.99x of the kernel above on the C2b / C5 forests, see profiles/r2_vote_staged_tops.md -- the walk
+// is bound by the two dependent loads per level and the issue slots around them, not by where the node
+// records live).
+//
+// The kernel above asks L2 (through the L1 tags) for one 32-byte sector per lane every two tree levels:
+// that request stream is its limit (ncu: l1tex throughput 91 %), not HBM.  Here the first `top_levels`
+// levels of every tree are laid out by the host as an implicit heap of 8-byte records (same record as the
+// blocked layout: {feat | cat << 14 | leaf << 15 | thr << 16, payload or next block}); a CTA of 256 rows
+// stages the heaps of four trees at a time with 16-byte cp.async copies (double-buffered: the copy of the
+// next four overlaps the walk of these four), every thread walks the top levels of its four trees out of
+// shared memory -- children of heap slot i are 2i+1 / 2i+2, no pointer to chase -- and only what lies below
+// the staged levels is fetched from global memory, entering the blocked layout at the record's `next`.  A
+// tree of the default configuration (~70 nodes, depth 7-8) is walked without a single global request; a
+// tree grown to purity on 8,000 rows (depth 16-17) keeps its last ~4 levels global.  Staging costs
+// heap bytes / 256 rows per (row, tree): 32 B for ten levels, against ~7 x 32 B of sector requests.
+// Accumulation is unchanged: leaves are consumed in forest order, fp64, multiply and add separate.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOP_THREADS = 256;
+constexpr int TOP_GROUP = 4;  // trees staged and walked together
+
+template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT>
+__global__ void __launch_bounds__(TOP_THREADS) predict_top_kernel(PredictArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int heap_n = (1 << a.top_levels) - 1;
+    const int heap_pad = (heap_n + 2) & ~1;  // records per staged tree, 16-byte multiple
+    uint2* stage = reinterpret_cast<uint2*>(smem_raw);  // [2][TOP_GROUP][heap_pad]
+    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw + (size_t)2 * TOP_GROUP * heap_pad * sizeof(uint2));
+    uint8_t* s_absent = reinterpret_cast<uint8_t*>(tile) + (size_t)TOP_THREADS * a.stride * sizeof(CodeT);
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * TOP_THREADS;
+    const int rows = (int)((a.n_rows - row0) < TOP_THREADS ? (a.n_rows - row0) : TOP_THREADS);
+    const CodeT* gcodes = reinterpret_cast<const CodeT*>(a.codes) + row0 * a.stride;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gcodes);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
+        const int words = (int)((size_t)rows * a.stride * sizeof(CodeT) / 4);
+        for (int i = tid; i < words; i += TOP_THREADS) dst[i] = __ldg(&src[i]);
+    }
+    if (HAS_ABSENT)
+        for (int i = tid; i < a.n_features; i += TOP_THREADS) s_absent[i] = a.absent[i];
+
+    auto stage_group = [&](int t0, int buf) {  // heaps of trees t0 .. t0+3 -> stage[buf]
+        const int n_tr = a.n_trees - t0 < TOP_GROUP ? a.n_trees - t0 : TOP_GROUP;
+        const int per_tree = heap_pad / 2;  // 16-byte pieces
+        const uint4* src = reinterpret_cast<const uint4*>(a.tops + (size_t)t0 * heap_pad);
+        uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)buf * TOP_GROUP * heap_pad);
+        for (int i = tid; i < n_tr * per_tree; i += TOP_THREADS) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + i));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    const bool live = tid < rows;
+    const CodeT* myrow = tile + (size_t)(live ? tid : 0) * a.stride;
+    const int C = a.n_classes;
+    double acc[CMAX];
+    uint32_t cnt[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        acc[c] = 0.0;
+        cnt[c] = 0;
+    }
+    stage_group(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < a.n_trees; t0 += TOP_GROUP, buf ^= 1) {
+        if (t0 + TOP_GROUP < a.n_trees) {
+            stage_group(t0 + TOP_GROUP, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();  // this group's heaps (and, the first time, the row tile) are in shared memory
+        const uint2* heaps = stage + (size_t)buf * TOP_GROUP * heap_pad;
+        uint32_t node[TOP_GROUP], pay[TOP_GROUP], idx[TOP_GROUP];
+        bool done[TOP_GROUP], seen[TOP_GROUP];
+#pragma unroll
+        for (int k = 0; k < TOP_GROUP; ++k) {
+            done[k] = !(t0 + k < a.n_trees);
+            seen[k] = false;
+            pay[k] = 0u;
+            idx[k] = 0u;
+            node[k] = 0u;
+        }
+        // the staged levels: four independent chains of shared-memory loads per thread
+        for (int d = 0; d < a.top_levels; ++d) {
+            const bool last = d + 1 == a.top_levels;
+#pragma unroll
+            for (int k = 0; k < TOP_GROUP; ++k) {
+                if (done[k]) continue;
+                const uint2 rec = heaps[(size_t)k * heap_pad + idx[k]];
+                if (rec.x & 0x8000u) {
+                    pay[k] = rec.y;
+                    done[k] = true;
+                    continue;
+                }
+                const uint32_t f = rec.x & 0x3FFFu;
+                const uint32_t cv = (uint32_t)myrow[f];
+                bool go = (rec.x & 0x4000u) ? (cv == (rec.x >> 16)) : (cv >= (rec.x >> 16));
+                if (HAS_ABSENT) {
+                    const bool ab = s_absent[f] != 0;
+                    go = go || ab;
+                    seen[k] = seen[k] || ab;
+                }
+                if (last)
+                    node[k] = rec.y + (go ? 0u : 1u);  // below the staged levels: the child's block in global memory
+                else
+                    idx[k] = 2u * idx[k] + (go ? 1u : 2u);
+            }
+        }
+        // what is left of the deep trees: the blocked layout, two levels per 32-byte request
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < TOP_GROUP; ++k) any = any || !done[k];
+        uint4 b0[TOP_GROUP], b1[TOP_GROUP];
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int k = 0; k < TOP_GROUP; ++k)
+                if (!done[k]) ldg256(a.blocks + 2 * (size_t)node[k], b0[k], b1[k]);
+#pragma unroll
+            for (int k = 0; k < TOP_GROUP; ++k) {
+                if (done[k]) continue;
+                const uint32_t p_lo = b0[k].x;
+                if (p_lo & 0x8000u) {
+                    pay[k] = b0[k].y;
+                    done[k] = true;
+                    continue;
+                }
+                uint32_t f = p_lo & 0x3FFFu;
+                uint32_t cv = (uint32_t)myrow[f];
+                bool go = (p_lo & 0x4000u) ? (cv == (p_lo >> 16)) : (cv >= (p_lo >> 16));
+                if (HAS_ABSENT) {
+                    const bool ab = s_absent[f] != 0;
+                    go = go || ab;
+                    seen[k] = seen[k] || ab;
+                }
+                const uint32_t x_lo = go ? b0[k].z : b1[k].x, x_hi = go ? b0[k].w : b1[k].y;
+                if (x_lo & 0x8000u) {
+                    pay[k] = x_hi;
+                    done[k] = true;
+                    continue;
+                }
+                f = x_lo & 0x3FFFu;
+                cv = (uint32_t)myrow[f];
+                go = (x_lo & 0x4000u) ? (cv == (x_lo >> 16)) : (cv >= (x_lo >> 16));
+                if (HAS_ABSENT) {
+                    const bool ab = s_absent[f] != 0;
+                    go = go || ab;
+                    seen[k] = seen[k] || ab;
+                }
+                node[k] = x_hi + (go ? 0u : 1u);
+                any = true;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TOP_GROUP; ++k) {
+            const int t = t0 + k;
+            if (t >= a.n_trees) break;
+            const uint32_t payload = pay[k];
+            if (MODE == 0 || MODE == 1) {
+                const int v = (HAS_ABSENT && seen[k]) ? a.vote_absent[payload] : a.vote[payload];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
+                } else {
+                    const double sc = __ldg(&a.scores[t]);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) acc[c] = __dadd_rn(acc[c], (c == v) ? sc : 0.0);
+                }
+            } else {
+                const double* p = ((HAS_ABSENT && seen[k]) ? a.probs_absent : a.probs) + (size_t)payload * C;
+                if (MODE == 2) {
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c)
+                        if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+                } else {
+                    const double sc = __ldg(&a.scores[t]);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c)
+                        if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), sc));
+                }
+            }
+        }
+        __syncthreads();  // everybody is done with stage[buf] before the copy after next overwrites it
+    }
+    if (!live) return;
+    const double denom = (MODE == 0 || MODE == 2) ? (double)a.n_trees : a.score_fsum;
+    const int64_t row = row0 + tid;
+    int best = 0;
+    double bestv = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            const double num = (MODE == 0) ? (double)cnt[c] : acc[c];
+            const double v = __ddiv_rn(num, denom);
+            if (a.probs_out) a.probs_out[row * C + c] = v;
+            if (c == 0 || v > bestv) {  // first maximum in class_vals order (forest.py:200-202)
+                bestv = v;
+                best = c;
+            }
+        }
+    }
+    if (a.labels_out) a.labels_out[row] = best;
+}
+
 template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT>
 static int launch_tile(const PredictArgs& a, cudaStream_t stream) {
+    if (a.n_rows == 0) return 0;
+    if (a.tops != nullptr && a.blocks != nullptr && a.top_levels >= 2) {
+        const int heap_pad = ((1 << a.top_levels) + 1) & ~1;
+        const size_t smem = (size_t)2 * TOP_GROUP * heap_pad * sizeof(uint2) + (size_t)TOP_THREADS * a.stride * sizeof(CodeT) +
+                            (HAS_ABSENT ? (size_t)((a.n_features + 15) / 16 * 16) : 0);
+        if (smem <= 110 * 1024) {  // two CTAs per SM
+            auto k = predict_top_kernel<CodeT, CMAX, MODE, HAS_ABSENT>;
+            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<(unsigned)((a.n_rows + TOP_THREADS - 1) / TOP_THREADS), TOP_THREADS, smem, stream>>>(a);
+            RFMC_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const int64_t blocks = (a.n_rows + PRED_THREADS - 1) / PRED_THREADS;
-    if (blocks == 0) return 0;
     size_t tile_bytes = (size_t)PRED_THREADS * a.stride * sizeof(CodeT);
     size_t extra = HAS_ABSENT ? (size_t)((a.n_features + 15) / 16 * 16) : 0;
     if (tile_bytes + extra <= 200 * 1024) {
@@ -312,6 +537,8 @@ int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n
     a.root = f->d_root;
     a.blocks = nullptr;
     a.root_b = nullptr;
+    a.tops = nullptr;
+    a.top_levels = 0;
     a.n_trees = f->n_trees;
     a.vote = f->d_vote;
     a.vote_absent = f->d_vote_absent;
@@ -347,6 +574,9 @@ int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t 
     a.root = f->d_root;
     a.blocks = (code_width <= 2) ? f->d_blocks : nullptr;
     a.root_b = f->d_root_b;
+    // measured slower than the all-global blocked walk on B200 (profiles/r2_vote_staged_tops.md): opt-in only
+    a.tops = (a.blocks != nullptr && getenv("RFMC_PRED_TOPS")) ? f->d_tops : nullptr;
+    a.top_levels = f->top_levels;
     a.n_trees = f->n_trees;
     a.vote = f->d_vote;
     a.vote_absent = f->d_vote_absent;
