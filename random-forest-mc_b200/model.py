@@ -168,7 +168,8 @@ class RandomForestMC(BaseRandomForestMC):
         # resolve helpers of the host RNG walk: the sequential part (MT19937 blocks + rejection) is the
         # floor; two helpers keep up with it.  A producer thread for the blocks is opt-in only: since
         # the blocks are generated with AVX-512 the cache-to-cache hand-off costs more than it saves.
-        self.rng_threads = max(0, min(2, (os.cpu_count() or 1) - 1))
+        ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        self.rng_threads = max(0, min(2, (os.cpu_count() or 1) // ranks_here - 1))
         self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"
         self.gil_switch_interval = float(os.environ.get("RFMC_GIL_SWITCH_INTERVAL", "1e-4"))  # seconds, host-stream fits only
         # numpy's stream can be walked on the GPU (csrc/rng_walk.cu: same rows, counts and stream states, row
@@ -591,8 +592,10 @@ class RandomForestMC(BaseRandomForestMC):
                 self._tls.pack_hook = self._stream_hooks[r]
                 self._tls.np_rng = np.random.RandomState(int(seeds[r]))
                 self._tls.py_rng = _pyrandom.Random(int(seeds[r]))
-                # one resolve helper per stream while there are cores for it; no producer thread
-                self._tls.rng_flags = 1 if 2 * k <= (os.cpu_count() or 1) else 0
+                # one resolve helper per stream while there are cores for it (the box's cores are shared by the
+                # ranks of a multi-GPU run); no producer thread
+                ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+                self._tls.rng_flags = 1 if 2 * k * ranks_here <= (os.cpu_count() or 1) else 0
                 lo, hi = shard_bounds(n_slots, r, k)
                 parts[r] = self._fit_slots(hi - lo, stream) if hi > lo else []
                 stats[r] = getattr(self._tls, "last_stats", None)
