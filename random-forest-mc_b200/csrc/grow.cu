@@ -105,6 +105,12 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool acti
     if (active && (__ffs(m) - 1) == lane) atomicAdd(&hist[bin], (uint32_t)__popc(m));
 }
 
+// Digit histograms of a radix pass: 256 bins, a warp's 32 digits rarely coincide, so the election of
+// hist_add (MATCH.ANY + leader) costs more than it saves -- one shared-memory atomic per lane.
+__device__ __forceinline__ void hist_add_sparse(uint32_t* hist, uint32_t bin, bool active) {
+    if (active) atomicAdd(&hist[bin], 1u);
+}
+
 // Locate the bin of hist[0..256) that contains 0-based rank r; r becomes the rank inside that bin.
 __device__ __forceinline__ uint32_t find_bin256(const uint32_t* hist, uint32_t& r, int lane) {
     uint32_t loc[8];
@@ -145,9 +151,11 @@ __device__ __forceinline__ uint32_t find_bin256(const uint32_t* hist, uint32_t& 
 
 // The two middle order statistics (0-based ranks k0 and k0+1) of a node with more than 32 rows:
 // MSD radix select over 8-bit digits; both ranks share one histogram until their prefixes diverge.
+// less_a / less_b: rows of the node with a code below ca / cb; eq_a / eq_b: rows with exactly that code --
+// the side sizes of any split at ca, ca + 1, cb or cb + 1 follow from them without another pass over the rows.
 template <typename CodeT, typename PosT>
 __device__ void select_two(const CodeT* col, const PosT* P, uint32_t n, int npass, uint32_t k0, uint32_t* hist, int lane,
-                           uint32_t& ca, uint32_t& cb) {
+                           uint32_t& ca, uint32_t& cb, uint32_t& less_a, uint32_t& eq_a, uint32_t& less_b, uint32_t& eq_b) {
     uint32_t prefA = 0, prefB = 0, rA = k0, rB = k0 + 1;
     bool same = true;
     for (int pass = npass - 1; pass >= 0; --pass) {
@@ -170,8 +178,8 @@ __device__ void select_two(const CodeT* col, const PosT* P, uint32_t n, int npas
             for (int u = 0; u < 4; ++u) {
                 if (base + u * 32 >= n) break;
                 const uint32_t d = (c[u] >> shift) & 255u;
-                hist_add(hist, d, act[u] && ((c[u] & himask) == (prefA & himask)), lane);
-                if (!same) hist_add(hist + 256, d, act[u] && ((c[u] & himask) == (prefB & himask)), lane);
+                hist_add_sparse(hist, d, act[u] && ((c[u] & himask) == (prefA & himask)));
+                if (!same) hist_add_sparse(hist + 256, d, act[u] && ((c[u] & himask) == (prefB & himask)));
             }
         }
         __syncwarp();
@@ -179,16 +187,34 @@ __device__ void select_two(const CodeT* col, const PosT* P, uint32_t n, int npas
         uint32_t dB;
         if (same) {
             dB = find_bin256(hist, rB, lane);
+            eq_b = hist[dB];
             if (dB != dA) same = false;
         } else {
             dB = find_bin256(hist + 256, rB, lane);
+            eq_b = hist[256 + dB];
         }
+        eq_a = hist[dA];  // after the last pass: rows equal to the selected code
         prefA |= dA << shift;
         prefB |= dB << shift;
         __syncwarp();
     }
     ca = prefA;
     cb = prefB;
+    less_a = k0 - rA;  // the rank inside the final bin is what is left of the rank
+    less_b = k0 + 1 - rB;
+}
+
+// Rows of the node with code >= t, for the thresholds a median split can take (numpy's `>=`, then `>`
+// when a side is empty, model.py:238-245); false when t is none of them and the rows have to be counted.
+__device__ __forceinline__ bool side_from_select(uint32_t t, uint32_t n, uint32_t ca, uint32_t cb, uint32_t less_a, uint32_t eq_a,
+                                                 uint32_t less_b, uint32_t eq_b, uint32_t& cnt_a) {
+    if (t == ca) cnt_a = n - less_a;
+    else if (cb == 0u) return false;  // categorical mode: only ca is set
+    else if (t == cb) cnt_a = n - less_b;
+    else if (t == ca + 1u) cnt_a = n - less_a - eq_a;
+    else if (t == cb + 1u) cnt_a = n - less_b - eq_b;
+    else return false;
+    return true;
 }
 
 // numpy's q=0.5 linear interpolation between adjacent order statistics, in the column's dtype
@@ -795,6 +821,8 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
             const bool cat = a.col_kind[f] == RFMC_KIND_CATEGORICAL;
             const CodeT* col = c.cc + (size_t)f * a.nt_pad;
             uint32_t t_store = 0, t_part = 0, cnt_a = 0, pend = 0;
+            uint32_t sel_ca = 0, sel_cb = 0, less_a = 0, eq_a = 0, less_b = 0, eq_b = 0;
+            bool have_sel = false;
             const uint32_t fl_flags = cat ? RFMC_FLAG_CATEGORICAL : 0u;
             double sv = 0.0;
 
@@ -829,6 +857,9 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
                         }
                         key = warp_max_u64(key);
                         t_store = t_part = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+                        sel_ca = t_part;  // rows equal to the mode: its histogram count
+                        less_a = n - (uint32_t)(key >> 32);
+                        have_sel = true;
                         __syncwarp();
                     } else {  // high-cardinality categorical: all-pairs counting (rare path)
                         unsigned long long key = 0;
@@ -850,17 +881,19 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
                     }
                 } else {
                     int npass = (K < 0x100u) ? 1 : ((K < 0x10000u) ? 2 : ((K < 0x1000000u) ? 3 : 4));
-                    uint32_t ca, cb;
-                    select_two<CodeT, PosT>(col, P, n, npass, (n - 1) >> 1, hist, lane, ca, cb);
+                    select_two<CodeT, PosT>(col, P, n, npass, (n - 1) >> 1, hist, lane, sel_ca, sel_cb, less_a, eq_a, less_b, eq_b);
+                    have_sel = true;
+                    const uint32_t ca = sel_ca, cb = sel_cb;
                     const double* tab = a.tables + a.tab_off[f];
                     double va = __ldg(&tab[ca - 1]), vb = __ldg(&tab[cb - 1]);
                     sv = median_value(va, vb, (n & 1) != 0, a.col_tag[f]);
                     t_part = threshold_deferred(tab, K, sv, va, vb, ca, cb, t_store, pend);
                 }
-                // side sizes
+                // side sizes: from the select's rank bookkeeping when the threshold is one of its codes, else by counting
                 for (int attempt = 0; attempt < 2; ++attempt) {
                     cnt_a = 0;
-                    for (uint32_t base = 0; base < n; base += 128) {
+                    const bool known = have_sel && side_from_select(t_part, n, sel_ca, sel_cb, less_a, eq_a, less_b, eq_b, cnt_a);
+                    for (uint32_t base = 0; !known && base < n; base += 128) {
                         uint32_t cv[4];
                         bool act[4];
 #pragma unroll
@@ -1089,8 +1122,8 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const uint32_t d = (cv[u] >> shift) & 255u;
-                            hist_add(hist, d, act[u] && ((cv[u] & himask) == (prefA & himask)), lane);
-                            if (!same) hist_add(hist + 256, d, act[u] && ((cv[u] & himask) == (prefB & himask)), lane);
+                            hist_add_sparse(hist, d, act[u] && ((cv[u] & himask) == (prefA & himask)));
+                            if (!same) hist_add_sparse(hist + 256, d, act[u] && ((cv[u] & himask) == (prefB & himask)));
                         }
                     }
                     __syncthreads();
