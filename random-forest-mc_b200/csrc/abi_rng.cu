@@ -34,14 +34,13 @@ int poly_table(int device, int64_t chunk_words, int64_t n_chunks, cudaStream_t s
     PolyTable& t = g_polys[{device, chunk_words}];
     if (t.have < want) {
         if (t.cap < want) {
-            int64_t cap = t.cap ? t.cap : 64;
+            // Plans in flight on other streams hold the table's address: a table that has to grow is replaced
+            // by a larger one and LEFT ALLOCATED (a few MB, once per chunk length), never freed under them.
+            int64_t cap = t.cap ? t.cap : 1024;
             while (cap < want) cap *= 2;
             uint32_t* nd = nullptr;
             RFMC_CUDA(cudaMalloc((void**)&nd, (size_t)cap * MT_N * 4));
             if (t.have) RFMC_CUDA(cudaMemcpy(nd, t.d, (size_t)t.have * MT_N * 4, cudaMemcpyDeviceToDevice));
-            // the old table may still be read by a fill kernel in flight on another stream
-            RFMC_CUDA(cudaDeviceSynchronize());
-            if (t.d) cudaFree(t.d);
             t.d = nd;
             t.cap = cap;
         }

@@ -488,149 +488,153 @@ __device__ __forceinline__ int32_t chord_slack(const Sched& sc, int32_t kr_a, in
     return 4 + (int32_t)((float)CH_WORDS * 0.25f * (1.0f - r_lo));
 }
 
-constexpr int CN_THREADS = 256;          // warp 0 settles, warps 1..7 stage the next unit's pending words
-constexpr int CN_MAX = 8192;             // pending words per unit (a unit = up to 8 chunks)
-constexpr int CN_UNIT_CHUNKS = 8;
-
-struct ChainUnit {
-    int first, count;  // chunks [first, first + count) of the round
-    int n;             // pending words in them
-    int ent0[CN_UNIT_CHUNKS + 1];  // entry index where each chunk starts
-    int sure0[CN_UNIT_CHUNKS + 1]; // certain accepts before each chunk's start, inside the unit
-};
+constexpr int CN_THREADS = 1024;  // one pending word per thread
+constexpr int CN_ROUND_MAX = 256; // chunks per round the chain's tables hold
 
 struct ChainShared {
-    uint2 ent[2][CN_MAX];  // {word, certain accepts before it inside the unit}
-    ChunkHdr hdr[256];
-    ChainUnit unit[2];
-    int64_t k;
+    int32_t ent0[CN_ROUND_MAX + 1];   // pending words before chunk g of the round
+    int32_t sure0[CN_ROUND_MAX + 1];  // certain accepts before chunk g of the round
+    uint32_t bal[32];                 // accept ballots of the unit's 32 warps
+    uint32_t pre[32];                 // exclusive prefix of their counts
+    int32_t tot;
 };
 
-// Greedy unit: chunks from `first` while the pending words fit.  A single chunk always fits (4,096).
-__device__ void plan_unit(const ChunkHdr* hdr, int n_here, int first, ChainUnit& u) {
-    u.first = first;
-    u.count = 0;
-    u.n = 0;
-    int sure = 0;
-    while (first + u.count < n_here && u.count < CN_UNIT_CHUNKS && u.n + hdr[first + u.count].n_pend <= CN_MAX) {
-        u.ent0[u.count] = u.n;
-        u.sure0[u.count] = sure;
-        u.n += hdr[first + u.count].n_pend;
-        sure += hdr[first + u.count].n_sure;
-        ++u.count;
-    }
-    u.ent0[u.count] = u.n;
-    u.sure0[u.count] = sure;
-}
-
-// global -> shared copy of a unit's pending lists by `n_thr` threads (rank `t`), the count of certain accepts
-// made relative to the unit on the way
-__device__ __forceinline__ void stage_unit(const WalkBuffers& b, const ChainUnit& u, uint2* dst, int t, int n_thr) {
-    for (int c = 0; c < u.count; ++c) {
-        const uint2* src = b.pend + (size_t)(u.first + c) * CH_WORDS;
-        const int n = u.ent0[c + 1] - u.ent0[c];
-        const uint32_t add = (uint32_t)u.sure0[c];
-        for (int e = t; e < n; e += n_thr) {
-            const uint2 x = __ldg(&src[e]);
-            dst[u.ent0[c] + e] = make_uint2(x.x, add + ((x.y >> 16) & 0x7FFFu));
-        }
-    }
-}
-
+// The chain: the round's pending words in stream order, 1,024 at a time, one per thread.  Jacobi fix-point:
+// every word is decided at the ordinal that the PREVIOUS iteration's verdicts put it at; the counts are
+// re-derived from the new verdicts by a ballot scan; an iteration that changes no verdict is the exact walk
+// (the recurrence is causal, so its fixed point is unique).  The first guess is the classifier's verdict at
+// the predicted ordinal; 3-4 iterations of ~300 cycles settle 1,024 words.
 __global__ void __launch_bounds__(CN_THREADS, 1) chain_kernel(const __grid_constant__ Sched sc, WalkBuffers b, int64_t chunk0,
                                                               int n_here, int n_next) {
-    extern __shared__ __align__(16) unsigned char chain_dyn[];
-    ChainShared& sh = *reinterpret_cast<ChainShared*>(chain_dyn);
+    __shared__ ChainShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     int64_t k = chunk0 == 0 ? 0 : b.k0[chunk0];
     if (chunk0 == 0 && tid == 0) b.k0[0] = 0;
-    int pend_total = 0;
-    for (int g = tid; g < n_here; g += CN_THREADS) sh.hdr[g] = b.hdr[g];
-    __syncthreads();
-    if (n_here > 0) {
-        if (tid == 0) plan_unit(sh.hdr, n_here, 0, sh.unit[0]);
-        __syncthreads();
-        stage_unit(b, sh.unit[0], sh.ent[0], tid, CN_THREADS);
-        __syncthreads();
+    // prefix sums of the round's chunk headers
+    if (warp == 0) {
+        int run_e = 0, run_s = 0;
+        for (int g0 = 0; g0 < n_here; g0 += 32) {
+            const int g = g0 + lane;
+            const ChunkHdr h = g < n_here ? b.hdr[g] : ChunkHdr{0, 0};
+            int ie = h.n_pend, is = h.n_sure;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int te = __shfl_up_sync(FULL, ie, d), ts = __shfl_up_sync(FULL, is, d);
+                if (lane >= d) {
+                    ie += te;
+                    is += ts;
+                }
+            }
+            if (g < n_here) {
+                sh.ent0[g + 1] = run_e + ie;
+                sh.sure0[g + 1] = run_s + is;
+            }
+            run_e += __shfl_sync(FULL, ie, 31);
+            run_s += __shfl_sync(FULL, is, 31);
+        }
+        if (lane == 0) sh.ent0[0] = sh.sure0[0] = 0;
     }
-    int buf = 0;
-    for (int first = 0; first < n_here;) {
-        const ChainUnit& u = sh.unit[buf];
-        const int next_first = first + u.count;
-        if (next_first < n_here && tid == 32) plan_unit(sh.hdr, n_here, next_first, sh.unit[buf ^ 1]);
-        if (warp != 0) {
-            // named barrier among the staging warps only: the plan of the next unit is theirs
-            asm volatile("bar.sync 1, %0;" ::"r"(CN_THREADS - 32));
-            if (next_first < n_here) stage_unit(b, sh.unit[buf ^ 1], sh.ent[buf ^ 1], tid - 32, CN_THREADS - 32);
-        } else {
-            // warp 0: the unit's pending words in stream order, 32 at a time, each at its exact ordinal
-            const uint2* ent = sh.ent[buf];
-            const int n = u.n;
-            const int32_t kr0 = (int32_t)(k % sc.steps);
-            const int e_hint = ent_of(sc, kr0, 0);
-            // the usual unit lies inside one class's shuffle: the step number is then i0 - (accepts before the word)
-            const bool one_class = sc.nn[e_hint] > 0 && kr0 + u.sure0[u.count] + n < sc.ks[e_hint + 1];
-            const int32_t i0 = sc.nn[e_hint] - 1 - (kr0 - sc.ks[e_hint]);
-            const int my_idx = lane < u.count ? u.ent0[lane + 1] : -1;  // lane c reports the boundary after chunk c
-            int my_D = 0, D = 0;
-            for (int base = 0; base < n; base += 32) {
-                const int e = base + lane;
-                const bool valid = e < n;
-                const uint2 x = valid ? ent[e] : make_uint2(0u, 0u);
-                const int32_t before = (int32_t)x.y + D;
-                uint32_t bits;
+    __syncthreads();
+    const int total = n_here > 0 ? sh.ent0[n_here] : 0;
+    const int32_t kr0 = (int32_t)(k % sc.steps);
+    const int e_hint = ent_of(sc, kr0, 0);
+    // the usual round lies inside one class's shuffle: the step number is then i0 - (accepts before the word)
+    const bool one_class = n_here > 0 && sc.nn[e_hint] > 0 && kr0 + sh.sure0[n_here] + total < sc.ks[e_hint + 1];
+    const int32_t i0 = sc.nn[e_hint] - 1 - (kr0 - sc.ks[e_hint]);
+    // boundaries that have no pending word before them
+    for (int g = tid; g < n_here; g += CN_THREADS)
+        if (sh.ent0[g + 1] == 0) b.k0[chunk0 + g + 1] = k + sh.sure0[g + 1];
+
+    auto fetch = [&](int E, uint2& x) {  // entry E of the round: {word, certain accepts before it in the round | guess << 31}
+        x = make_uint2(0u, 0u);
+        if (E >= total) return;
+        int lo = 0, hi = n_here;  // chunk g with ent0[g] <= E < ent0[g + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sh.ent0[mid] <= E) lo = mid; else hi = mid;
+        }
+        const uint2 raw = __ldg(&b.pend[(size_t)lo * CH_WORDS + (E - sh.ent0[lo])]);
+        x = make_uint2(raw.x, (uint32_t)(sh.sure0[lo] + (int)((raw.y >> 16) & 0x7FFFu)) | (raw.y & 0x80000000u));
+    };
+
+    int D_unit = 0;  // accepted pending words before the current unit
+    uint2 nxt;
+    fetch(tid, nxt);
+    for (int u0 = 0; u0 < total; u0 += CN_THREADS) {
+        const uint2 cur = nxt;
+        fetch(u0 + CN_THREADS + tid, nxt);  // in flight while this unit iterates
+        const int E = u0 + tid;
+        const bool valid = E < total;
+        const int32_t before = (int32_t)(cur.y & 0x7FFFFFFFu);
+        uint32_t bits = __ballot_sync(FULL, valid && (cur.y >> 31));
+        for (;;) {
+            if (lane == 0) {
+                sh.bal[warp] = bits;
+                sh.pre[warp] = (uint32_t)__popc(bits);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t c = sh.pre[lane];
+                uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                sh.pre[lane] = inc - c;
+                if (lane == 31) sh.tot = (int)inc;
+            }
+            __syncthreads();
+            const int32_t D = D_unit + (int32_t)sh.pre[warp] + __popc(bits & lt);
+            bool acc = false;
+            if (valid) {
                 if (one_class) {
-                    const int32_t i_a = i0 - before;
-                    bits = __ballot_sync(FULL, valid && (x.x & (0xFFFFFFFFu >> __clz(i_a))) <= (uint32_t)i_a);
-                    for (;;) {  // lane l is final once the lanes below it are: at most 32 rounds, usually 2
-                        const int32_t i = i_a - __popc(bits & lt);
-                        const uint32_t nb = __ballot_sync(FULL, valid && (x.x & (0xFFFFFFFFu >> __clz(i))) <= (uint32_t)i);
-                        if (nb == bits) break;
-                        bits = nb;
-                    }
+                    const int32_t i = i0 - before - D;
+                    acc = (cur.x & (0xFFFFFFFFu >> __clz(i))) <= (uint32_t)i;
                 } else {
                     int en = e_hint;
                     uint32_t uu;
-                    bits = __ballot_sync(FULL, valid && accept_at(sc, x.x, wrap_slot(sc, kr0 + before), en, uu));
-                    for (;;) {
-                        const uint32_t nb =
-                            __ballot_sync(FULL, valid && accept_at(sc, x.x, wrap_slot(sc, kr0 + before + __popc(bits & lt)), en, uu));
-                        if (nb == bits) break;
-                        bits = nb;
-                    }
+                    acc = accept_at(sc, cur.x, wrap_slot(sc, kr0 + before + D), en, uu);
                 }
-                if (my_idx >= base && my_idx < base + 32) my_D = D + __popc(bits & ((1u << (my_idx - base)) - 1u));
-                D += __popc(bits);
             }
-            if (my_idx >= n) my_D = D;
-            if (lane < u.count) b.k0[chunk0 + u.first + lane + 1] = k + u.sure0[lane + 1] + my_D;
-            if (lane == 0) sh.k = k + u.sure0[u.count] + D;
+            const uint32_t nb = __ballot_sync(FULL, acc);
+            const bool changed = nb != bits;
+            bits = nb;
+            if (!__syncthreads_or(changed)) break;
         }
-        __syncthreads();
-        k = sh.k;
-        pend_total += u.n;
-        first = next_first;
-        buf ^= 1;
+        // sh.bal / sh.pre / sh.tot describe the converged verdicts: exact ordinals at the chunk boundaries that
+        // fall inside this unit (boundary B = pending words before chunk g + 1)
+        const int u1 = u0 + CN_THREADS < total ? u0 + CN_THREADS : total;
+        for (int g = tid; g < n_here; g += CN_THREADS) {
+            const int B = sh.ent0[g + 1];
+            if (B > u0 && B <= u1) {
+                const int r = B - u0;  // entries of the unit before the boundary
+                const int D = r >= CN_THREADS ? sh.tot : (int)sh.pre[r >> 5] + __popc(sh.bal[r >> 5] & ((1u << (r & 31)) - 1u));
+                b.k0[chunk0 + g + 1] = k + sh.sure0[g + 1] + D_unit + D;
+            }
+        }
+        D_unit += sh.tot;
         __syncthreads();
     }
+    if (n_here > 0) k += sh.sure0[n_here] + D_unit;
     // boundaries of the next round, from the exact ordinal reached: one thread per chunk
     if (n_next > 0) {
-        const int32_t kr0 = (int32_t)(k % sc.steps);
+        const int32_t kr1 = (int32_t)(k % sc.steps);
         if (tid == 0) b.kpred[0] = k;
         float var = 0.0f;
         if (tid < n_next) {
             double dk;
-            predict_span(sc, kr0, (float)(tid + 1) * (float)CH_WORDS, dk, var);
+            predict_span(sc, kr1, (float)(tid + 1) * (float)CH_WORDS, dk, var);
             b.kpred[tid + 1] = k + (int64_t)(dk + 0.5);
         }
         __syncthreads();
         if (tid < n_next) {
-            const int32_t ka = (int32_t)((b.kpred[tid] - k + kr0) % sc.steps), kb = (int32_t)((b.kpred[tid + 1] - k + kr0) % sc.steps);
+            const int32_t ka = (int32_t)((b.kpred[tid] - k + kr1) % sc.steps), kb = (int32_t)((b.kpred[tid + 1] - k + kr1) % sc.steps);
             b.eband[tid] = 8 + (int32_t)(7.5f * sqrtf(var + 1.0f)) + chord_slack(sc, ka, kb);
         }
     }
-    if (tid == 0) atomicAdd(&b.status[4], pend_total >> 10);  // thousands of pending words the chain settled
+    if (tid == 0) atomicAdd(&b.status[4], total >> 10);  // thousands of pending words the chain settled
 }
 
 struct FinalShared {
@@ -1101,14 +1105,13 @@ int drawplan_launch(rfmc_drawplan* pl) {
         b.status = pl->d_status;
         const int G = pl->chunks_per_round;
         const int64_t N = pl->n_walk_chunks;
-        RFMC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared)));
-        chain_kernel<<<1, CN_THREADS, sizeof(ChainShared), st>>>(sc, b, 0, 0, (int)(N < G ? N : G));
+        chain_kernel<<<1, CN_THREADS, 0, st>>>(sc, b, 0, 0, (int)(N < G ? N : G));
         ++launches;
         for (int64_t c0 = 0; c0 < N; c0 += G) {
             const int here = (int)(N - c0 < G ? N - c0 : G);
             const int64_t left = N - c0 - here;
             classify_kernel<<<here, CH_THREADS, 0, st>>>(sc, b, c0);
-            chain_kernel<<<1, CN_THREADS, sizeof(ChainShared), st>>>(sc, b, c0, here, (int)(left < G ? left : G));
+            chain_kernel<<<1, CN_THREADS, 0, st>>>(sc, b, c0, here, (int)(left < G ? left : G));
             launches += 2;
         }
         RFMC_CUDA(cudaGetLastError());
