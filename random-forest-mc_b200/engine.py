@@ -250,6 +250,9 @@ def pyrandom_sample_plan(rng, n_pop: int, ks: np.ndarray):
     return out
 
 
+_CLASS_ROWS_LOCK = __import__("threading").Lock()
+
+
 class DeviceDataset:
     """rfmc_dataset handle: the encoded training matrix resident in HBM (process_dataset)."""
 
@@ -291,9 +294,12 @@ class DeviceDataset:
         """Per-class row lists (class_vals order) for the device draws; uploaded once."""
         if getattr(self, "_class_rows_id", None) is class_rows:
             return
-        rows, off = _flat_class_rows(class_rows)
-        _check(load_library().rfmc_dataset_set_class_rows(self._h, len(class_rows), _ptr(rows), _ptr(off)))
-        self._class_rows_id = class_rows
+        with _CLASS_ROWS_LOCK:  # the host streams of a fit reach this together: one upload, before any plan uses it
+            if getattr(self, "_class_rows_id", None) is class_rows:
+                return
+            rows, off = _flat_class_rows(class_rows)
+            _check(load_library().rfmc_dataset_set_class_rows(self._h, len(class_rows), _ptr(rows), _ptr(off)))
+            self._class_rows_id = class_rows
 
     def close(self):
         if getattr(self, "_h", None):
@@ -484,6 +490,7 @@ def encode_dataset_device(dataset_numpy, feature_cols, numeric_cols, target_col,
         fetch_codes=fetch_codes,
     )
     dev.enc = enc
+    dev.set_class_rows(class_rows)  # the per-class row lists of the device draws, uploaded once with the dataset
     return enc, dev
 
 
