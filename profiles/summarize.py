@@ -10,6 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+commit = sys.argv[2] if len(sys.argv) > 2 else None
 
 KEYS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -41,7 +42,7 @@ def to_bytes(val, unit):
     return num(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 
 
-lines = [f"# ncu summary ({tag})", "", "Commands: `profiles/prof_final.sh` (default bench configuration, `--clock-control none`).", ""]
+lines = [f"# ncu summary ({tag})", "", "Commands: `profiles/prof_r2.sh` (the default `python bench.py` command, `--clock-control none`).", ""]
 src = os.path.join(OUT, "launchesF.csv")
 if os.path.exists(src):
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
@@ -71,7 +72,13 @@ for rep, name in (("prof_growF", "grow_kernel"), ("prof_gatherF", "slot_gather_k
         if k in d:
             lines.append(f"| {k} | {d[k][0]} {d[k][1]} |")
     lines.append("")
-    traffic[name] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+    traffic[name] = {
+        "dram_bytes_per_launch": to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]),
+        # one shared-memory wavefront moves up to 128 bytes (the denominator of SURVEY 8d's secondary bound)
+        "shared_wavefront_bytes_per_launch": num(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"][0]) * 128.0,
+        "issue_slot_utilisation": num(d["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) / 100.0,
+        "ms_per_launch_under_ncu": num(d["gpu__time_duration.sum"][0]) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(d["gpu__time_duration.sum"][1], 1.0),
+    }
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
 workload = None
@@ -79,5 +86,6 @@ plain = os.path.join(OUT, "plainF.json")
 if os.path.exists(plain):
     workload = json.load(open(plain))["config"]["workload"]
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
-    json.dump({"workload": workload, "bytes_per_launch": traffic}, f)
+    json.dump({"workload": workload, "capture": f"profiles/{tag}_ncu_summary.md (ncu --set full --clock-control none, one launch per kernel, default bench command)",
+               "commit": commit, "kernels": traffic}, f, indent=1)
 print("\n".join(lines))

@@ -32,6 +32,7 @@
 //   resolve_prefix_kernel  steps i < N act inside the prefix (one warp per draw), then
 //                       idx_train / idx_val = class_rows[head[p]] straight into the grower's inputs.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -277,8 +278,26 @@ template <bool TIGHT>
 __device__ __forceinline__ void classify_words(const Sched& sc, ChunkShared& sh, const uint32_t (&w)[CH_ROWS], int32_t kr0,
                                                int32_t dk_end, int32_t e_band, bool all_pending, int e_hint,
                                                uint32_t (&bs)[CH_ROWS], uint32_t (&ba)[CH_ROWS], int32_t (&klo)[CH_ROWS],
-                                               int32_t (&khi)[CH_ROWS]) {
+                                               int32_t (&khi)[CH_ROWS], uint32_t& level_mask) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The usual chunk: every band stays inside ONE mask level of ONE class's shuffle.  Then the step number is
+    // i_base - ordinal offset and the verdict two compares; the schedule walk (band_verdict) is for the chunks
+    // that touch a level, class or slot boundary.
+    bool one_level = false;
+    int32_t i_base = 0;
+    level_mask = 0u;
+    {
+        const int32_t n = sc.nn[e_hint];
+        const int32_t kmin = kr0 - (TIGHT ? 0 : e_band), kmax = kr0 + dk_end + (TIGHT ? 0 : e_band);
+        if (!all_pending && n > 0 && dk_end >= 0 && kmin >= sc.ks[e_hint] && kmax < sc.ks[e_hint + 1]) {
+            i_base = n - 1 - (kr0 - sc.ks[e_hint]);
+            const int32_t i_top = i_base + (kr0 - kmin), i_bot = i_base - (kmax - kr0);  // >= 1: kmax is inside the class
+            if (__clz(i_top) == __clz(i_bot)) {
+                one_level = true;
+                level_mask = 0xFFFFFFFFu >> __clz(i_top);
+            }
+        }
+    }
 #pragma unroll
     for (int v = 0; v < CH_ROWS; ++v) {
         const int q = v * CH_THREADS + tid;
@@ -286,7 +305,7 @@ __device__ __forceinline__ void classify_words(const Sched& sc, ChunkShared& sh,
         int32_t E = e_band;
         if (TIGHT) {  // both ends of the chunk are exact: the walk is a bridge, widest in the middle
             const int m = q < CH_WORDS - q ? q : CH_WORDS - q;
-            E += (int32_t)(7.5f * 0.5f * sqrtf((float)m)) + 1;
+            E += (int32_t)(3.75f * __fsqrt_rn((float)m)) + 1;
         }
         int32_t lo_k = dk - E, hi_k = dk + E;
         if (TIGHT) {  // exact start: between none and q accepts before word q, at most dk_end in the whole chunk
@@ -299,11 +318,19 @@ __device__ __forceinline__ void classify_words(const Sched& sc, ChunkShared& sh,
         klo[v] = lo_k;
         khi[v] = hi_k;
         int verdict = 0;
-        if (!all_pending && hi_k >= lo_k) verdict = band_verdict(sc, w[v], kr0 + lo_k, hi_k - lo_k, e_hint);
+        if (!all_pending && hi_k >= lo_k) {
+            if (one_level) {
+                const uint32_t u = w[v] & level_mask;
+                verdict = u <= (uint32_t)(i_base - hi_k) ? 1 : (u > (uint32_t)(i_base - lo_k) ? 2 : 0);
+            } else {
+                verdict = band_verdict(sc, w[v], kr0 + lo_k, hi_k - lo_k, e_hint);
+            }
+        }
         bs[v] = __ballot_sync(FULL, verdict == 1);
         ba[v] = __ballot_sync(FULL, verdict == 0);
         if (lane == 0) sh.seg[v * (CH_THREADS / 32) + warp] = (uint32_t)__popc(bs[v]) | ((uint32_t)__popc(ba[v]) << 16);
     }
+    if (!one_level) level_mask = 0u;
     __syncthreads();
     if (warp == 0) {  // exclusive scan of the 128 segment counts (both 16-bit fields at once)
         constexpr int PER = CH_SEGS / 32;
@@ -352,7 +379,8 @@ __global__ void __launch_bounds__(CH_THREADS) classify_kernel(const __grid_const
     const int64_t ks = b.kpred[g], ke = b.kpred[g + 1];
     const int32_t kr0 = (int32_t)(ks % sc.steps);
     const int e_hint = ent_of(sc, kr0, 0);
-    classify_words<false>(sc, sh, w, kr0, (int32_t)(ke - ks), b.eband[g], false, e_hint, bs, ba, klo, khi);
+    uint32_t level_mask;
+    classify_words<false>(sc, sh, w, kr0, (int32_t)(ke - ks), b.eband[g], false, e_hint, bs, ba, klo, khi, level_mask);
     const uint32_t tot = sh.tot;
     if (tid == 0) b.hdr[g] = ChunkHdr{(int32_t)(tot & 0xFFFFu), (int32_t)(tot >> 16)};
     uint2* out = b.pend + (size_t)g * CH_WORDS;
@@ -645,7 +673,7 @@ struct FinalShared {
     int32_t pend_acc;
 };
 
-__global__ void __launch_bounds__(CH_THREADS) final_kernel(const __grid_constant__ Sched sc, WalkBuffers b) {
+__global__ void __launch_bounds__(CH_THREADS, 2) final_kernel(const __grid_constant__ Sched sc, WalkBuffers b) {
     __shared__ FinalShared sh;
     const int64_t chunk = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -666,7 +694,8 @@ __global__ void __launch_bounds__(CH_THREADS) final_kernel(const __grid_constant
     bool counted = false;
     for (int attempt = sane ? 0 : 1; attempt < 2 && !counted; ++attempt) {
         const bool all_pending = attempt == 1;
-        classify_words<true>(sc, sh.cs, w, kr0, sane ? dk_end : 0, e_band, all_pending, e_hint, bs, ba, klo, khi);
+        uint32_t level_mask;
+        classify_words<true>(sc, sh.cs, w, kr0, sane ? dk_end : 0, e_band, all_pending, e_hint, bs, ba, klo, khi, level_mask);
         const uint32_t tot = sh.cs.tot;
         const int n_pend = (int)(tot >> 16), n_sure = (int)(tot & 0xFFFFu);
 #pragma unroll
@@ -715,9 +744,13 @@ __global__ void __launch_bounds__(CH_THREADS) final_kernel(const __grid_constant
             const bool acc = is_pend ? ((res >> 15) & 1u) : ((bs[v] >> lane) & 1u);
             const int64_t kg = ka + k;
             if (acc && kg < sc.k_total) {
-                int ent = e_hint;
                 uint32_t u;
-                accept_at(sc, w[v], wrap_slot(sc, kr0 + k), ent, u);
+                if (level_mask) {
+                    u = w[v] & level_mask;
+                } else {
+                    int ent = e_hint;
+                    accept_at(sc, w[v], wrap_slot(sc, kr0 + k), ent, u);
+                }
                 b.A[kg] = u;
                 const int64_t after = kg + 1;  // a slot ends with its last draw
                 if (after >= next_slot_k && (after - next_slot_k) % sc.steps == 0)
@@ -1185,6 +1218,10 @@ int drawplan_geometry(rfmc_drawplan* pl, int64_t words) {
     const int64_t walk_chunks = (words + CH_WORDS - 1) / CH_WORDS + 1;
     pl->n_walk_chunks = walk_chunks;
     pl->chunks_per_round = 128;
+    if (const char* e = getenv("RFMC_DRAW_ROUND_CHUNKS")) {  // experiment knob: chunks classified per round (<= 256)
+        const int want = atoi(e);
+        if (want >= 8 && want <= 256) pl->chunks_per_round = want;
+    }
     pl->n_blocks = (pl->pos0 + walk_chunks * CH_WORDS + MT_N - 1) / MT_N + 1;
     // fill CTAs: about two per SM; the chunk length is one of five sizes so that the jump polynomials are shared
     int bpc = RNG_BLOCKS_PER_CHUNK;
