@@ -575,7 +575,9 @@ def run_b200(args):
 
     # ---- C2b (default) / C2a: the headline configuration ----
     frame = make_frame(args.rows, args.features, args.classes, seed=0)
-    k_streams = max(1, min(args.host_streams or max(1, min(16, cores // world)), cores, args.n_trees))
+    # host RNG streams per rank: one per core at N = 1; with several ranks on the box twice the rank's share of the
+    # cores (the streams of a rank alternate between drawing and waiting for their launch)
+    k_streams = max(1, min(args.host_streams or max(1, min(16, cores if world == 1 else max(4, 2 * cores // world))), cores, args.n_trees))
     sampler = ClockSampler(local).start()
     model, main = fit_config(frame, args.regime, args.n_trees, workload_name(args), args.steps, args.warmup, args.e2e_steps, k_streams,
                              1 if args.regime == "c2b" else 3)

@@ -126,7 +126,7 @@ def all_gather_trees_abi(trees, scores, n_classes, used_masks, dev_payload, devi
         at = 0
         for k in range(len(r_sizes)):
             s = int(r_sizes[k])
-            soa = trees[k] if r == g.rank else LazyTreeSoA(block, r, at, s)
+            soa = LazyTreeSoA(block, r, at, s) if (r != g.rank or dev_payload is not None) else trees[k]
             out.append((soa, np.float64(r_scores[k]), r_masks[k] if g.mask_bytes else None))
             at += s
     return out, g
@@ -149,6 +149,35 @@ class LazyTreeSoA:
     @property
     def counts(self):
         return self._block.host()[self._rank][1][self._start : self._start + self._size]
+
+
+class PackedTreeSoA:
+    """TreeSoA interface over a slice of a PackRecorder's device buffers (copied to the host on first read)."""
+
+    def __init__(self, nodes_t, counts_t, start: int, size: int, n_classes: int):
+        self._nodes_t, self._counts_t, self._start, self._size, self._C = nodes_t, counts_t, start, size, n_classes
+        self._host = None
+
+    @property
+    def n_nodes(self) -> int:
+        return self._size
+
+    def _fetch(self):
+        if self._host is None:
+            nb, cb = NODE_DTYPE.itemsize, self._C * 4
+            n = self._nodes_t[self._start * nb : (self._start + self._size) * nb].cpu().numpy().view(NODE_DTYPE)
+            c = self._counts_t[self._start * cb : (self._start + self._size) * cb].cpu().numpy().view(np.int32).reshape(self._size, self._C)
+            self._host = (n, c)
+            self._nodes_t = self._counts_t = None
+        return self._host
+
+    @property
+    def nodes(self):
+        return self._fetch()[0]
+
+    @property
+    def counts(self):
+        return self._fetch()[1]
 
 
 class PackRecorder:
@@ -176,7 +205,13 @@ class PackRecorder:
         self.counts.append(tc)
         self.sizes.append(sizes)
         self.n_trees += len(ids)
-        return batch.fetch(ids)  # host copy through the engine's pinned staging
+        # no host copy here: after the exchange this rank's trees are read, like everybody else's, from the
+        # gathered block; until then a tree knows its size and where its tables sit on the device
+        out, at = [], 0
+        for s in sizes:
+            out.append(PackedTreeSoA(tn, tc, at, int(s), self.n_classes))
+            at += int(s)
+        return out
 
 
 def all_gather_trees(trees: Sequence[TreeSoA], scores: Sequence[float], n_classes: int, used_masks=None, dev_payload=None):
@@ -298,8 +333,10 @@ def _gather_forest(model, local, recorder=None):
         t.features = model.feature_cols
         # model.py:413-417 semantics (flat.reference_used_features); every class of the balanced bootstrap
         # ends up in some leaf, so the leaf labels of a fitted tree are the class labels
-        split_names = [model.feature_cols[j] for j in np.flatnonzero(mask)]
-        t.used_features = reference_used_features(model.feature_cols, split_names, model.class_vals, len(split_names) > 0)
+        if mask is not None:
+            t._used_mask = (mask, model.feature_cols, model.class_vals)  # used_features is derived on first access
+        else:
+            t.used_features = reference_used_features(model.feature_cols, [], model.class_vals, False)
         forest.append(t)
     return forest
 

@@ -81,6 +81,13 @@ class DecisionTreeMC(UserDict):
     def used_features(self):
         """Features the tree splits on (model.py:413-417).  For a tree that came from the grower the
         list is read off the node table on first access."""
+        if self._used_features is None and getattr(self, "_used_mask", None) is not None:
+            # a tree that came over the survivor exchange: the mask of its split features travelled with it
+            from .flat import reference_used_features
+
+            mask, feature_cols, class_vals = self._used_mask
+            split_names = [feature_cols[j] for j, hit in enumerate(mask) if hit]
+            self._used_features = reference_used_features(feature_cols, split_names, class_vals, len(split_names) > 0)
         if self._used_features is None and self._soa is not None and self._enc is not None:
             from .flat import reference_used_features_of_soa
 
