@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RFMC_ABI_VERSION 1
+#define RFMC_ABI_VERSION 2 /* 2: device draw plans, survivor exchange, jump polynomials */
 
 /* column kinds and arithmetic tags (tag | bits<<8 | signed<<16) */
 #define RFMC_KIND_NUMERIC 0
