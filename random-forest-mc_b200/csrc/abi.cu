@@ -649,17 +649,62 @@ static int batch_create_impl(rfmc_dataset* ds, int32_t n_slots, int32_t n_train,
     b->stream = st;
     const size_t g = (size_t)b->grid, ntp = (size_t)b->nt_pad, C = (size_t)ds->n_classes;
     int rc = 0;
-    if (idx_on_device) {
-        b->own_idx = false;
-        b->d_idx_train = const_cast<int32_t*>(idx_train);
-        b->d_idx_val = const_cast<int32_t*>(idx_val);
-    } else {
-        rc |= upload(&b->d_idx_train, idx_train, (size_t)n_slots * n_train, st);
-        rc |= upload(&b->d_idx_val, idx_val, (size_t)n_slots * n_val, st);
+    {
+        // All inputs leave through ONE pinned staging buffer and one copy.  A cudaMemcpyAsync from pageable memory
+        // is not asynchronous: the driver stages it itself, under a lock shared by every host thread of the fit, and
+        // the call waits for whatever the stream is still running (the previous plan's kernels) before it returns.
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t b_tr = idx_on_device ? 0 : al((size_t)n_slots * n_train * 4), b_va = idx_on_device ? 0 : al((size_t)n_slots * n_val * 4);
+        const size_t b_cs = al((size_t)n_cand * 4), b_fo = al(((size_t)n_cand + 1) * 4), b_fl = al((size_t)feat_off[n_cand] * 2);
+        const size_t total = b_tr + b_va + b_cs + b_fo + b_fl;
+        PinnedLease* lease = new PinnedLease(total);
+        uint8_t* d_in = nullptr;
+        if (lease->p != nullptr && dev_alloc((void**)&d_in, total) == cudaSuccess) {
+            uint8_t* h = (uint8_t*)lease->p;
+            size_t at = 0;
+            if (!idx_on_device) {
+                std::memcpy(h + at, idx_train, (size_t)n_slots * n_train * 4);
+                b->d_idx_train = (int32_t*)(d_in + at);
+                at += b_tr;
+                if (n_val) std::memcpy(h + at, idx_val, (size_t)n_slots * n_val * 4);
+                b->d_idx_val = (int32_t*)(d_in + at);
+                at += b_va;
+            }
+            std::memcpy(h + at, cand_slot, (size_t)n_cand * 4);
+            b->d_cand_slot = (int32_t*)(d_in + at);
+            at += b_cs;
+            std::memcpy(h + at, feat_off, ((size_t)n_cand + 1) * 4);
+            b->d_feat_off = (int32_t*)(d_in + at);
+            at += b_fo;
+            std::memcpy(h + at, feat_list, (size_t)feat_off[n_cand] * 2);
+            b->d_feat_list = (uint16_t*)(d_in + at);
+            b->d_inputs = d_in;
+            b->up_lease = lease;
+            if (cudaMemcpyAsync(d_in, h, total, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+                set_error(std::string("batch upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+            }
+            if (idx_on_device) {
+                b->d_idx_train = const_cast<int32_t*>(idx_train);
+                b->d_idx_val = const_cast<int32_t*>(idx_val);
+            }
+            b->own_idx = false;  // slices of d_inputs, or the plan's arrays
+        } else {
+            delete lease;
+            cudaGetLastError();
+            if (idx_on_device) {
+                b->own_idx = false;
+                b->d_idx_train = const_cast<int32_t*>(idx_train);
+                b->d_idx_val = const_cast<int32_t*>(idx_val);
+            } else {
+                rc |= upload(&b->d_idx_train, idx_train, (size_t)n_slots * n_train, st);
+                rc |= upload(&b->d_idx_val, idx_val, (size_t)n_slots * n_val, st);
+            }
+            rc |= upload(&b->d_cand_slot, cand_slot, (size_t)n_cand, st);
+            rc |= upload(&b->d_feat_off, feat_off, (size_t)n_cand + 1, st);
+            rc |= upload(&b->d_feat_list, feat_list, (size_t)feat_off[n_cand], st);
+        }
     }
-    rc |= upload(&b->d_cand_slot, cand_slot, (size_t)n_cand, st);
-    rc |= upload(&b->d_feat_off, feat_off, (size_t)n_cand + 1, st);
-    rc |= upload(&b->d_feat_list, feat_list, (size_t)feat_off[n_cand], st);
     rc |= reserve((uint8_t**)&b->d_cc, (size_t)n_slots * ds->n_features * ntp * ds->code_width);  // [slot][feature][row]
     rc |= reserve(&b->d_lab, (size_t)n_slots * ntp);
     rc |= reserve(&b->d_pos, g * 2 * ntp);
@@ -814,9 +859,14 @@ int rfmc_batch_destroy(rfmc_batch* b) {
         release(b->d_idx_train);
         release(b->d_idx_val);
     }
-    release(b->d_cand_slot);
-    release(b->d_feat_off);
-    release(b->d_feat_list);
+    if (b->d_inputs) {
+        release(b->d_inputs);
+        delete (PinnedLease*)b->up_lease;
+    } else {
+        release(b->d_cand_slot);
+        release(b->d_feat_off);
+        release(b->d_feat_list);
+    }
     release(b->d_cc);
     release(b->d_lab);
     release(b->d_pos);

@@ -80,6 +80,8 @@ struct rfmc_batch {
     int32_t* d_cand_slot = nullptr;
     int32_t* d_feat_off = nullptr;
     uint16_t* d_feat_list = nullptr;
+    void* d_inputs = nullptr;  // non-null: the five input arrays are slices of this one block (one pinned staging copy)
+    void* up_lease = nullptr;  // the pinned staging buffer of that copy, held until the batch is destroyed
     // per tree slot: compact [feature][row] codes and labels of the bootstrap rows (slot_gather_kernel)
     void* d_cc = nullptr;
     uint8_t* d_lab = nullptr;

@@ -282,6 +282,13 @@ __device__ __forceinline__ int size_class(int n) {
     return n <= TINY_MAX ? 0 : (n <= SMALL_MAX ? 1 : (n <= MEDIUM_MAX ? 2 : (n <= HUGE_MIN ? 3 : 4)));
 }
 
+// dynamic shared memory of a grower CTA: labels | positions | split bitmap | bitmap prefix
+template <typename PosT>
+__host__ __device__ __forceinline__ size_t smem_bits_offset(int nt_pad) {
+    const size_t lab = (((size_t)nt_pad + 15) / 16) * 16;
+    return (lab + (size_t)nt_pad * sizeof(PosT) + 15) / 16 * 16;
+}
+
 template <typename CodeT, typename PosT>
 struct CandCtx {
     const GrowArgs<CodeT, PosT>* a;
@@ -290,6 +297,7 @@ struct CandCtx {
     PosT* pos;  // nt_pad: every node owns a segment; small/tiny nodes partition it in place
     PosT* tmp;  // nt_pad (global): partition target of > 32-row nodes, copied back
     uint32_t* resna;  // this level's buffer
+    uint32_t* sbits;  // shared-memory bitmap of the level positions that split (nullptr: ranks come from resna)
     uint16_t* resfin;
     rfmc_node* nodes;
     int32_t* counts;
@@ -299,6 +307,11 @@ struct CandCtx {
     uint32_t base;  // node id of level position 0
     int level;
 };
+
+// A node that split marks its level position: the child numbering (phase 2 of a level) ranks the set bits.
+__device__ __forceinline__ void mark_split(uint32_t* sbits, uint32_t lpos, uint32_t na) {
+    if (sbits != nullptr && na > 0) atomicOr(&sbits[lpos >> 5], 1u << (lpos & 31));
+}
 
 __device__ __forceinline__ void write_leaf(rfmc_node* nd) {
     nd->feat = -1;
@@ -447,6 +460,7 @@ __device__ void process_tiny(const CandCtx<CodeT, PosT>& c, WorkItem* item) {
     }
     c.nodes[node] = nd;
     c.resna[w.lpos] = na_out;
+    mark_split(c.sbits, w.lpos, na_out);
     c.resfin[w.lpos] = (uint16_t)fin_out;
 }
 
@@ -750,6 +764,7 @@ __device__ void process_group(const CandCtx<CodeT, PosT>& c, WorkItem* items, ui
         }
         c.nodes[node] = nd;
         c.resna[w.lpos] = accepted ? na : 0u;
+        mark_split(c.sbits, w.lpos, accepted ? na : 0u);
         c.resfin[w.lpos] = (uint16_t)fin;
     }
 }
@@ -920,17 +935,27 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
                 if (cnt_a >= (uint32_t)a.mss && n - cnt_a >= (uint32_t)a.mss) {
                     accepted = true;
                     uint32_t oa = 0, ob = cnt_a;
-                    for (uint32_t base = 0; base < n; base += 32) {  // stable partition
-                        uint32_t i = base + lane;
-                        bool act = i < n;
-                        uint32_t pi = act ? (uint32_t)P[i] : 0u;
-                        uint32_t cv = act ? (uint32_t)col[pi] : 0u;
-                        bool go = act && (cat ? cv == t_part : cv >= t_part);
-                        uint32_t ma = __ballot_sync(FULL, go);
-                        uint32_t mb = __ballot_sync(FULL, act && !go);
-                        if (act) Pn[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi;
-                        oa += __popc(ma);
-                        ob += __popc(mb);
+                    for (uint32_t base = 0; base < n; base += 128) {  // stable partition, four gathers in flight per lane
+                        uint32_t pi[4], cv[4];
+                        bool act[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t i = base + u * 32 + lane;
+                            act[u] = i < n;
+                            pi[u] = act[u] ? (uint32_t)P[i] : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[pi[u]] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (base + u * 32 >= n) break;
+                            const bool go = act[u] && (cat ? cv[u] == t_part : cv[u] >= t_part);
+                            const uint32_t ma = __ballot_sync(FULL, go);
+                            const uint32_t mb = __ballot_sync(FULL, act[u] && !go);
+                            if (act[u]) Pn[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi[u];
+                            oa += __popc(ma);
+                            ob += __popc(mb);
+                        }
                     }
                     __syncwarp();
                     for (uint32_t i = lane; i < n; i += 32) P[i] = Pn[i];
@@ -959,6 +984,7 @@ __device__ void process_warp(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint
         }
         c.nodes[node] = nd;
         c.resna[w.lpos] = accepted ? na : 0u;
+        mark_split(c.sbits, w.lpos, accepted ? na : 0u);
         c.resfin[w.lpos] = (uint16_t)fin;
     }
 }
@@ -1201,17 +1227,27 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
                         ob += (s1 - s0) - s_part[w8];
                     }
                 }
-                for (uint32_t base = r0; base < r1; base += 32) {
-                    const uint32_t i = base + lane;
-                    const bool act = i < r1;
-                    const uint32_t pi = act ? (uint32_t)P[i] : 0u;
-                    const uint32_t cv = act ? (uint32_t)col[pi] : 0u;
-                    const bool go = act && (cat ? cv == t_part : cv >= t_part);
-                    const uint32_t ma = __ballot_sync(FULL, go);
-                    const uint32_t mb = __ballot_sync(FULL, act && !go);
-                    if (act) T[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi;
-                    oa += __popc(ma);
-                    ob += __popc(mb);
+                for (uint32_t base = r0; base < r1; base += 128) {  // four gathers in flight per lane
+                    uint32_t pi[4], cv[4];
+                    bool act[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t i = base + u * 32 + lane;
+                        act[u] = i < r1;
+                        pi[u] = act[u] ? (uint32_t)P[i] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cv[u] = act[u] ? (uint32_t)col[pi[u]] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (base + u * 32 >= r1) break;
+                        const bool go = act[u] && (cat ? cv[u] == t_part : cv[u] >= t_part);
+                        const uint32_t ma = __ballot_sync(FULL, go);
+                        const uint32_t mb = __ballot_sync(FULL, act[u] && !go);
+                        if (act[u]) T[go ? oa + __popc(ma & lt) : ob + __popc(mb & lt)] = (PosT)pi[u];
+                        oa += __popc(ma);
+                        ob += __popc(mb);
+                    }
                 }
                 __syncthreads();
                 for (uint32_t i = tid; i < n; i += GROW_THREADS) P[i] = T[i];
@@ -1238,6 +1274,7 @@ __device__ void process_cta(const CandCtx<CodeT, PosT>& c, WorkItem* item, uint3
         }
         c.nodes[node] = nd;
         c.resna[w.lpos] = accepted ? na : 0u;
+        mark_split(c.sbits, w.lpos, accepted ? na : 0u);
         c.resfin[w.lpos] = (uint16_t)(NOT_FINAL | (NOT_FINAL << 8));
     }
     __syncthreads();
@@ -1332,6 +1369,10 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
     PosT* pos = a.use_smem ? reinterpret_cast<PosT*>(s_dyn + (((size_t)a.nt_pad + 15) / 16) * 16)
                            : a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad;
     PosT* tmp = a.pos_g + (size_t)blockIdx.x * 2 * a.nt_pad + a.nt_pad;
+    // split bitmap of the level + exclusive popcount prefix per word (only with the shared-memory layout)
+    const uint32_t bit_words = (uint32_t)a.nt_pad / 32 + 1;
+    uint32_t* s_bits = a.use_smem ? reinterpret_cast<uint32_t*>(s_dyn + smem_bits_offset<PosT>(a.nt_pad)) : nullptr;
+    uint32_t* s_pref = a.use_smem ? s_bits + bit_words : nullptr;
 
     for (int cand = blockIdx.x; cand < a.n_cand; cand += gridDim.x) {
         CandCtx<CodeT, PosT> c;
@@ -1339,6 +1380,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
         c.pos = pos;
         c.tmp = tmp;
         c.resfin = a.resfin + (size_t)blockIdx.x * a.nt_pad;
+        c.sbits = s_bits;
         c.nodes = a.nodes + (size_t)cand * a.max_nodes;
         c.counts = a.counts + (size_t)cand * a.max_nodes * a.n_classes;
         c.votes = a.votes + (size_t)cand * a.max_nodes;
@@ -1391,6 +1433,9 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                 if (tid < 4) s_ticket[tid] = 0;
                 s_cnt[nb][tid] = 0;
             }
+            const uint32_t lvl_words = (width + 31) / 32;
+            if (s_bits != nullptr)
+                for (uint32_t i = tid; i < lvl_words; i += GROW_THREADS) s_bits[i] = 0u;
             __syncthreads();
 #ifdef RFMC_GROW_TIMING
             if (blockIdx.x == 0 && cand == 0 && tid == 0 && 16 + 8 * level + 7 < 8192) {
@@ -1438,27 +1483,49 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
             // ---- phase 2a: split rank of every level position (block-wide exclusive scan) ----
             // each warp owns a contiguous range of positions and walks it 32 at a time (coalesced);
             // pass 1 counts, pass 2 re-reads the flags and writes the exclusive ranks
-            const uint32_t per = ((width + GROW_WARPS * 32 - 1) / (GROW_WARPS * 32)) * 32;
-            const uint32_t p0 = (uint32_t)warp * per, p1 = (p0 + per < width) ? p0 + per : width;
-            uint32_t mine = 0;
-            for (uint32_t p = p0; p < p1; p += 32)
-                mine += __popc(__ballot_sync(FULL, (p + lane < p1) && resna_cur[p + lane] > 0));
-            if (lane == 0) s_wtot[warp] = mine;
-            __syncthreads();
-            uint32_t run = 0, splits = 0;
+            uint32_t splits = 0;
+            if (s_bits != nullptr) {
+                // the nodes that split set their bit while they were processed: rank = set bits below the position
+                if (warp == 0) {
+                    uint32_t run = 0;
+                    for (uint32_t w0 = 0; w0 < lvl_words; w0 += 32) {
+                        const uint32_t v = (w0 + lane < lvl_words) ? (uint32_t)__popc(s_bits[w0 + lane]) : 0u;
+                        uint32_t inc = v;
 #pragma unroll
-            for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
-                const uint32_t t = s_wtot[w8];
-                if (w8 < warp) run += t;
-                splits += t;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                            if (lane >= d) inc += t;
+                        }
+                        if (w0 + lane < lvl_words) s_pref[w0 + lane] = run + inc - v;
+                        run += __shfl_sync(FULL, inc, 31);
+                    }
+                    if (lane == 0) s_wtot[0] = run;
+                }
+                __syncthreads();
+                splits = s_wtot[0];
+            } else {
+                const uint32_t per = ((width + GROW_WARPS * 32 - 1) / (GROW_WARPS * 32)) * 32;
+                const uint32_t p0 = (uint32_t)warp * per, p1 = (p0 + per < width) ? p0 + per : width;
+                uint32_t mine = 0;
+                for (uint32_t p = p0; p < p1; p += 32)
+                    mine += __popc(__ballot_sync(FULL, (p + lane < p1) && resna_cur[p + lane] > 0));
+                if (lane == 0) s_wtot[warp] = mine;
+                __syncthreads();
+                uint32_t run = 0;
+#pragma unroll
+                for (int w8 = 0; w8 < GROW_WARPS; ++w8) {
+                    const uint32_t t = s_wtot[w8];
+                    if (w8 < warp) run += t;
+                    splits += t;
+                }
+                for (uint32_t p = p0; p < p1; p += 32) {
+                    const bool in = p + lane < p1;
+                    const uint32_t bal = __ballot_sync(FULL, in && resna_cur[p + lane] > 0);
+                    if (in) rank[p + lane] = run + __popc(bal & lt);
+                    run += __popc(bal);
+                }
+                __syncthreads();
             }
-            for (uint32_t p = p0; p < p1; p += 32) {
-                const bool in = p + lane < p1;
-                const uint32_t bal = __ballot_sync(FULL, in && resna_cur[p + lane] > 0);
-                if (in) rank[p + lane] = run + __popc(bal & lt);
-                run += __popc(bal);
-            }
-            __syncthreads();
             RFMC_TICK(16 + 8 * level + 2);
             // ---- phase 2b: child ids, finished leaves, next level's work lists ----
             const uint32_t base_next = base + width;
@@ -1471,16 +1538,23 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
                         if (qq >= n_medium) { qq -= n_medium; rc = 3;
                             if (qq >= n_large) { qq -= n_large; rc = 4; } } } }
                 const WorkItem w = cur[reg0[rc] + qq];
+                uint32_t s;
+                if (s_bits != nullptr) {
+                    const uint32_t bw = s_bits[w.lpos >> 5], bit = 1u << (w.lpos & 31);
+                    if (!(bw & bit)) continue;
+                    s = s_pref[w.lpos >> 5] + (uint32_t)__popc(bw & (bit - 1u));
+                } else {
+                    if (resna_cur[w.lpos] == 0) continue;
+                    s = rank[w.lpos];
+                }
                 const uint32_t na = resna_cur[w.lpos];
-                if (na == 0) continue;
-                const uint32_t s = rank[w.lpos];
                 const uint32_t fin = c.resfin[w.lpos];
                 c.nodes[base + w.lpos].child = (int32_t)(base_next + 2 * s);
 #pragma unroll
                 for (int side = 0; side < 2; ++side) {
                     const uint32_t lo = side ? w.lo + na : w.lo, hi = side ? w.hi : w.lo + na;
                     const uint32_t sz = hi - lo, cpos = 2 * s + side, f8 = (fin >> (8 * side)) & 0xFFu;
-                    resna_nxt[cpos] = 0;
+                    if (s_bits == nullptr) resna_nxt[cpos] = 0;  // positions that never become work items must rank as leaves
                     if (f8 != NOT_FINAL) {  // finished leaf: all rows of one class
                         const uint32_t cn = base_next + cpos;
                         write_leaf(&c.nodes[cn]);
@@ -1547,7 +1621,7 @@ __global__ void __launch_bounds__(GROW_THREADS, RFMC_GROW_MIN_CTAS) grow_kernel(
 
 template <typename CodeT, typename PosT>
 static size_t smem_bytes(int nt_pad) {
-    return (((size_t)nt_pad + 15) / 16) * 16 + (size_t)nt_pad * sizeof(PosT);
+    return smem_bits_offset<PosT>(nt_pad) + 2 * ((size_t)nt_pad / 32 + 1) * sizeof(uint32_t);
 }
 constexpr size_t SMEM_BUDGET = 100 * 1024;  // per CTA, keeps >= 2 CTAs per SM
 
@@ -1610,8 +1684,8 @@ static int launch_grow_t(rfmc_batch* b, cudaStream_t stream) {
     if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[1], stream));
     k<<<b->grid, GROW_THREADS, smem, stream>>>(a);
     RFMC_CUDA(cudaGetLastError());
-    if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[2], stream));
     b->launches = 2;
+    if (b->timing) RFMC_CUDA(cudaEventRecord(b->ev[2], stream));
     return 0;
 }
 

@@ -494,6 +494,31 @@ def encode_dataset_device(dataset_numpy, feature_cols, numeric_cols, target_col,
     return enc, dev
 
 
+class FlatFeatureLists:
+    """The feature id lists of a plan's candidates stored back to back (what rfmc_batch_create takes): a
+    read-only sequence of per-candidate arrays that costs the fit loop no Python work per candidate."""
+
+    def __init__(self, flat: np.ndarray, counts: np.ndarray):
+        self.flat = np.ascontiguousarray(flat)
+        self.counts = np.ascontiguousarray(counts, dtype=np.int64).reshape(-1)
+        self.off = np.zeros(len(self.counts) + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.off[1:])
+
+    def __len__(self):
+        return len(self.counts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self.flat[self.off[i] : self.off[i + 1]]
+
+    def __iter__(self):
+        o = self.off.tolist()
+        return (self.flat[a:b] for a, b in zip(o[:-1], o[1:]))
+
+
 class GrowBatch:
     """rfmc_batch handle: grow + score a batch of candidates (plantTree + validationTree)."""
 
@@ -514,9 +539,13 @@ class GrowBatch:
         self.ds = ds
         cand_slot = np.ascontiguousarray(cand_slot, dtype=np.int32)
         self.n_cand = len(cand_slot)
-        off = np.zeros(self.n_cand + 1, dtype=np.int32)
-        off[1:] = np.cumsum([len(f) for f in feat_lists])
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint16) for f in feat_lists]), dtype=np.uint16)
+        if isinstance(feat_lists, FlatFeatureLists):
+            off = feat_lists.off.astype(np.int32)
+            flat = feat_lists.flat.astype(np.uint16)
+        else:
+            off = np.zeros(self.n_cand + 1, dtype=np.int32)
+            off[1:] = np.cumsum([len(f) for f in feat_lists])
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint16) for f in feat_lists]), dtype=np.uint16)
         self._stream = _stream_ptr(stream)
         h = _p()
         if plan is not None:

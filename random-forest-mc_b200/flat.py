@@ -14,6 +14,8 @@ key order and Python/numpy value types:
 
 from __future__ import annotations
 
+import gc
+
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -45,36 +47,79 @@ class TreeSoA:
 
 
 def soa_to_dict(tree: TreeSoA, enc: EncodedDataset, type_of_cols: Optional[dict] = None) -> dict:
-    """Materialise the nested dict the reference would have built for this tree."""
+    """Materialise the nested dict the reference would have built for this tree.
+
+    Nodes are in BFS order (a child's index is larger than its parent's), so the dicts are built bottom-up in
+    one reverse pass over plain Python lists; everything that can be computed for all nodes at once (depths,
+    leaf probabilities, split values) is, because a forest grown to purity has millions of nodes and
+    ``model2dict()`` / ``tree.data`` pay this per node."""
     nodes, counts = tree.nodes, tree.counts
-    feat, thr, child, flags, sval = (nodes[k] for k in ("feat", "thr", "child", "flags", "sval"))
+    n = len(nodes)
+    feat_a = nodes["feat"]
+    feat, thr, child, flags, sval = (nodes[k].tolist() for k in ("feat", "thr", "child", "flags", "sval"))
     labels = enc.class_sorted
-    holder = {}
-    todo = [(0, 1, holder, "root")]
-    while todo:
-        i, depth, slot, key = todo.pop()
-        f = int(feat[i])
+    cols = enc.columns
+    names = [c.name for c in cols]
+    if type_of_cols is not None:
+        kinds = [type_of_cols[c.name] for c in cols]
+    else:
+        kinds = ["categorical" if c.kind == KIND_CATEGORICAL else "numeric" for c in cols]
+    uniq = {}  # per used column: its value table as a list of numpy scalars (what uniq[k] returns)
+
+    # depth of every node (root = 1): parents come first in BFS order
+    depth = [1] * n
+    for i in range(n):
+        if feat[i] >= 0:
+            c = child[i]
+            depth[c] = depth[c + 1] = depth[i] + 1
+    dstr = {}
+
+    # leaf payloads {label: count / total} in sorted-label order, np.float64 values as genLeaf's (model.py:222-229)
+    leaf_idx = np.flatnonzero(feat_a < 0)
+    cnt = np.asarray(counts)[leaf_idx]
+    tot = cnt.sum(axis=1)
+    rr, cc = np.nonzero(cnt)  # row-major: per leaf, classes ascending
+    vals = list(cnt[rr, cc].astype(np.int64) / tot[rr]) if len(rr) else []
+    lab_of = [labels[c] for c in cc.tolist()]
+    first = np.searchsorted(rr, np.arange(len(leaf_idx) + 1)).tolist()
+    leaf_pos = dict(zip(leaf_idx.tolist(), range(len(leaf_idx))))
+
+    objs = [None] * n
+    special = FLAG_CATEGORICAL | FLAG_TWO_ROW
+    # tens of thousands of small dicts and no reference cycle among them: the cyclic collector would only
+    # re-traverse the growing forest again and again
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        _build_dicts(n, feat, thr, child, flags, sval, depth, dstr, leaf_pos, first, lab_of, vals, uniq, cols, names, kinds, objs, special)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    return objs[0]
+
+
+def _build_dicts(n, feat, thr, child, flags, sval, depth, dstr, leaf_pos, first, lab_of, vals, uniq, cols, names, kinds, objs, special):
+    for i in range(n - 1, -1, -1):
+        f = feat[i]
         if f < 0:
-            row = counts[i]
-            total = int(row.sum())
-            leaf = {labels[c]: np.int64(row[c]) / total for c in np.flatnonzero(row)}
-            slot[key] = {"leaf": leaf, "depth": f"{depth}#"}
+            k = leaf_pos[i]
+            a, b = first[k], first[k + 1]
+            leaf = {lab_of[a]: vals[a]} if b - a == 1 else dict(zip(lab_of[a:b], vals[a:b]))
+            d = depth[i]
+            ds = dstr.get(d)
+            if ds is None:
+                ds = dstr[d] = f"{d}#"
+            objs[i] = {"leaf": leaf, "depth": ds}
             continue
-        col = enc.columns[f]
-        fl = int(flags[i])
-        if fl & FLAG_CATEGORICAL or fl & FLAG_TWO_ROW:
-            value = col.uniq[int(thr[i]) - 1]
+        if flags[i] & special:
+            u = uniq.get(f)
+            if u is None:
+                u = uniq[f] = list(cols[f].uniq)
+            value = u[thr[i] - 1]
         else:
-            value = float(sval[i])
-        kind = "categorical" if col.kind == KIND_CATEGORICAL else "numeric"
-        if type_of_cols is not None:
-            kind = type_of_cols[col.name]
-        body = {"feat_type": kind, "split_val": value, ">=": None, "<": None}
-        slot[key] = {col.name: {"split": body}}
-        c = int(child[i])
-        todo.append((c + 1, depth + 1, body, "<"))
-        todo.append((c, depth + 1, body, ">="))
-    return holder["root"]
+            value = sval[i]
+        c = child[i]
+        objs[i] = {names[f]: {"split": {"feat_type": kinds[f], "split_val": value, ">=": objs[c], "<": objs[c + 1]}}}
 
 
 def used_feature_ids(tree: TreeSoA) -> List[int]:

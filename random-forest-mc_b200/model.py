@@ -109,9 +109,14 @@ class _DeviceSlotState:
 
 
 class _PlanList(list):
-    """The slots of one plan; ``dev`` is the device draw plan that owns their row ids (or None)."""
+    """The slots of one plan; ``dev`` is the device draw plan that owns their row ids (or None).  ``rows`` /
+    ``feats`` / ``spec`` hold the whole plan's host arrays as the draw calls returned them (row ids [n_slots, n],
+    feature ids back to back, candidates per slot), so a launch needs no per-slot Python work."""
 
     dev = None
+    rows = None
+    feats = None
+    spec = 0
 
 
 class RandomForestMC(BaseRandomForestMC):
@@ -178,6 +183,10 @@ class RandomForestMC(BaseRandomForestMC):
         # replays, single-slot calls and draws wider than the device resolve always use the host walk.
         self.device_draws = os.environ.get("RFMC_DEVICE_DRAWS", "0") == "1"
         self.device_draw_min_slots = 2
+        # software pipelining of the fit loop (_fit_slots): plans of more than this many slots are cut into
+        # sub-plans so that the kernels and copies of one hide behind the draws of the next; 0 = one plan at a time
+        self.pipeline_slots = int(os.environ.get("RFMC_PIPELINE_SLOTS", "0"))
+        self.pipeline_min_words = int(os.environ.get("RFMC_PIPELINE_MIN_WORDS", "2000000"))
 
     # ---------------------------------------------------------------------------------------------
     # process_dataset (model.py:162-195)
@@ -350,8 +359,7 @@ class RandomForestMC(BaseRandomForestMC):
         if not self.temporal_features:
             # CPython's stream walked in one host call as well (engine.pyrandom_sample_plan)
             flat = engine.pyrandom_sample_plan(py_rng, len(cols), ks)
-            ends = np.cumsum(ks.reshape(-1))
-            per_cand = np.split(flat, ends[:-1])
+            per_cand = engine.FlatFeatureLists(flat, ks)
         else:
             per_cand = []
             where = {name: j for j, name in enumerate(cols)}
@@ -360,6 +368,10 @@ class RandomForestMC(BaseRandomForestMC):
                 per_cand.append(np.array([where[f] for f in out], dtype=np.int32))
         plan = _PlanList()
         plan.dev = dev
+        plan.rows = (T, V)
+        plan.feats = per_cand if isinstance(per_cand, engine.FlatFeatureLists) else None
+        plan.spec = spec
+        per_cand = list(per_cand)
         for s in range(n_plan):
             if dev is not None:
                 start = (_DeviceSlotState(dev, s, st), ("replay", py_state0, K, spec, s))
@@ -471,18 +483,30 @@ class RandomForestMC(BaseRandomForestMC):
 
     def _grow_plan(self, plan, stream=None):
         """One launch for every (slot, candidate) of the plan.  Returns (batch, first cand id per slot)."""
-        slot_of, feats, first = [], [], []
-        for s, p in enumerate(plan):
-            first.append(len(feats))
-            for f in p[2]:
-                slot_of.append(s)
-                feats.append(f)
         dev = getattr(plan, "dev", None)
+        whole = getattr(plan, "feats", None)
+        if whole is not None and plan.spec > 0 and len(whole) == len(plan) * plan.spec:
+            # a plan as _draw_plan made it: the arrays of the draw calls go to the launch as they are
+            spec = plan.spec
+            slot_of = np.repeat(np.arange(len(plan), dtype=np.int32), spec)
+            feats = whole
+            first = list(range(0, len(plan) * spec, spec))
+            rows = plan.rows
+        else:
+            slot_of, feats, first, rows = [], [], [], None
+            for s, p in enumerate(plan):
+                first.append(len(feats))
+                for f in p[2]:
+                    slot_of.append(s)
+                    feats.append(f)
         if dev is not None:  # the row ids are already in HBM
             b = engine.GrowBatch(self._dev_dataset, None, None, slot_of, feats, self.max_depth, self.min_samples_split, stream, plan=dev)
         else:
-            idx_T = np.stack([p[0] for p in plan])
-            idx_V = np.stack([p[1] for p in plan])
+            if rows is not None and rows[0] is not None:
+                idx_T, idx_V = rows
+            else:
+                idx_T = np.stack([p[0] for p in plan])
+                idx_V = np.stack([p[1] for p in plan])
             b = engine.GrowBatch(self._dev_dataset, idx_T, idx_V, slot_of, feats, self.max_depth, self.min_samples_split, stream)
         b.run()
         return b, first
@@ -492,81 +516,145 @@ class RandomForestMC(BaseRandomForestMC):
         with np.errstate(invalid="ignore", divide="ignore"):
             return np.float64(correct) / np.float64(n_val) if n_val else np.float64("nan")
 
+    def _scores(self, correct, n_val):
+        """``_score`` for a whole launch: float64 division element by element, np.float64 scalars out."""
+        c = np.asarray(correct).astype(np.float64)
+        if not n_val:
+            return np.full(len(c), np.nan, dtype=np.float64)
+        return c / np.float64(n_val)
+
     def _fit_slots(self, n_slots: int, stream=None):
-        """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's."""
+        """Grow ``n_slots`` surviving trees; the committed RNG stream equals the serial reference's.
+
+        Plans are software-pipelined: while the GPU grows and scores plan A, the host already draws (and
+        launches) plan B from the stream state A leaves behind if its speculation holds; A is then judged
+        and its survivors fetched while the GPU works on B.  A plan that needs a rewind (a slot that used
+        fewer or more draws than assumed) voids its successor: B is dropped, the streams are restored from
+        A's snapshots, and drawing resumes there -- the committed draws are the reference's either way."""
         if n_slots > 0:
             self._reference_preflight()
         self._require_dataset()
         trees: List[DecisionTreeMC] = []
-        stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0,
+        stats = dict(candidates_grown=0, candidates_used=0, gpu_launches=0, rewinds=0, batches=0, plans_dropped=0,
                      t_draw=0.0, t_launch=0.0, t_wait=0.0, t_fetch=0.0)
         from time import perf_counter as _now
 
         K = max(1, int(self.max_discard_trees))
         cap = max(1, min(self.max_candidates_per_launch, self.max_batch_bytes // max(1, self._candidate_bytes())))
-        assume_pass = False  # hypothesis on the candidates a slot consumes: K, or 1 when trees mostly pass
+        state = dict(assume_pass=False, avg_commit=float("inf"))  # hypothesis on the candidates a slot consumes: K, or 1 when trees mostly pass
         recent_used: List[int] = []
-        avg_commit = float("inf")
-        while len(trees) < n_slots:
-            spec = 1 if assume_pass else K
-            n_plan = min(n_slots - len(trees), max(1, cap // spec))
-            if avg_commit != float("inf"):
-                n_plan = min(n_plan, max(4, int(4 * avg_commit) + 1))
+        # pipelining pays when a plan's draws take about as long as its kernels (numpy's stream costs one word per
+        # dataset row and slot); below that a second launch only adds latency (titanic-sized fits)
+        pipe = max(0, int(self.pipeline_slots))
+        if sum(len(r) for r in self.encoded.class_rows) * max(1, n_slots) < self.pipeline_min_words:
+            pipe = 0
+
+        def start(ahead: int):
+            """Draw and launch the next plan, ``ahead`` slots being in flight already (0: none)."""
+            spec = 1 if state["assume_pass"] else K
+            left = n_slots - len(trees) - ahead
+            n_plan = min(left, max(1, cap // spec))
+            if state["avg_commit"] != float("inf"):
+                n_plan = min(n_plan, max(4, int(4 * state["avg_commit"]) + 1))
+            if pipe and n_plan > pipe:
+                # sub-plans: about four per call, so that all but the last one's kernels and copies hide behind draws
+                n_plan = max(pipe, min(n_plan, 8 * pipe, -(-(n_slots) // 4)))
             t0 = _now()
             plan = self._draw_plan(n_plan, spec, stream)
             t1 = _now()
-            batch, first = self._grow_plan(plan, stream)
-            t2 = _now()
-            stats["t_draw"] += t1 - t0
-            stats["t_launch"] += t2 - t1
             try:
-                correct, _ = batch.results()
-                stats["t_wait"] += _now() - t2
-                stats["batches"] += 1
-                stats["gpu_launches"] += batch.launches
-                stats["candidates_grown"] += batch.n_cand
-                chosen: List[Tuple[int, float]] = []
-                resume = extend = None
-                for s, p in enumerate(plan):
-                    judge = _SlotJudge(self.th_start, self.delta_th, self.max_discard_trees, self.get_best_tree)
-                    for k in range(spec):
-                        if judge.feed(first[s] + k, self._score(correct[first[s] + k], batch.n_val)):
-                            break
-                    if not judge.done:
-                        # needs more candidates than were drawn: everything drawn after this slot is
-                        # off-stream; continue the slot from the state right after its last draw
-                        resume, extend = (p, spec), (p, judge)
-                        break
-                    if judge.choice is None:
-                        # every candidate of the slot scored 0.0: the reference dies on Tree.survived_score
-                        # (model.py:345) with both streams where this slot left them
-                        self._rewind_into_slot(p, judge.used)
-                        raise AttributeError("'NoneType' object has no attribute 'survived_score'")
-                    chosen.append((judge.choice, judge.best_score))
-                    stats["candidates_used"] += judge.used
-                    recent_used.append(judge.used)
-                    if judge.used != spec:
-                        resume = (p, judge.used)
-                        break
-                t3 = _now()
-                self._collect(batch, chosen, trees)
-                stats["t_fetch"] += _now() - t3
-                committed = len(chosen)
-                if resume is not None and not (extend is None and resume[0] is plan[-1] and resume[1] == spec):
-                    stats["rewinds"] += 1
-                    self._rewind_into_slot(resume[0], resume[1])
-                if extend is not None:
-                    trees.append(self._extend_slot(extend[0], extend[1], batch, stream, stats))
-                    recent_used.append(extend[1].used)
-                    committed += 1
-            finally:
-                batch.close()
+                batch, first = self._grow_plan(plan, stream)
+            except BaseException:
                 if getattr(plan, "dev", None) is not None:
                     plan.dev.close()
-            avg_commit = committed if avg_commit == float("inf") else 0.5 * avg_commit + 0.5 * committed
+                raise
+            stats["t_draw"] += t1 - t0
+            stats["t_launch"] += _now() - t1
+            return plan, batch, first, spec
+
+        def drop(rec):
+            if rec is None:
+                return
+            plan, batch = rec[0], rec[1]
+            batch.close()
+            if getattr(plan, "dev", None) is not None:
+                plan.dev.close()
+
+        def finish(rec) -> bool:
+            """Judge one plan, collect its survivors; True when every slot used exactly the draws assumed."""
+            plan, batch, first, spec = rec
+            t2 = _now()
+            correct, _ = batch.results()
+            stats["t_wait"] += _now() - t2
+            stats["batches"] += 1
+            stats["gpu_launches"] += batch.launches
+            stats["candidates_grown"] += batch.n_cand
+            chosen: List[Tuple[int, float]] = []
+            resume = extend = None
+            scores = self._scores(correct, batch.n_val)
+            for s, p in enumerate(plan):
+                judge = _SlotJudge(self.th_start, self.delta_th, self.max_discard_trees, self.get_best_tree)
+                for k in range(spec):
+                    if judge.feed(first[s] + k, scores[first[s] + k]):
+                        break
+                if not judge.done:
+                    # needs more candidates than were drawn: everything drawn after this slot is
+                    # off-stream; continue the slot from the state right after its last draw
+                    resume, extend = (p, spec), (p, judge)
+                    break
+                if judge.choice is None:
+                    # every candidate of the slot scored 0.0: the reference dies on Tree.survived_score
+                    # (model.py:345) with both streams where this slot left them
+                    self._rewind_into_slot(p, judge.used)
+                    raise AttributeError("'NoneType' object has no attribute 'survived_score'")
+                chosen.append((judge.choice, judge.best_score))
+                stats["candidates_used"] += judge.used
+                recent_used.append(judge.used)
+                if judge.used != spec:
+                    resume = (p, judge.used)
+                    break
+            t3 = _now()
+            self._collect(batch, chosen, trees)
+            stats["t_fetch"] += _now() - t3
+            committed = len(chosen)
+            clean = resume is None and extend is None
+            if resume is not None and not (extend is None and resume[0] is plan[-1] and resume[1] == spec):
+                stats["rewinds"] += 1
+                self._rewind_into_slot(resume[0], resume[1])
+            if extend is not None:
+                trees.append(self._extend_slot(extend[0], extend[1], batch, stream, stats))
+                recent_used.append(extend[1].used)
+                committed += 1
+            state["avg_commit"] = committed if state["avg_commit"] == float("inf") else 0.5 * state["avg_commit"] + 0.5 * committed
             if len(recent_used) >= 4:
                 tail = recent_used[-16:]
-                assume_pass = K > 1 and (sum(1 for u in tail if u == 1) * 2 > len(tail))
+                state["assume_pass"] = K > 1 and (sum(1 for u in tail if u == 1) * 2 > len(tail))
+            return clean
+
+        cur = nxt = None
+        last_clean = True
+        try:
+            if n_slots > 0:
+                cur = start(0)
+            while cur is not None:
+                # the successor is drawn before this plan is judged only while plans keep their promise
+                if pipe and last_clean and len(trees) + len(cur[0]) < n_slots:
+                    nxt = start(len(cur[0]))
+                try:
+                    last_clean = finish(cur)
+                finally:
+                    drop(cur)
+                    cur = None
+                if nxt is not None and not last_clean:
+                    stats["plans_dropped"] += 1
+                    drop(nxt)
+                    nxt = None
+                cur, nxt = nxt, None
+                if cur is None and len(trees) < n_slots:
+                    cur = start(0)
+        finally:
+            drop(cur)
+            drop(nxt)
         for t in trees:
             t.features = self.feature_cols  # used_features is derived from the node table on first access
         self.fit_stats = stats

@@ -36,6 +36,28 @@ def test_fit_through_device_draw_plans_matches_reference(name, cap):
     assert fake_engine.FakeDrawPlan.created > before
 
 
+@pytest.mark.parametrize("name", ["titanic_c1", "mixed_feat", "mixed_nobest", "mixed_default", "ties_default"])
+@pytest.mark.parametrize("cap,sub", [(4096, 1), (4096, 2), (4096, 4), (3, 1), (7, 2), (16, 1)])
+@pytest.mark.parametrize("device_draws", [False, True])
+def test_pipelined_plans_match_reference(name, cap, sub, device_draws):
+    """The software-pipelined fit loop (plan B drawn and launched before plan A is judged; B dropped when A
+    needs a rewind), forced on for small data: same forest, consumed candidates and RNG end states."""
+    g, m = model_checks.check_fit_matches_reference(
+        name, pipeline_min_words=0, pipeline_slots=sub, max_candidates_per_launch=cap, device_draws=device_draws, device_draw_min_slots=1)
+    assert m.fit_stats["batches"] >= 1 and m.fit_stats["plans_dropped"] >= 0
+
+
+def test_pipelined_plans_drop_successor_on_rewind():
+    """A forest whose slots stop early under full speculation rewinds: the successor drawn ahead is dropped."""
+    g, m = model_checks.check_fit_matches_reference("mixed_nobest", pipeline_min_words=0, pipeline_slots=1)
+    assert m.fit_stats["rewinds"] == 0 or m.fit_stats["plans_dropped"] >= 0
+    dropped = 0
+    for name in ("titanic_c1", "mixed_feat", "mixed_nobest", "mixed_default"):
+        _, mm = model_checks.check_fit_matches_reference(name, pipeline_min_words=0, pipeline_slots=1, max_candidates_per_launch=3)
+        dropped += mm.fit_stats["plans_dropped"]
+    assert dropped > 0
+
+
 def test_persistence_and_merge():
     g, m = model_checks.fitted_model("mixed_default")
     model_checks.check_persistence_and_merge(g, m)
