@@ -338,6 +338,67 @@ static void build_tops(const rfmc_pnode* nodes, const int64_t* roots, int32_t n_
     }
 }
 
+// Compact layout for forests of SMALL trees (the reference's default configuration grows trees of a few dozen
+// nodes): 8-byte records {feat | lo << 16, span | next << 16} in per-tree BFS order, children adjacent ('>=' at
+// next, '<' at next + 1, tree-relative).  One unsigned compare serves every node kind:
+//     go '>=' child  <=>  (code - lo) <= span      numeric: lo = thr, span = 0xFFFF - thr;  categorical: span = 0;
+//                                                  leaf: lo = 0, span = 0xFFFF, next = itself (the walk stays put)
+// so a walk is a fixed number of identical steps (the tree's depth) without a leaf test.  Trees are grouped into
+// stages of at most `stage_nodes` records that the vote kernel copies to shared memory whole.  Returns false
+// when the forest is not eligible (a tree larger than a stage, codes or feature ids too wide).
+constexpr uint32_t SMALL_STAGE_NODES = 1024, SMALL_STAGE_TREES = 64;
+static bool build_compact(const rfmc_pnode* nodes, const int64_t* roots, int32_t n_trees, std::vector<uint32_t>& rec,
+                          std::vector<uint32_t>& pay, std::vector<uint32_t>& tree_at, std::vector<uint8_t>& depth,
+                          std::vector<uint32_t>& stage) {
+    rec.clear();
+    pay.clear();
+    tree_at.assign(1, 0u);
+    depth.clear();
+    stage.assign(1, 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> queue;  // (node, depth)
+    uint32_t in_stage = 0;
+    for (int32_t t = 0; t < n_trees; ++t) {
+        const uint32_t base = (uint32_t)pay.size();
+        queue.clear();
+        queue.emplace_back((uint32_t)roots[t], 0u);
+        uint32_t used = 1, deepest = 0;  // records handed out so far (tree-relative)
+        for (size_t q = 0; q < queue.size(); ++q) {
+            if (queue.size() > SMALL_STAGE_NODES) return false;
+            const rfmc_pnode& p = nodes[queue[q].first];
+            const uint32_t d = queue[q].second;
+            if (p.feat_flags & RFMC_PNODE_LEAF) {
+                rec.push_back(0u);
+                rec.push_back(0xFFFFu | ((uint32_t)q << 16));
+                pay.push_back(p.thr);
+                deepest = d > deepest ? d : deepest;
+                continue;
+            }
+            const uint32_t f = p.feat_flags & 0xFFFFu;
+            if (f >= 0x8000u) return false;
+            if (p.thr != 0xFFFFFFFFu && p.thr > 65534u) return false;
+            const uint32_t lo = p.thr == 0xFFFFFFFFu ? 0xFFFFu : p.thr;
+            const uint32_t span = (p.feat_flags & RFMC_PNODE_CATEGORICAL) ? 0u : (0xFFFFu - lo);
+            rec.push_back(f | (lo << 16));
+            rec.push_back(span | (used << 16));
+            pay.push_back(0u);
+            queue.emplace_back(p.child, d + 1);      // '>=' child at `used`
+            queue.emplace_back(p.child + 1, d + 1);  // '<' child at `used + 1`
+            used += 2;
+        }
+        if (deepest > 255u) return false;
+        const uint32_t n = (uint32_t)queue.size();
+        if (in_stage + n > SMALL_STAGE_NODES || (uint32_t)t - stage.back() >= SMALL_STAGE_TREES) {
+            stage.push_back((uint32_t)t);
+            in_stage = 0;
+        }
+        in_stage += n;
+        depth.push_back((uint8_t)deepest);
+        tree_at.push_back(base + n);
+    }
+    stage.push_back((uint32_t)n_trees);
+    return true;
+}
+
 extern "C" {
 
 int rfmc_abi_version(void) { return RFMC_ABI_VERSION; }
@@ -928,6 +989,16 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
         f->top_levels = levels;
         rc |= upload((uint32_t**)&f->d_tops, tops.data(), tops.size(), 0);
     }
+    std::vector<uint32_t> crec, cpay, ctree, cstage;
+    std::vector<uint8_t> cdepth;
+    if (!rc && build_compact(nodes, tree_root, n_trees, crec, cpay, ctree, cdepth, cstage)) {
+        rc |= upload((uint32_t**)&f->d_crec, crec.data(), crec.size(), 0);
+        rc |= upload(&f->d_cpay, cpay.data(), cpay.size(), 0);
+        rc |= upload(&f->d_ctree, ctree.data(), ctree.size(), 0);
+        rc |= upload(&f->d_cdepth, cdepth.data(), cdepth.size(), 0);
+        rc |= upload(&f->d_cstage, cstage.data(), cstage.size(), 0);
+        f->n_stages = (int32_t)cstage.size() - 1;
+    }
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) {
         set_error("forest upload failed");
         rc = 1;
@@ -954,6 +1025,11 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     release(f->d_blocks);
     release(f->d_root_b);
     release(f->d_tops);
+    release(f->d_crec);
+    release(f->d_cpay);
+    release(f->d_ctree);
+    release(f->d_cdepth);
+    release(f->d_cstage);
     release(f->d_thresholds);
     release(f->d_thr_off);
     delete f;

@@ -165,6 +165,13 @@ struct rfmc_forest {
     int64_t n_blocks = 0;
     uint2* d_tops = nullptr;  // per tree: the top `top_levels` levels as an implicit heap of 8-byte records
     int32_t top_levels = 0;
+    // compact layout of a forest of small trees (predict_small_kernel): whole trees are staged in shared memory
+    uint2* d_crec = nullptr;        // per node {feat | lo << 16, span | next << 16}, tree-relative child index
+    uint32_t* d_cpay = nullptr;     // per node: payload index of a leaf
+    uint32_t* d_ctree = nullptr;    // [n_trees + 1] first record of every tree
+    uint8_t* d_cdepth = nullptr;    // [n_trees] levels to walk (depth of the deepest leaf)
+    uint32_t* d_cstage = nullptr;   // [n_stages + 1] first tree of every shared-memory stage
+    int32_t n_stages = 0;
     double* d_thresholds = nullptr;  // code book of the frame encoder (rfmc_forest_set_codebook)
     int64_t* d_thr_off = nullptr;
     int32_t n_features_book = 0;

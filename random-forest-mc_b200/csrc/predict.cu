@@ -38,6 +38,13 @@ struct PredictArgs {
     const uint32_t* root_b;  // block of every tree's root
     const uint2* tops;       // every tree's top `top_levels` levels as an implicit heap of 8-byte records
     int32_t top_levels;      // even, >= 2 (0: no tops)
+    // compact layout of a forest of small trees (nullptr: not eligible), see build_compact in abi.cu
+    const uint2* crec;
+    const uint32_t* cpay;
+    const uint32_t* ctree;
+    const uint8_t* cdepth;
+    const uint32_t* cstage;
+    int32_t n_stages;
     int32_t n_trees;
     const uint8_t* vote;
     const uint8_t* vote_absent;
@@ -445,9 +452,145 @@ __global__ void __launch_bounds__(TOP_THREADS) predict_top_kernel(PredictArgs a)
     if (a.labels_out) a.labels_out[row] = best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vote kernel for forests of SMALL trees (the reference's default configuration: 10 + 10 rows per class grow
+// trees of a few dozen nodes; BASELINE config 5 votes 4,096 of them).  The generic kernel above spends ~27
+// issue slots per tree level on leaf tests, node-kind selects and per-walk bookkeeping.  Here the forest is
+// laid out so that a level is the same handful of instructions for every node kind (abi.cu, build_compact):
+//     rec = stage[idx];  go = (row[rec.feat] - rec.lo) <= rec.span;  idx = rec.next + !go
+// a leaf points at itself, so every row of the CTA walks a tree for exactly `depth[tree]` steps: no leaf test,
+// no divergence.  Whole trees (up to 1,024 records per stage) are copied to shared memory by the CTA and
+// walked from there, SMALL_ILP trees in flight per thread; the leaves are consumed in forest order with the
+// reference's fp64 multiply-then-add, exactly as above.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_STAGE = 1024;  // records per stage (SMALL_STAGE_NODES in abi.cu)
+#ifndef RFMC_SMALL_ILP
+#define RFMC_SMALL_ILP 4
+#endif
+constexpr int SMALL_ILP = RFMC_SMALL_ILP;
+
+template <typename CodeT, int CMAX, int MODE>
+__global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);
+    uint32_t* s_pay = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SMALL_STAGE * sizeof(uint2));
+    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw + (size_t)SMALL_STAGE * (sizeof(uint2) + sizeof(uint32_t)));
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * SMALL_THREADS;
+    const int rows = (int)((a.n_rows - row0) < SMALL_THREADS ? (a.n_rows - row0) : SMALL_THREADS);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const CodeT*>(a.codes) + row0 * a.stride);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
+        const int words = (int)((size_t)rows * a.stride * sizeof(CodeT) / 4);
+        for (int i = tid; i < words; i += SMALL_THREADS) dst[i] = __ldg(&src[i]);
+    }
+    const bool live = tid < rows;
+    const CodeT* myrow = tile + (size_t)(live ? tid : 0) * a.stride;
+    const int C = a.n_classes;
+    double acc[CMAX];
+    uint32_t cnt[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        acc[c] = 0.0;
+        cnt[c] = 0;
+    }
+
+    for (int s = 0; s < a.n_stages; ++s) {
+        const int t0 = (int)__ldg(&a.cstage[s]), t1 = (int)__ldg(&a.cstage[s + 1]);
+        const uint32_t n0 = __ldg(&a.ctree[t0]), n1 = __ldg(&a.ctree[t1]);
+        __syncthreads();  // the previous stage's walks (and, the first time, the row tile's stores) are done
+        for (uint32_t i = tid; i < n1 - n0; i += SMALL_THREADS) {
+            s_rec[i] = __ldg(&a.crec[n0 + i]);
+            s_pay[i] = __ldg(&a.cpay[n0 + i]);
+        }
+        __syncthreads();
+        for (int tg = t0; tg < t1; tg += SMALL_ILP) {
+            uint32_t base[SMALL_ILP], idx[SMALL_ILP];
+            int levels = 0;
+#pragma unroll
+            for (int k = 0; k < SMALL_ILP; ++k) {
+                const int t = tg + k < t1 ? tg + k : t1 - 1;  // a short last group walks its last tree again (result unused)
+                base[k] = __ldg(&a.ctree[t]) - n0;
+                idx[k] = 0u;
+                const int d = (int)__ldg(&a.cdepth[t]);
+                levels = d > levels ? d : levels;
+            }
+#pragma unroll 1
+            for (int l = 0; l < levels; ++l) {
+#pragma unroll
+                for (int k = 0; k < SMALL_ILP; ++k) {
+                    const uint2 rec = s_rec[base[k] + idx[k]];
+                    const uint32_t cv = (uint32_t)myrow[rec.x & 0xFFFFu];
+                    const bool go = (cv - (rec.x >> 16)) <= (rec.y & 0xFFFFu);
+                    idx[k] = (rec.y >> 16) + (go ? 0u : 1u);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SMALL_ILP; ++k) {
+                const int t = tg + k;
+                if (t >= t1) break;
+                const uint32_t payload = s_pay[base[k] + idx[k]];
+                if (MODE == 0 || MODE == 1) {
+                    const int v = a.vote[payload];
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
+                    } else {
+                        const double sc = __ldg(&a.scores[t]);
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c) acc[c] = __dadd_rn(acc[c], (c == v) ? sc : 0.0);
+                    }
+                } else {
+                    const double* p = a.probs + (size_t)payload * C;
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c)
+                            if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+                    } else {
+                        const double sc = __ldg(&a.scores[t]);
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c)
+                            if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), sc));
+                    }
+                }
+            }
+        }
+    }
+    if (!live) return;
+    const double denom = (MODE == 0 || MODE == 2) ? (double)a.n_trees : a.score_fsum;
+    const int64_t row = row0 + tid;
+    int best = 0;
+    double bestv = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            const double num = (MODE == 0) ? (double)cnt[c] : acc[c];
+            const double v = __ddiv_rn(num, denom);
+            if (a.probs_out) a.probs_out[row * C + c] = v;
+            if (c == 0 || v > bestv) {  // first maximum in class_vals order (forest.py:200-202)
+                bestv = v;
+                best = c;
+            }
+        }
+    }
+    if (a.labels_out) a.labels_out[row] = best;
+}
+
 template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT>
 static int launch_tile(const PredictArgs& a, cudaStream_t stream) {
     if (a.n_rows == 0) return 0;
+    if (!HAS_ABSENT && a.crec != nullptr && sizeof(CodeT) <= 2) {
+        const size_t smem = (size_t)SMALL_STAGE * (sizeof(uint2) + sizeof(uint32_t)) + (size_t)SMALL_THREADS * a.stride * sizeof(CodeT);
+        if (smem <= 100 * 1024) {  // two or more CTAs per SM
+            auto k = predict_small_kernel<CodeT, CMAX, MODE>;
+            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<(unsigned)((a.n_rows + SMALL_THREADS - 1) / SMALL_THREADS), SMALL_THREADS, smem, stream>>>(a);
+            RFMC_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     if (a.tops != nullptr && a.blocks != nullptr && a.top_levels >= 2) {
         const int heap_pad = ((1 << a.top_levels) + 1) & ~1;
         const size_t smem = (size_t)2 * TOP_GROUP * heap_pad * sizeof(uint2) + (size_t)TOP_THREADS * a.stride * sizeof(CodeT) +
@@ -539,6 +682,12 @@ int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n
     a.root_b = nullptr;
     a.tops = nullptr;
     a.top_levels = 0;
+    a.crec = nullptr;
+    a.cpay = nullptr;
+    a.ctree = nullptr;
+    a.cdepth = nullptr;
+    a.cstage = nullptr;
+    a.n_stages = 0;
     a.n_trees = f->n_trees;
     a.vote = f->d_vote;
     a.vote_absent = f->d_vote_absent;
@@ -577,6 +726,14 @@ int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t 
     // measured slower than the all-global blocked walk on B200 (profiles/r2_vote_staged_tops.md): opt-in only
     a.tops = (a.blocks != nullptr && getenv("RFMC_PRED_TOPS")) ? f->d_tops : nullptr;
     a.top_levels = f->top_levels;
+    const char* small_off = getenv("RFMC_PRED_SMALL");  // experiment knob: 0 = always the generic kernel
+    const bool small = f->d_crec != nullptr && code_width <= 2 && !(small_off && atoi(small_off) == 0);
+    a.crec = small ? f->d_crec : nullptr;
+    a.cpay = f->d_cpay;
+    a.ctree = f->d_ctree;
+    a.cdepth = f->d_cdepth;
+    a.cstage = f->d_cstage;
+    a.n_stages = f->n_stages;
     a.n_trees = f->n_trees;
     a.vote = f->d_vote;
     a.vote_absent = f->d_vote_absent;
