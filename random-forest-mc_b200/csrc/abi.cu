@@ -1011,6 +1011,25 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
     return 0;
 }
 
+/* test hook (not in the header; host code only, no device needed): the compact small-tree layout of a forest
+   (build_compact above).  Pass NULL buffers to query the sizes; returns 1 when the forest is not eligible. */
+int rfmc_debug_compact_layout(const rfmc_pnode* nodes, const int64_t* tree_root, int32_t n_trees, int64_t* n_records,
+                              int32_t* n_stages, uint32_t* rec_xy, uint32_t* pay, uint32_t* tree_at, uint8_t* depth,
+                              uint32_t* stage) {
+    std::vector<uint32_t> crec, cpay, ctree, cstage;
+    std::vector<uint8_t> cdepth;
+    if (!nodes || !tree_root || n_trees <= 0) return 1;
+    if (!build_compact(nodes, tree_root, n_trees, crec, cpay, ctree, cdepth, cstage)) return 1;
+    if (n_records) *n_records = (int64_t)cpay.size();
+    if (n_stages) *n_stages = (int32_t)cstage.size() - 1;
+    if (rec_xy) std::memcpy(rec_xy, crec.data(), crec.size() * 4);
+    if (pay) std::memcpy(pay, cpay.data(), cpay.size() * 4);
+    if (tree_at) std::memcpy(tree_at, ctree.data(), ctree.size() * 4);
+    if (depth) std::memcpy(depth, cdepth.data(), cdepth.size());
+    if (stage) std::memcpy(stage, cstage.data(), cstage.size() * 4);
+    return 0;
+}
+
 int rfmc_forest_destroy(rfmc_forest* f) {
     if (!f) return 0;
     cudaSetDevice(f->device);

@@ -470,12 +470,31 @@ constexpr int SMALL_STAGE = 1024;  // records per stage (SMALL_STAGE_NODES in ab
 #endif
 constexpr int SMALL_ILP = RFMC_SMALL_ILP;
 
+__device__ __forceinline__ uint32_t lds_code(uint32_t addr, uint8_t) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_code(uint32_t addr, uint16_t) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t lds_code(uint32_t addr, uint32_t) {  // instantiated, never launched (codes <= 16 bits only)
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 template <typename CodeT, int CMAX, int MODE>
 __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t REC_BYTES = 8u;
     uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);
-    uint32_t* s_pay = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SMALL_STAGE * sizeof(uint2));
-    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw + (size_t)SMALL_STAGE * (sizeof(uint2) + sizeof(uint32_t)));
+    uint32_t* s_pay = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SMALL_STAGE * REC_BYTES);
+    CodeT* tile = reinterpret_cast<CodeT*>(smem_raw + (size_t)SMALL_STAGE * (REC_BYTES + sizeof(uint32_t)));
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * SMALL_THREADS;
@@ -487,7 +506,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
         for (int i = tid; i < words; i += SMALL_THREADS) dst[i] = __ldg(&src[i]);
     }
     const bool live = tid < rows;
-    const CodeT* myrow = tile + (size_t)(live ? tid : 0) * a.stride;
+    const uint32_t rowaddr = (uint32_t)__cvta_generic_to_shared(tile + (size_t)(live ? tid : 0) * a.stride);
     const int C = a.n_classes;
     double acc[CMAX];
     uint32_t cnt[CMAX];
@@ -503,17 +522,19 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
         __syncthreads();  // the previous stage's walks (and, the first time, the row tile's stores) are done
         for (uint32_t i = tid; i < n1 - n0; i += SMALL_THREADS) {
             s_rec[i] = __ldg(&a.crec[n0 + i]);
-            s_pay[i] = __ldg(&a.cpay[n0 + i]);
+            const uint32_t payload = __ldg(&a.cpay[n0 + i]);
+            // hard votes: the leaf's class is looked up once per staged record instead of once per walk
+            s_pay[i] = (MODE == 0 || MODE == 1) ? (uint32_t)__ldg(&a.vote[payload]) : payload;
         }
         __syncthreads();
         for (int tg = t0; tg < t1; tg += SMALL_ILP) {
-            uint32_t base[SMALL_ILP], idx[SMALL_ILP];
+            uint32_t tb[SMALL_ILP], at[SMALL_ILP];  // shared-memory address of the tree's first record / of the current one
             int levels = 0;
 #pragma unroll
             for (int k = 0; k < SMALL_ILP; ++k) {
                 const int t = tg + k < t1 ? tg + k : t1 - 1;  // a short last group walks its last tree again (result unused)
-                base[k] = __ldg(&a.ctree[t]) - n0;
-                idx[k] = 0u;
+                tb[k] = rec_base + (__ldg(&a.ctree[t]) - n0) * REC_BYTES;
+                at[k] = tb[k];
                 const int d = (int)__ldg(&a.cdepth[t]);
                 levels = d > levels ? d : levels;
             }
@@ -521,19 +542,19 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
             for (int l = 0; l < levels; ++l) {
 #pragma unroll
                 for (int k = 0; k < SMALL_ILP; ++k) {
-                    const uint2 rec = s_rec[base[k] + idx[k]];
-                    const uint32_t cv = (uint32_t)myrow[rec.x & 0xFFFFu];
-                    const bool go = (cv - (rec.x >> 16)) <= (rec.y & 0xFFFFu);
-                    idx[k] = (rec.y >> 16) + (go ? 0u : 1u);
+                    uint32_t x, y;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(at[k]));
+                    const uint32_t cv = lds_code(rowaddr + (x & 0xFFFFu) * (uint32_t)sizeof(CodeT), CodeT());
+                    at[k] = tb[k] + (y >> 16) * REC_BYTES + ((cv - (x >> 16)) > (y & 0xFFFFu) ? REC_BYTES : 0u);
                 }
             }
 #pragma unroll
             for (int k = 0; k < SMALL_ILP; ++k) {
                 const int t = tg + k;
                 if (t >= t1) break;
-                const uint32_t payload = s_pay[base[k] + idx[k]];
+                const uint32_t payload = s_pay[(at[k] - rec_base) / REC_BYTES];
                 if (MODE == 0 || MODE == 1) {
-                    const int v = a.vote[payload];
+                    const int v = (int)payload;  // staged as the class already
                     if (MODE == 0) {
 #pragma unroll
                         for (int c = 0; c < CMAX; ++c) cnt[c] += (c == v) ? 1u : 0u;
@@ -544,15 +565,23 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
                     }
                 } else {
                     const double* p = a.probs + (size_t)payload * C;
+                    double pv[CMAX];
+                    if (CMAX == 4 && C == 4) {  // a payload's four probabilities are one aligned 32-byte row
+                        const double2 lo2 = __ldg(reinterpret_cast<const double2*>(p)), hi2 = __ldg(reinterpret_cast<const double2*>(p) + 1);
+                        pv[0] = lo2.x, pv[1] = lo2.y, pv[2 % CMAX] = hi2.x, pv[3 % CMAX] = hi2.y;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c) pv[c] = c < C ? __ldg(&p[c]) : 0.0;
+                    }
                     if (MODE == 2) {
 #pragma unroll
                         for (int c = 0; c < CMAX; ++c)
-                            if (c < C) acc[c] = __dadd_rn(acc[c], __ldg(&p[c]));
+                            if (c < C) acc[c] = __dadd_rn(acc[c], pv[c]);
                     } else {
                         const double sc = __ldg(&a.scores[t]);
 #pragma unroll
                         for (int c = 0; c < CMAX; ++c)
-                            if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(__ldg(&p[c]), sc));
+                            if (c < C) acc[c] = __dadd_rn(acc[c], __dmul_rn(pv[c], sc));
                     }
                 }
             }
@@ -587,18 +616,6 @@ static int launch_tile(const PredictArgs& a, cudaStream_t stream) {
             auto k = predict_small_kernel<CodeT, CMAX, MODE>;
             if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k<<<(unsigned)((a.n_rows + SMALL_THREADS - 1) / SMALL_THREADS), SMALL_THREADS, smem, stream>>>(a);
-            RFMC_CUDA(cudaGetLastError());
-            return 0;
-        }
-    }
-    if (a.tops != nullptr && a.blocks != nullptr && a.top_levels >= 2) {
-        const int heap_pad = ((1 << a.top_levels) + 1) & ~1;
-        const size_t smem = (size_t)2 * TOP_GROUP * heap_pad * sizeof(uint2) + (size_t)TOP_THREADS * a.stride * sizeof(CodeT) +
-                            (HAS_ABSENT ? (size_t)((a.n_features + 15) / 16 * 16) : 0);
-        if (smem <= 110 * 1024) {  // two CTAs per SM
-            auto k = predict_top_kernel<CodeT, CMAX, MODE, HAS_ABSENT>;
-            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<(unsigned)((a.n_rows + TOP_THREADS - 1) / TOP_THREADS), TOP_THREADS, smem, stream>>>(a);
             RFMC_CUDA(cudaGetLastError());
             return 0;
         }
