@@ -643,7 +643,7 @@ def run_b200(args):
         "frame_api": {"value": frame_e2e, "unit": "rows*trees/s", "seconds": frame_s, "h2d_bytes_per_step": raw_bytes,
                       "api": "model.testForest(DataFrame): host categorical mapping + pinned staging + GPU encode + vote + D2H labels"},
         "host_encode_s": t_encode,
-        "roofline": {"kernel": "rfmc::predict_kernel", "bound": "hbm", "achieved": pred_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pred_gbs / hbm_peak,
+        "roofline": {"kernel": dev.vote_kernel, "bound": "hbm", "achieved": pred_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pred_gbs / hbm_peak,
                      "traffic": None if stored_p is None else stored_p.get("dram_bytes_per_launch"),
                      "traffic_source": None if stored_p is None else {k_: stored_p.get(k_) for k_ in ("source", "capture", "commit")},
                      "algorithmic_bytes_per_launch": pred_algo,
@@ -781,10 +781,13 @@ def predict_c5(args, frame, local, rank, world, stream, barrier, max_over_ranks,
         "scaling": "weak", "data": "code rows drawn on the device (torch.randint per column, missing code included); inputs (1.65 GB per GPU) larger than L2",
         "e2e": {"value": world * n_e2e * t5.n_trees / e2e_s, "unit": "rows*trees/s", "h2d_bytes_per_step": int(host_codes.nbytes), "d2h_bytes_per_step": int(n_e2e * C * 8),
                 "api": f"DeviceForest.predict on {n_e2e} host code rows of the shard: pinned double-buffered chunks, vote kernel, float64 probabilities back"},
-        "roofline": {"kernel": "rfmc::predict_kernel", "bound": "hbm", "achieved": algo5 / (np.mean(ms5) / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"kernel": dev5.vote_kernel, "bound": "hbm", "achieved": algo5 / (np.mean(ms5) / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": algo5 / (np.mean(ms5) / 1e3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": algo5,
-                     "secondary": {"bound": "dependent node loads (SURVEY 8d)", "shared_peak_gbs": smem_peak,
-                                   "frac_of_that_bound_for_path_7": value / world / (smem_peak * 1e9 / (7 * 8))}},
+                     "secondary": {"bound": "shared-memory wavefronts of the walk (SURVEY 8d): per tree level one 8-byte node record + one 2-byte row code, "
+                                            "both from shared memory in predict_small_kernel (bank conflicts of 32 lanes in 32 different records are what it pays)",
+                                   "shared_peak_gbs": smem_peak, "small_tree_stages": dev5.small_tree_stages,
+                                   "frac_of_that_bound_for_path_7": value / world / (smem_peak * 1e9 / (7 * 8)),
+                                   "frac_of_that_bound_for_path_7_incl_row_codes": value / world / (smem_peak * 1e9 / (7 * 10))}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         small = [t_.data for t_ in m5.data[:16]]

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RFMC_ABI_VERSION 2 /* 2: device draw plans, survivor exchange, jump polynomials */
+#define RFMC_ABI_VERSION 3 /* 2: device draw plans, survivor exchange, jump polynomials; 3: rfmc_forest_layout */
 
 /* column kinds and arithmetic tags (tag | bits<<8 | signed<<16) */
 #define RFMC_KIND_NUMERIC 0
@@ -201,6 +201,13 @@ int rfmc_forest_predict_frame(rfmc_forest* f, int64_t n_rows, int32_t n_features
  * set when the walk crossed an absent column.  Host buffers, synchronous. */
 int rfmc_forest_leaves(rfmc_forest* f, const void* codes, int code_width, int64_t n_rows, int64_t row_stride,
                        int32_t n_features, const uint8_t* absent, int32_t* leaves_out, void* stream);
+
+/* Which traversal kernel a forest votes with: *small_tree_stages > 0 when every tree fits a shared-memory stage
+ * (<= 1,024 nodes) and the forest is held in the compact layout of predict_small_kernel (whole trees staged in
+ * shared memory, branch-free fixed-depth walks; frames without absent columns, codes of at most 16 bits);
+ * 0: the generic blocked walk (predict_kernel).  Both replace tree.py:155-212 / forest.py:204-233 and are
+ * bit-equal; this is a measurement / diagnostics query. */
+int rfmc_forest_layout(rfmc_forest* f, int32_t* small_tree_stages);
 
 /* ---- split_train_val (model.py:198-210): the draw behind np.random.choice(a, size, replace=False)
  * on numpy's global legacy MT19937 stream, restated on the host: out[0..size) =

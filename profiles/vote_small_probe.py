@@ -26,8 +26,9 @@ def time_votes(model, label, soft, weighted):
     codes, absent = encode_frame(tables, frame.drop(columns=["target"]).head(rows))
     codes_t = torch.from_numpy(codes).cuda()
     out = {}
-    for small in ("0", "1"):
-        os.environ["RFMC_PRED_SMALL"] = small
+    for small in ("0", "r8", "1"):
+        os.environ["RFMC_PRED_SMALL"] = "0" if small == "0" else "1"
+        os.environ["RFMC_PRED_SMALL_REC4"] = "0" if small == "r8" else "1"
         probs_t = torch.empty((rows, 4), dtype=torch.float64, device="cuda")
         labels_t = torch.empty(rows, dtype=torch.int32, device="cuda")
         run = lambda: dev.predict_device(codes_t.data_ptr(), tables.width, rows, tables.stride, None, soft, weighted, probs_t.data_ptr(), labels_t.data_ptr(), stream)
@@ -42,10 +43,12 @@ def time_votes(model, label, soft, weighted):
         torch.cuda.synchronize()
         out[small] = (a.elapsed_time(b) / 3, probs_t.cpu().numpy().copy(), labels_t.cpu().numpy().copy())
     os.environ.pop("RFMC_PRED_SMALL", None)
-    same = np.array_equal(out["0"][1], out["1"][1]) and np.array_equal(out["0"][2], out["1"][2])
+    os.environ.pop("RFMC_PRED_SMALL_REC4", None)
+    same = all(np.array_equal(out["0"][1], out[k][1]) and np.array_equal(out["0"][2], out[k][2]) for k in ("r8", "1"))
     T = tables.n_trees
-    print(f"{label} soft={soft} weighted={weighted}: generic {out['0'][0]:.3f} ms = {rows * T / out['0'][0] / 1e-3:.3e} rows*trees/s | small-tree kernel "
-          f"{out['1'][0]:.3f} ms = {rows * T / out['1'][0] / 1e-3:.3e} | bit-equal {same} | trees {T} nodes {len(tables.pnodes)}", flush=True)
+    print(f"{label} soft={soft} weighted={weighted}: generic {out['0'][0]:.3f} ms = {rows * T / out['0'][0] / 1e-3:.3e} rows*trees/s | small-tree kernel, 8-byte records "
+          f"{out['r8'][0]:.3f} ms | 4-byte records {out['1'][0]:.3f} ms = {rows * T / out['1'][0] / 1e-3:.3e} "
+          f"| bit-equal {same} | trees {T} nodes {len(tables.pnodes)}", flush=True)
 
 
 m5 = RandomForestMC(n_trees=256, target_col="target", max_discard_trees=4)

@@ -347,10 +347,16 @@ static void build_tops(const rfmc_pnode* nodes, const int64_t* roots, int32_t n_
 // stages of at most `stage_nodes` records that the vote kernel copies to shared memory whole.  Returns false
 // when the forest is not eligible (a tree larger than a stage, codes or feature ids too wide).
 constexpr uint32_t SMALL_STAGE_NODES = 1024, SMALL_STAGE_TREES = 64;
+// rec4: the same forest as 4-byte records {feat (8 bits) | delta << 8 (7 bits) | numeric << 15 | lo << 16} when every
+// feature id is below 256 and every '>=' child lies at most 127 records behind its parent (BFS order: the width of a
+// level); left empty otherwise.  next = own index + delta, span = numeric ? 0x10000 : 0, a leaf = {numeric, lo 0,
+// delta 0}.  Half the bytes per record halve the shared-memory bank conflicts of 32 lanes in 32 different records.
 static bool build_compact(const rfmc_pnode* nodes, const int64_t* roots, int32_t n_trees, std::vector<uint32_t>& rec,
-                          std::vector<uint32_t>& pay, std::vector<uint32_t>& tree_at, std::vector<uint8_t>& depth,
-                          std::vector<uint32_t>& stage) {
+                          std::vector<uint32_t>& rec4, std::vector<uint32_t>& pay, std::vector<uint32_t>& tree_at,
+                          std::vector<uint8_t>& depth, std::vector<uint32_t>& stage) {
     rec.clear();
+    rec4.clear();
+    bool narrow = true;
     pay.clear();
     tree_at.assign(1, 0u);
     depth.clear();
@@ -369,6 +375,7 @@ static bool build_compact(const rfmc_pnode* nodes, const int64_t* roots, int32_t
             if (p.feat_flags & RFMC_PNODE_LEAF) {
                 rec.push_back(0u);
                 rec.push_back(0xFFFFu | ((uint32_t)q << 16));
+                rec4.push_back(0x8000u);
                 pay.push_back(p.thr);
                 deepest = d > deepest ? d : deepest;
                 continue;
@@ -380,6 +387,9 @@ static bool build_compact(const rfmc_pnode* nodes, const int64_t* roots, int32_t
             const uint32_t span = (p.feat_flags & RFMC_PNODE_CATEGORICAL) ? 0u : (0xFFFFu - lo);
             rec.push_back(f | (lo << 16));
             rec.push_back(span | (used << 16));
+            const uint32_t delta = used - (uint32_t)q;
+            if (f >= 256u || delta > 127u) narrow = false;
+            rec4.push_back((f & 0xFFu) | ((delta & 0x7Fu) << 8) | ((p.feat_flags & RFMC_PNODE_CATEGORICAL) ? 0u : 0x8000u) | (lo << 16));
             pay.push_back(0u);
             queue.emplace_back(p.child, d + 1);      // '>=' child at `used`
             queue.emplace_back(p.child + 1, d + 1);  // '<' child at `used + 1`
@@ -396,6 +406,7 @@ static bool build_compact(const rfmc_pnode* nodes, const int64_t* roots, int32_t
         tree_at.push_back(base + n);
     }
     stage.push_back((uint32_t)n_trees);
+    if (!narrow) rec4.clear();
     return true;
 }
 
@@ -989,10 +1000,11 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
         f->top_levels = levels;
         rc |= upload((uint32_t**)&f->d_tops, tops.data(), tops.size(), 0);
     }
-    std::vector<uint32_t> crec, cpay, ctree, cstage;
+    std::vector<uint32_t> crec, crec4, cpay, ctree, cstage;
     std::vector<uint8_t> cdepth;
-    if (!rc && build_compact(nodes, tree_root, n_trees, crec, cpay, ctree, cdepth, cstage)) {
+    if (!rc && build_compact(nodes, tree_root, n_trees, crec, crec4, cpay, ctree, cdepth, cstage)) {
         rc |= upload((uint32_t**)&f->d_crec, crec.data(), crec.size(), 0);
+        if (!crec4.empty()) rc |= upload(&f->d_crec4, crec4.data(), crec4.size(), 0);
         rc |= upload(&f->d_cpay, cpay.data(), cpay.size(), 0);
         rc |= upload(&f->d_ctree, ctree.data(), ctree.size(), 0);
         rc |= upload(&f->d_cdepth, cdepth.data(), cdepth.size(), 0);
@@ -1015,18 +1027,26 @@ int rfmc_forest_create(int device, const rfmc_pnode* nodes, int64_t n_nodes, con
    (build_compact above).  Pass NULL buffers to query the sizes; returns 1 when the forest is not eligible. */
 int rfmc_debug_compact_layout(const rfmc_pnode* nodes, const int64_t* tree_root, int32_t n_trees, int64_t* n_records,
                               int32_t* n_stages, uint32_t* rec_xy, uint32_t* pay, uint32_t* tree_at, uint8_t* depth,
-                              uint32_t* stage) {
-    std::vector<uint32_t> crec, cpay, ctree, cstage;
+                              uint32_t* stage, uint32_t* rec4, int32_t* has_rec4) {
+    std::vector<uint32_t> crec, crec4, cpay, ctree, cstage;
     std::vector<uint8_t> cdepth;
     if (!nodes || !tree_root || n_trees <= 0) return 1;
-    if (!build_compact(nodes, tree_root, n_trees, crec, cpay, ctree, cdepth, cstage)) return 1;
+    if (!build_compact(nodes, tree_root, n_trees, crec, crec4, cpay, ctree, cdepth, cstage)) return 1;
     if (n_records) *n_records = (int64_t)cpay.size();
     if (n_stages) *n_stages = (int32_t)cstage.size() - 1;
+    if (has_rec4) *has_rec4 = crec4.empty() ? 0 : 1;
+    if (rec4 && !crec4.empty()) std::memcpy(rec4, crec4.data(), crec4.size() * 4);
     if (rec_xy) std::memcpy(rec_xy, crec.data(), crec.size() * 4);
     if (pay) std::memcpy(pay, cpay.data(), cpay.size() * 4);
     if (tree_at) std::memcpy(tree_at, ctree.data(), ctree.size() * 4);
     if (depth) std::memcpy(depth, cdepth.data(), cdepth.size());
     if (stage) std::memcpy(stage, cstage.data(), cstage.size() * 4);
+    return 0;
+}
+
+int rfmc_forest_layout(rfmc_forest* f, int32_t* small_tree_stages) {
+    RFMC_REQUIRE(f != nullptr && small_tree_stages != nullptr, "NULL argument");
+    *small_tree_stages = f->d_crec != nullptr ? f->n_stages : 0;
     return 0;
 }
 
@@ -1045,6 +1065,7 @@ int rfmc_forest_destroy(rfmc_forest* f) {
     release(f->d_root_b);
     release(f->d_tops);
     release(f->d_crec);
+    release(f->d_crec4);
     release(f->d_cpay);
     release(f->d_ctree);
     release(f->d_cdepth);

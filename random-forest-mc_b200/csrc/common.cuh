@@ -167,6 +167,7 @@ struct rfmc_forest {
     int32_t top_levels = 0;
     // compact layout of a forest of small trees (predict_small_kernel): whole trees are staged in shared memory
     uint2* d_crec = nullptr;        // per node {feat | lo << 16, span | next << 16}, tree-relative child index
+    uint32_t* d_crec4 = nullptr;    // the same as 4-byte records (nullptr: feature ids or level widths too large)
     uint32_t* d_cpay = nullptr;     // per node: payload index of a leaf
     uint32_t* d_ctree = nullptr;    // [n_trees + 1] first record of every tree
     uint8_t* d_cdepth = nullptr;    // [n_trees] levels to walk (depth of the deepest leaf)

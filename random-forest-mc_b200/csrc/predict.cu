@@ -40,6 +40,7 @@ struct PredictArgs {
     int32_t top_levels;      // even, >= 2 (0: no tops)
     // compact layout of a forest of small trees (nullptr: not eligible), see build_compact in abi.cu
     const uint2* crec;
+    const uint32_t* crec4;  // 4-byte records (nullptr: not eligible)
     const uint32_t* cpay;
     const uint32_t* ctree;
     const uint8_t* cdepth;
@@ -466,9 +467,8 @@ __global__ void __launch_bounds__(TOP_THREADS) predict_top_kernel(PredictArgs a)
 constexpr int SMALL_THREADS = 256;
 constexpr int SMALL_STAGE = 1024;  // records per stage (SMALL_STAGE_NODES in abi.cu)
 #ifndef RFMC_SMALL_ILP
-#define RFMC_SMALL_ILP 4
+#define RFMC_SMALL_ILP 2  // trees in flight per thread: measured 1 / 2 / 4 / 8 -> 24.3 / 22.5 / 23.3 / 23.6 ms (C5, weighted soft)
 #endif
-constexpr int SMALL_ILP = RFMC_SMALL_ILP;
 
 __device__ __forceinline__ uint32_t lds_code(uint32_t addr, uint8_t) {
     uint32_t v;
@@ -487,11 +487,10 @@ __device__ __forceinline__ uint32_t lds_code(uint32_t addr, uint32_t) {  // inst
     return v;
 }
 
-template <typename CodeT, int CMAX, int MODE>
+template <typename CodeT, int CMAX, int MODE, bool REC4, int SMALL_ILP = RFMC_SMALL_ILP>
 __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr uint32_t REC_BYTES = 8u;
-    uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);
+    constexpr uint32_t REC_BYTES = REC4 ? 4u : 8u;
     uint32_t* s_pay = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SMALL_STAGE * REC_BYTES);
     CodeT* tile = reinterpret_cast<CodeT*>(smem_raw + (size_t)SMALL_STAGE * (REC_BYTES + sizeof(uint32_t)));
     const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -521,7 +520,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
         const uint32_t n0 = __ldg(&a.ctree[t0]), n1 = __ldg(&a.ctree[t1]);
         __syncthreads();  // the previous stage's walks (and, the first time, the row tile's stores) are done
         for (uint32_t i = tid; i < n1 - n0; i += SMALL_THREADS) {
-            s_rec[i] = __ldg(&a.crec[n0 + i]);
+            if (REC4)
+                reinterpret_cast<uint32_t*>(smem_raw)[i] = __ldg(&a.crec4[n0 + i]);
+            else
+                reinterpret_cast<uint2*>(smem_raw)[i] = __ldg(&a.crec[n0 + i]);
             const uint32_t payload = __ldg(&a.cpay[n0 + i]);
             // hard votes: the leaf's class is looked up once per staged record instead of once per walk
             s_pay[i] = (MODE == 0 || MODE == 1) ? (uint32_t)__ldg(&a.vote[payload]) : payload;
@@ -542,10 +544,17 @@ __global__ void __launch_bounds__(SMALL_THREADS) predict_small_kernel(PredictArg
             for (int l = 0; l < levels; ++l) {
 #pragma unroll
                 for (int k = 0; k < SMALL_ILP; ++k) {
-                    uint32_t x, y;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(at[k]));
-                    const uint32_t cv = lds_code(rowaddr + (x & 0xFFFFu) * (uint32_t)sizeof(CodeT), CodeT());
-                    at[k] = tb[k] + (y >> 16) * REC_BYTES + ((cv - (x >> 16)) > (y & 0xFFFFu) ? REC_BYTES : 0u);
+                    if (REC4) {
+                        uint32_t r;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(at[k]));
+                        const uint32_t cv = lds_code(rowaddr + (r & 0xFFu) * (uint32_t)sizeof(CodeT), CodeT());
+                        at[k] = at[k] + ((r >> 8) & 0x7Fu) * 4u + ((cv - (r >> 16)) > ((r & 0x8000u) << 1) ? 4u : 0u);
+                    } else {
+                        uint32_t x, y;
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(at[k]));
+                        const uint32_t cv = lds_code(rowaddr + (x & 0xFFFFu) * (uint32_t)sizeof(CodeT), CodeT());
+                        at[k] = tb[k] + (y >> 16) * REC_BYTES + ((cv - (x >> 16)) > (y & 0xFFFFu) ? REC_BYTES : 0u);
+                    }
                 }
             }
 #pragma unroll
@@ -611,11 +620,16 @@ template <typename CodeT, int CMAX, int MODE, bool HAS_ABSENT>
 static int launch_tile(const PredictArgs& a, cudaStream_t stream) {
     if (a.n_rows == 0) return 0;
     if (!HAS_ABSENT && a.crec != nullptr && sizeof(CodeT) <= 2) {
-        const size_t smem = (size_t)SMALL_STAGE * (sizeof(uint2) + sizeof(uint32_t)) + (size_t)SMALL_THREADS * a.stride * sizeof(CodeT);
+        const bool rec4 = a.crec4 != nullptr;
+        const size_t smem = (size_t)SMALL_STAGE * ((rec4 ? 4 : 8) + sizeof(uint32_t)) + (size_t)SMALL_THREADS * a.stride * sizeof(CodeT);
         if (smem <= 100 * 1024) {  // two or more CTAs per SM
-            auto k = predict_small_kernel<CodeT, CMAX, MODE>;
-            if (smem > 48 * 1024) RFMC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<(unsigned)((a.n_rows + SMALL_THREADS - 1) / SMALL_THREADS), SMALL_THREADS, smem, stream>>>(a);
+            const unsigned grid = (unsigned)((a.n_rows + SMALL_THREADS - 1) / SMALL_THREADS);
+            auto run = [&](auto k) {
+                if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
+                k<<<grid, SMALL_THREADS, smem, stream>>>(a);
+            };
+            if (rec4) run(predict_small_kernel<CodeT, CMAX, MODE, true>);
+            else run(predict_small_kernel<CodeT, CMAX, MODE, false>);
             RFMC_CUDA(cudaGetLastError());
             return 0;
         }
@@ -700,6 +714,7 @@ int launch_leaves(rfmc_forest* f, const void* d_codes, int code_width, int64_t n
     a.tops = nullptr;
     a.top_levels = 0;
     a.crec = nullptr;
+    a.crec4 = nullptr;
     a.cpay = nullptr;
     a.ctree = nullptr;
     a.cdepth = nullptr;
@@ -746,6 +761,10 @@ int launch_predict(rfmc_forest* f, const void* d_codes, int code_width, int64_t 
     const char* small_off = getenv("RFMC_PRED_SMALL");  // experiment knob: 0 = always the generic kernel
     const bool small = f->d_crec != nullptr && code_width <= 2 && !(small_off && atoi(small_off) == 0);
     a.crec = small ? f->d_crec : nullptr;
+    a.crec4 = f->d_crec4;
+    if (const char* e = getenv("RFMC_PRED_SMALL_REC4")) {  // experiment knob: 0 = 8-byte records even when eligible
+        if (atoi(e) == 0) a.crec4 = nullptr;
+    }
     a.cpay = f->d_cpay;
     a.ctree = f->d_ctree;
     a.cdepth = f->d_cdepth;

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "rfmc_legacy_permutation_prefix": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, _p]),
     "rfmc_pyrandom_sample_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p]),
     "rfmc_forest_set_codebook": (C.c_int, [_p, C.c_int32, _p, _p]),
+    "rfmc_forest_layout": (C.c_int, [_p, _p]),
     "rfmc_forest_predict_frame": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, C.c_int, C.c_int32, _p, _p, _p, _p,
                                             C.c_int, C.c_int, _p, _p]),
     "rfmc_legacy_draw_plan": (C.c_int, [_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _p, _p, C.c_int64, C.c_int64,
@@ -724,6 +725,17 @@ class DeviceForest:
 
     _DT = {"float64": 0, "float32": 1, "int64": 2, "int32": 3, "int16": 4, "int8": 5, "uint8": 6, "uint16": 7,
            "uint32": 8, "uint64": 9}
+
+    @property
+    def small_tree_stages(self) -> int:
+        """> 0: the forest votes with the small-tree kernel (whole trees staged in shared memory)."""
+        n = C.c_int32(0)
+        _check(load_library().rfmc_forest_layout(self._h, C.byref(n)))
+        return int(n.value)
+
+    @property
+    def vote_kernel(self) -> str:
+        return "rfmc::predict_small_kernel" if self.small_tree_stages > 0 and self.tables.width <= 2 else "rfmc::predict_kernel"
 
     def predict_frame(self, frame, soft: bool, weighted: bool, want_probs: bool = True, want_labels: bool = True):
         """Vote a raw pandas frame: numeric columns go to the GPU as they are and are encoded there

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(engine.EXPORTED_SYMBOLS) <= set(names)
-    assert lib.rfmc_abi_version() == 2
+    assert lib.rfmc_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -17,21 +17,38 @@ def compact_layout(tables):
     lib = engine.load_library()
     fn = lib.rfmc_debug_compact_layout
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p] * 2 + [C.c_int32] + [C.c_void_p] * 7
+    fn.argtypes = [C.c_void_p] * 2 + [C.c_int32] + [C.c_void_p] * 9
     nodes = np.ascontiguousarray(tables.pnodes)
     roots = np.ascontiguousarray(tables.roots, dtype=np.int64)
-    n_rec, n_st = C.c_int64(0), C.c_int32(0)
+    n_rec, n_st, has4 = C.c_int64(0), C.c_int32(0), C.c_int32(0)
     T = len(roots)
-    if fn(nodes.ctypes.data, roots.ctypes.data, T, C.addressof(n_rec), C.addressof(n_st), None, None, None, None, None):
+    if fn(nodes.ctypes.data, roots.ctypes.data, T, C.addressof(n_rec), C.addressof(n_st), None, None, None, None, None, None, C.addressof(has4)):
         return None
     rec = np.zeros((n_rec.value, 2), dtype=np.uint32)
+    rec4 = np.zeros(n_rec.value, dtype=np.uint32)
     pay = np.zeros(n_rec.value, dtype=np.uint32)
     tree_at = np.zeros(T + 1, dtype=np.uint32)
     depth = np.zeros(T, dtype=np.uint8)
     stage = np.zeros(n_st.value + 1, dtype=np.uint32)
     assert fn(nodes.ctypes.data, roots.ctypes.data, T, None, None, rec.ctypes.data, pay.ctypes.data, tree_at.ctypes.data,
-              depth.ctypes.data, stage.ctypes.data) == 0
+              depth.ctypes.data, stage.ctypes.data, rec4.ctypes.data, None) == 0
+    LAST_REC4[0] = rec4 if has4.value else None
     return rec, pay, tree_at, depth, stage
+
+
+LAST_REC4 = [None]  # the 4-byte records of the last layout asked for (None: the forest is not eligible for them)
+
+
+def walk_rec4(rec4, layout, t, row):
+    """The kernel's walk over 4-byte records {feat | delta << 8 | numeric << 15 | lo << 16}: next = own index + delta."""
+    _, pay, tree_at, depth, _ = layout
+    base, idx = int(tree_at[t]), 0
+    for _ in range(int(depth[t])):
+        r = int(rec4[base + idx])
+        d = (int(row[r & 0xFF]) - (r >> 16)) & 0xFFFFFFFF
+        idx = idx + ((r >> 8) & 0x7F) + (1 if d > ((r & 0x8000) << 1) else 0)
+    assert int(rec4[base + idx]) == 0x8000, "the walk must end on a leaf record"
+    return int(pay[base + idx])
 
 
 def walk_pnodes(tables, t, row):
@@ -73,10 +90,15 @@ def test_compact_walk_equals_node_walk(name):
     for j, cats in enumerate(tables.categories):
         if cats:
             hi[j] = 1 + len(cats)
+    rec4 = LAST_REC4[0]  # None for a forest with a level wider than 127 nodes (mixed_big)
+    assert rec4 is not None or name not in ("titanic_c1", "mixed_default", "ties_default")
     for _ in range(300):
         row = np.array([rng.integers(0, h + 1) for h in hi], dtype=np.int64)  # code 0 = missing / unseen
         for t in range(T):
-            assert walk_compact(layout, t, row) == walk_pnodes(tables, t, row)
+            want = walk_pnodes(tables, t, row)
+            assert walk_compact(layout, t, row) == want
+            if rec4 is not None:
+                assert walk_rec4(rec4, layout, t, row) == want
 
 
 def test_big_trees_are_not_eligible_and_many_small_trees_split_into_stages():
@@ -113,3 +135,33 @@ def test_big_trees_are_not_eligible_and_many_small_trees_split_into_stages():
     for t in range(200):
         assert walk_compact((rec, pay, tree_at, depth, stage), t, np.array([1])) == 2 * t
         assert walk_compact((rec, pay, tree_at, depth, stage), t, np.array([0])) == 2 * t + 1
+
+
+def test_wide_forests_keep_eight_byte_records():
+    """A feature id of 256 or more, or a '>=' child more than 127 records behind its parent, rules out 4-byte records."""
+    from random_forest_mc_b200.flat import PNODE_DTYPE
+
+    one = np.zeros(3, dtype=PNODE_DTYPE)
+    one[0]["feat_flags"], one[0]["thr"], one[0]["child"] = 300, 1, 1
+    one[1]["feat_flags"], one[2]["feat_flags"] = LEAF, LEAF
+
+    class W_:
+        pnodes, roots = one, np.array([0], dtype=np.int64)
+
+    assert compact_layout(W_) is not None and LAST_REC4[0] is None
+    # a complete tree of depth 8: level 7 has 128 nodes, so the children of its first node are 128+ records away
+    n = 2 ** 9 - 1
+    full = np.zeros(n, dtype=PNODE_DTYPE)
+    for i in range(n):
+        if 2 * i + 2 < n:
+            full[i]["feat_flags"], full[i]["thr"], full[i]["child"] = 0, 1, 2 * i + 1
+        else:
+            full[i]["feat_flags"], full[i]["thr"] = LEAF, i
+
+    class F_:
+        pnodes, roots = full, np.array([0], dtype=np.int64)
+
+    layout = compact_layout(F_)
+    assert layout is not None and LAST_REC4[0] is None
+    for code in (0, 1):
+        assert walk_compact(layout, 0, np.array([code])) == walk_pnodes(F_, 0, np.array([code]))

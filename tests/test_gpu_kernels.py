@@ -148,3 +148,36 @@ def test_voting_many_rows_matches_cpu_model():
             assert np.array_equal(probs, p2)
             assert np.array_equal(labels, l2)
     forest.close()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_small_tree_and_generic_vote_kernels_agree(name, monkeypatch):
+    """Golden forests are small: they vote with predict_small_kernel (whole trees in shared memory, fixed-depth
+    branch-free walks).  The generic blocked walk (RFMC_PRED_SMALL=0) must give the same bits in every mode,
+    with missing cells and a ragged last tile; both equal the CPU statement."""
+    eng = _engine()
+    g = load_golden(name)
+    t = forest_tables_from_dicts(g["forest"], g["survived_scores"], g["class_vals"], g["feature_cols"])
+    forest = eng.DeviceForest(t)
+    assert forest.small_tree_stages > 0 and forest.vote_kernel.endswith("predict_small_kernel")
+    frame = g["frames"]["nan"] if "nan" in g["frames"] else g["frames"]["clean"]
+    reps = max(1, 600 // max(1, len(frame)))
+    codes, absent = encode_frame(t, frame)
+    codes = np.ascontiguousarray(np.tile(codes, (reps, 1)))[: max(len(frame), 517)]
+    assert absent is None or not np.any(absent)
+    for soft in (False, True):
+        for weighted in (False, True):
+            monkeypatch.delenv("RFMC_PRED_SMALL", raising=False)
+            monkeypatch.delenv("RFMC_PRED_SMALL_REC4", raising=False)
+            p_small, l_small = forest.predict(codes, absent, soft, weighted)  # 4-byte records when the forest allows them
+            monkeypatch.setenv("RFMC_PRED_SMALL_REC4", "0")
+            p_rec8, l_rec8 = forest.predict(codes, absent, soft, weighted)  # 8-byte records
+            monkeypatch.setenv("RFMC_PRED_SMALL", "0")
+            p_gen, l_gen = forest.predict(codes, absent, soft, weighted)
+            p_cpu, l_cpu = cm.vote_tables(t, codes, absent, soft, weighted)
+            assert np.array_equal(p_small, p_gen) and np.array_equal(l_small, l_gen), (soft, weighted)
+            assert np.array_equal(p_rec8, p_gen) and np.array_equal(l_rec8, l_gen), (soft, weighted)
+            assert np.array_equal(p_small, p_cpu) and np.array_equal(l_small, l_cpu), (soft, weighted)
+    monkeypatch.delenv("RFMC_PRED_SMALL", raising=False)
+    monkeypatch.delenv("RFMC_PRED_SMALL_REC4", raising=False)
+    forest.close()
