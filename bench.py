@@ -230,7 +230,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def stored_ncu(kernel, workload):
+def stored_ncu(kernel, workload, any_workload=False):
     """Figures of the committed ncu capture of `kernel` (profiles/ncu_traffic.json) -- only for the workload it
     was taken on.  They are STORED captures (ncu replays kernels; nothing is profiled inside a bench run):
     the dict names the capture and the commit it was taken at."""
@@ -238,12 +238,12 @@ def stored_ncu(kernel, workload):
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        if d.get("workload") == workload:
+        if any_workload or d.get("workload") == workload:
             k = d.get("kernels", {}).get(kernel)
             if k is None and kernel in d.get("bytes_per_launch", {}):
                 k = {"dram_bytes_per_launch": d["bytes_per_launch"][kernel]}
             if k is not None:
-                return dict(k, source="stored ncu capture", capture=d.get("capture"), commit=d.get("commit"))
+                return dict(k, source="stored ncu capture", capture=k.get("capture", d.get("capture")), commit=k.get("commit", d.get("commit")))
     return None
 
 
@@ -292,7 +292,7 @@ def run_b200(args):
     logging.disable(logging.WARNING)
     hbm_peak, peak_src, sm_mhz = peaks()
     smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9  # GB/s: 148 SMs x 128 B/clk
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)  # taskset / cpuset aware
     K = args.max_discard_trees
 
     def barrier():
@@ -775,6 +775,7 @@ def predict_c5(args, frame, local, rank, world, stream, barrier, max_over_ranks,
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     value = world * R5 * t5.n_trees * args.steps / s5
+    stored_small = stored_ncu(dev5.vote_kernel.split("::")[-1], None, any_workload=True)  # taken on 1,048,576 rows of this forest, not on R5
     block = {
         "workload": f"C5 shard: {R5} rows x {t5.n_trees} trees per GPU (16 fits x 256 slots at the default 10+10 rows per class, appended = mergeForest by add), weighted soft voting, float64 probabilities out",
         "metric": "predict_rows_trees_per_s", "value": value, "unit": "rows*trees/s", "ms_per_step": float(np.mean(ms5)), "forest_nodes": int(len(t5.pnodes)),
@@ -782,7 +783,8 @@ def predict_c5(args, frame, local, rank, world, stream, barrier, max_over_ranks,
         "e2e": {"value": world * n_e2e * t5.n_trees / e2e_s, "unit": "rows*trees/s", "h2d_bytes_per_step": int(host_codes.nbytes), "d2h_bytes_per_step": int(n_e2e * C * 8),
                 "api": f"DeviceForest.predict on {n_e2e} host code rows of the shard: pinned double-buffered chunks, vote kernel, float64 probabilities back"},
         "roofline": {"kernel": dev5.vote_kernel, "bound": "hbm", "achieved": algo5 / (np.mean(ms5) / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": algo5 / (np.mean(ms5) / 1e3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": algo5,
+                     "frac": algo5 / (np.mean(ms5) / 1e3) / 1e9 / hbm_peak, "traffic": None, "traffic_stored_capture": stored_small,
+                     "algorithmic_bytes_per_launch": algo5,
                      "secondary": {"bound": "shared-memory wavefronts of the walk (SURVEY 8d): per tree level one 8-byte node record + one 2-byte row code, "
                                             "both from shared memory in predict_small_kernel (bank conflicts of 32 lanes in 32 different records are what it pays)",
                                    "shared_peak_gbs": smem_peak, "small_tree_stages": dev5.small_tree_stages,

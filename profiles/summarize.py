@@ -28,7 +28,11 @@ KEYS = [
 
 
 def raw(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    pre = rep[: -len(".ncu-rep")] + ".raw.csv"  # extracted on the GPU box (profiles/prof_r2b.sh); else read the report here
+    if os.path.exists(pre):
+        txt = open(pre).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     return {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
@@ -42,7 +46,9 @@ def to_bytes(val, unit):
     return num(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 
 
-lines = [f"# ncu summary ({tag})", "", "Commands: `profiles/prof_r2.sh` (the default `python bench.py` command, `--clock-control none`).", ""]
+script = sys.argv[3] if len(sys.argv) > 3 else "profiles/prof_r2.sh"
+lines = [f"# ncu summary ({tag})", "", f"Commands: `{script}` (the default `python bench.py` command, `--clock-control none`; `predict_small_kernel`: "
+         "the C5 forest on 1,048,576 rows of the shard).", ""]
 src = os.path.join(OUT, "launchesF.csv")
 if os.path.exists(src):
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
@@ -62,9 +68,10 @@ if os.path.exists(src):
         lines.append(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {sum(v)/tot*100:.1f}% |")
     lines.append("")
 traffic = {}
-for rep, name in (("prof_growF", "grow_kernel"), ("prof_gatherF", "slot_gather_kernel"), ("prof_predictF", "predict_kernel")):
+for rep, name in (("prof_growF", "grow_kernel"), ("prof_gatherF", "slot_gather_kernel"), ("prof_predictF", "predict_kernel"),
+                  ("prof_smallF", "predict_small_kernel")):
     path = os.path.join(OUT, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    if not os.path.exists(path) and not os.path.exists(path[: -len(".ncu-rep")] + ".raw.csv"):
         continue
     d = raw(path)
     lines += [f"## `rfmc::{name}` (one launch, `--set full`)", "", "| metric | value |", "|---|---|"]
@@ -73,6 +80,7 @@ for rep, name in (("prof_growF", "grow_kernel"), ("prof_gatherF", "slot_gather_k
             lines.append(f"| {k} | {d[k][0]} {d[k][1]} |")
     lines.append("")
     traffic[name] = {
+        "capture": f"profiles/{tag}_ncu_summary.md (ncu --set full --clock-control none, one launch)", "commit": commit,
         "dram_bytes_per_launch": to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]),
         # one shared-memory wavefront moves up to 128 bytes (the denominator of SURVEY 8d's secondary bound)
         "shared_wavefront_bytes_per_launch": num(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"][0]) * 128.0,
@@ -85,7 +93,14 @@ workload = None
 plain = os.path.join(OUT, "plainF.json")
 if os.path.exists(plain):
     workload = json.load(open(plain))["config"]["workload"]
-with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
-    json.dump({"workload": workload, "capture": f"profiles/{tag}_ncu_summary.md (ncu --set full --clock-control none, one launch per kernel, default bench command)",
-               "commit": commit, "kernels": traffic}, f, indent=1)
+tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+old_doc = json.load(open(tj)) if os.path.exists(tj) else {}
+kernels = {}
+for name, k in old_doc.get("kernels", {}).items():  # kernels not captured this time keep their own capture label
+    kernels[name] = dict(k)
+    kernels[name].setdefault("capture", old_doc.get("capture"))
+    kernels[name].setdefault("commit", old_doc.get("commit"))
+kernels.update(traffic)
+with open(tj, "w") as f:
+    json.dump({"workload": workload or old_doc.get("workload"), "kernels": kernels}, f, indent=1)
 print("\n".join(lines))

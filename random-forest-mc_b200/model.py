@@ -59,6 +59,14 @@ class DictValuesAllFeaturesMissing(Exception):
         super().__init__(message)
 
 
+def _usable_cores() -> int:
+    """Cores this process may run on (taskset / cpuset aware), not the cores of the box."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 class _SlotJudge:
     """The keep/discard state machine of one ``survivedTree`` call (model.py:319-342)."""
 
@@ -174,7 +182,7 @@ class RandomForestMC(BaseRandomForestMC):
         # floor; two helpers keep up with it.  A producer thread for the blocks is opt-in only: since
         # the blocks are generated with AVX-512 the cache-to-cache hand-off costs more than it saves.
         ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-        self.rng_threads = max(0, min(2, (os.cpu_count() or 1) // ranks_here - 1))
+        self.rng_threads = max(0, min(2, _usable_cores() // ranks_here - 1))
         self.rng_producer = os.environ.get("RFMC_RNG_PRODUCER", "0") == "1"
         self.gil_switch_interval = float(os.environ.get("RFMC_GIL_SWITCH_INTERVAL", "1e-4"))  # seconds, host-stream fits only
         # numpy's stream can be walked on the GPU (csrc/rng_walk.cu: same rows, counts and stream states, row
@@ -683,7 +691,7 @@ class RandomForestMC(BaseRandomForestMC):
                 # one resolve helper per stream while there are cores for it (the box's cores are shared by the
                 # ranks of a multi-GPU run); no producer thread
                 ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-                self._tls.rng_flags = 1 if 2 * k * ranks_here <= (os.cpu_count() or 1) else 0
+                self._tls.rng_flags = 1 if 2 * k * ranks_here <= _usable_cores() else 0
                 lo, hi = shard_bounds(n_slots, r, k)
                 parts[r] = self._fit_slots(hi - lo, stream) if hi > lo else []
                 stats[r] = getattr(self._tls, "last_stats", None)
@@ -810,7 +818,7 @@ class RandomForestMC(BaseRandomForestMC):
         if dist.is_distributed():
             Forest = dist.fit_sharded(self, host_streams=max_workers or 1)
         else:
-            k = max_workers or min(16, os.cpu_count() or 1)  # the reference's pool defaults to one worker per core
+            k = max_workers or min(16, _usable_cores())  # the reference's pool defaults to one worker per core
             k = max(1, min(int(k), self.n_trees))
             seeds = getattr(self, "worker_seeds", None)
             if seeds is None:  # derived from the global stream: reproducible under np.random.seed(s)
