@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RFMC_ABI_VERSION 3 /* 2: device draw plans, survivor exchange, jump polynomials; 3: rfmc_forest_layout */
+#define RFMC_ABI_VERSION 3 /* 2: device draw plans, survivor exchange, jump polynomials; 3: rfmc_forest_layout, rfmc_cache_trim */
 
 /* column kinds and arithmetic tags (tag | bits<<8 | signed<<16) */
 #define RFMC_KIND_NUMERIC 0
@@ -80,6 +80,11 @@ int rfmc_stream_create(int device, void** out);
 int rfmc_stream_destroy(int device, void* stream);
 const char* rfmc_last_error(void);
 int rfmc_device_count(int* count);
+/* The library keeps freed device blocks (up to 48 GB per device) and pinned staging buffers (up to 8 GB) in
+ * process-wide pools so that no cudaMalloc / cudaFree / cudaHostAlloc -- each a device-wide synchronisation --
+ * happens between the batches of a fit.  rfmc_cache_trim gives everything that is cached and not in use back to
+ * the driver (for a process that shares the GPU with another allocator, e.g. torch); *freed_bytes may be NULL. */
+int rfmc_cache_trim(int device, int64_t* freed_bytes);
 
 /* ---- process_dataset (model.py:162-195): upload the encoded training matrix once ------------
  * codes      [n_rows][row_stride] unsigned codes of `code_width` bytes (1, 2 or 4), row-major,

@@ -1044,6 +1044,28 @@ int rfmc_debug_compact_layout(const rfmc_pnode* nodes, const int64_t* tree_root,
     return 0;
 }
 
+int rfmc_cache_trim(int device, int64_t* freed_bytes) {
+    RFMC_CUDA(cudaSetDevice(device));
+    size_t freed = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        DevCache& dc = g_mem[device];
+        freed += dc.cached;
+        flush_cache_locked(dc);
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (auto& kv : g_pin_free) {
+            freed += kv.first;
+            cudaFreeHost(kv.second);
+        }
+        g_pin_free.clear();
+        g_pin_cached = 0;
+    }
+    if (freed_bytes) *freed_bytes = (int64_t)freed;
+    return 0;
+}
+
 int rfmc_forest_layout(rfmc_forest* f, int32_t* small_tree_stages) {
     RFMC_REQUIRE(f != nullptr && small_tree_stages != nullptr, "NULL argument");
     *small_tree_stages = f->d_crec != nullptr ? f->n_stages : 0;

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rfmc_abi_version": (C.c_int, []),
     "rfmc_last_error": (C.c_char_p, []),
     "rfmc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "rfmc_cache_trim": (C.c_int, [C.c_int, C.POINTER(C.c_int64)]),
     "rfmc_stream_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
     "rfmc_stream_destroy": (C.c_int, [C.c_int, _p]),
     "rfmc_dataset_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int32, C.c_int64, _p, C.c_int32, _p, _p, _p, _p, _p, C.POINTER(_p)]),
@@ -123,6 +124,13 @@ def load_library():
 def _check(rc: int):
     if rc != 0:
         raise EngineError(load_library().rfmc_last_error().decode("utf-8", "replace"))
+
+
+def cache_trim(device: int = 0) -> int:
+    """Give the library's cached device blocks and pinned staging buffers back to the driver; bytes freed."""
+    n = C.c_int64(0)
+    _check(load_library().rfmc_cache_trim(int(device), C.byref(n)))
+    return int(n.value)
 
 
 def device_count() -> int:

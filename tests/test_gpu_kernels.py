@@ -181,3 +181,31 @@ def test_small_tree_and_generic_vote_kernels_agree(name, monkeypatch):
     monkeypatch.delenv("RFMC_PRED_SMALL", raising=False)
     monkeypatch.delenv("RFMC_PRED_SMALL_REC4", raising=False)
     forest.close()
+
+
+def test_cache_trim_gives_the_pools_back_and_the_engine_keeps_working():
+    """rfmc_cache_trim frees the cached device blocks / pinned buffers of closed batches; the next batch
+    allocates afresh and gives the same trees."""
+    eng = _engine()
+    g = load_golden("mixed_default")
+    enc = encode_golden(g)
+    ds = eng.DeviceDataset(enc)
+    ref = g["trace"][0]
+    fidx = {name: j for j, name in enumerate(g["feature_cols"])}
+    feats = [[fidx[f] for f in ref["F"]]]
+
+    def grow():
+        b = eng.GrowBatch(ds, np.asarray(ref["idx_T"])[None, :], np.asarray(ref["idx_V"])[None, :], [0], feats, 1000, g["kwargs"].get("min_samples_split", 1))
+        b.run()
+        correct, _ = b.results()
+        tree = b.fetch([0])[0]
+        b.close()
+        return int(correct[0]), tree
+
+    c1, t1 = grow()
+    freed = eng.cache_trim(0)
+    assert freed > 0
+    assert eng.cache_trim(0) == 0
+    c2, t2 = grow()
+    assert c1 == c2 and np.array_equal(t1.nodes, t2.nodes) and np.array_equal(t1.counts, t2.counts)
+    ds.close()
