@@ -522,18 +522,16 @@ def run_b200(args):
 
     def fit_config(frame, regime, n_slots_local, label, steps, warmup, e2e_steps, streams, cpu_rounds, strong_total=None):
         model = make_model(args, regime, n_slots_local, local)
-        # With several ranks on one box a rank has only its share of the host cores for the walk of numpy's stream.
-        # Below ~6 cores per rank the DEVICE walk of the same stream (csrc/rng_walk.cu: same rows, counts and stream
-        # states) is the faster one -- measured with 2 ranks held to 4 cores each: 61.9 against 85.8 ms per step,
-        # profiles/r2b_experiments.md -- so the end-to-end fit uses it there (C2 frames; RFMC_DEVICE_DRAWS=0/1 overrides).
-        env_dd = os.environ.get("RFMC_DEVICE_DRAWS")
-        use_dev = (env_dd == "1") if env_dd in ("0", "1") else (world > 1 and cores // world < 6 and len(frame) <= 2_000_000)
-        model.device_draws = bool(use_dev)
-        if use_dev and not args.host_streams:
-            streams = min(streams, 4)  # four draw plans in flight per GPU: more only queue behind each other's kernels
         t0 = time.perf_counter()
         model.process_dataset(frame.copy())
         t_process = time.perf_counter() - t0
+        # With several ranks on one box a rank has only its share of the host cores for the walk of numpy's stream; below
+        # six cores per rank the model draws with the DEVICE walk of the same stream (model.device_draws_on(): same rows,
+        # counts and stream states; 2 ranks x 4 cores: 61.9 against 85.8 ms per step, profiles/r2b_experiments.md).
+        # RFMC_DEVICE_DRAWS=0/1 overrides the model's choice.
+        use_dev = model.device_draws_on()
+        if use_dev and not args.host_streams:
+            streams = min(streams, 4)  # four draw plans in flight per GPU: more only queue behind each other's kernels
         dev = device_fit(model, n_slots_local, steps, warmup, label)
         total_slots = strong_total if strong_total is not None else n_slots_local * world
         par = api_fit(model, total_slots, streams, e2e_steps, 9000)
@@ -553,13 +551,13 @@ def run_b200(args):
             "roofline": dev["roofline"],
             "roofline_slot_gather": dev["roofline_slot_gather"],
             "e2e": {
-                "value": par["value"], "unit": "candidate-trees/s", "h2d_bytes_per_step": (dev["h2d_plan_bytes"] - (dev["h2d_idx_bytes"] if model.device_draws else 0)) * max(1, total_slots // max(1, n_slots_local * world)),
+                "value": par["value"], "unit": "candidate-trees/s", "h2d_bytes_per_step": (dev["h2d_plan_bytes"] - (dev["h2d_idx_bytes"] if use_dev else 0)) * max(1, total_slots // max(1, n_slots_local * world)),
                 "d2h_bytes_per_step": d2h,
                 "api": f"RandomForestMC.fitParallel(max_workers={streams}): " + (f"slots sharded over {world} ranks, " if world > 1 else "") +
                 f"{streams} independent seeded RNG stream(s) per rank (the semantics of the reference's process pool and of the CPU arm): " +
-                ("numpy's stream walked on the DEVICE (rfmc_draw_plan_device, row ids stay in HBM) + " if model.device_draws else "host RNG draws + H2D + ") +
+                ("numpy's stream walked on the DEVICE (rfmc_draw_plan_device, row ids stay in HBM) + " if use_dev else "host RNG draws + H2D + ") +
                 "grow/score kernels + D2H scores + survivor tables" + ("; survivors all-gathered over NCCL (rfmc_allgather_survivors)" if world > 1 else ""),
-                "draws": "device" if model.device_draws else "host",
+                "draws": "device" if use_dev else "host",
                 "host_streams_per_rank": streams, "ms_per_step": par["ms_per_step"], "ms_each_rank0": par["ms_each_rank0"], "fit_stats": par["fit_stats"],
                 "host_rng_share": par["host_rng_share"], "dict_materialise_s": par["dict_materialise_s"],
                 "dict_materialise_note": "trees stay SoA after a fit; tree.data / model2dict() build the reference's nested dicts on first access, outside the timed fit",

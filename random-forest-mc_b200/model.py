@@ -189,7 +189,12 @@ class RandomForestMC(BaseRandomForestMC):
         # ids never leave HBM).  Measured on a B200 next to 32 AVX-512 host cores the host walk
         # (csrc/host_rng.cpp) is still the faster one, so the device walk is opt-in;
         # replays, single-slot calls and draws wider than the device resolve always use the host walk.
-        self.device_draws = os.environ.get("RFMC_DEVICE_DRAWS", "0") == "1"
+        # True / False, or None = decide per fit (device_draws_on): on when this process is one of several ranks on
+        # the box and its share of the host cores is below six -- there the device walk is the faster one (2 ranks x 4
+        # cores: 61.9 against 85.8 ms per 1,024 C2b candidates, profiles/r2b_experiments.md) -- off otherwise.
+        env_dd = os.environ.get("RFMC_DEVICE_DRAWS")
+        self.device_draws = (env_dd == "1") if env_dd in ("0", "1") else None
+        self.device_draw_auto_max_rows = 2_000_000  # frames the automatic choice has been measured on
         self.device_draw_min_slots = 2
         # software pipelining of the fit loop (_fit_slots): plans of more than this many slots are cut into
         # sub-plans so that the kernels and copies of one hide behind the draws of the next; 0 = one plan at a time
@@ -332,6 +337,16 @@ class RandomForestMC(BaseRandomForestMC):
         pos = {name: j for j, name in enumerate(self.feature_cols)}
         return [pos[f] for f in feature_list]
 
+    def device_draws_on(self) -> bool:
+        """Whether plans are drawn by the device walk of numpy's stream (``device_draws``; None = automatic)."""
+        if self.device_draws is not None:
+            return bool(self.device_draws)
+        ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        if ranks_here < 2 or self.encoded is None:
+            return False
+        rows = sum(len(r) for r in self.encoded.class_rows)
+        return _usable_cores() // ranks_here < 6 and rows <= self.device_draw_auto_max_rows
+
     def _draw_plan(self, n_plan: int, spec: int, stream=None):
         """All draws of ``n_plan`` slots with ``spec`` candidates each, in the reference's order.
         numpy's stream (rows per class, then one feature count per candidate) is walked in ONE call:
@@ -343,7 +358,7 @@ class RandomForestMC(BaseRandomForestMC):
             raise ValueError("low >= high")  # what np.random.randint raises in the reference
         st = self._np_rng().get_state()
         dev = None
-        if (self.device_draws and n_plan >= self.device_draw_min_slots and int(self._N) <= engine.DRAW_MAX_PER_CLASS
+        if (self.device_draws_on() and n_plan >= self.device_draw_min_slots and int(self._N) <= engine.DRAW_MAX_PER_CLASS
                 and int(self.max_feature) - int(self.min_feature) < 2**31 - 2):
             dev = engine.DrawPlan(self._dev_dataset, self.encoded.class_rows, st[1], int(st[2]), n_plan, int(self._N),
                                   int(self.batch_train_pclass), spec, int(self.min_feature), int(self.max_feature) + 1, stream)

@@ -187,3 +187,27 @@ def test_device_forest_follows_the_trees_not_their_ids():
     # replacing a tree's dict in place of the same object
     m.data[0].data = g["forest"][0]
     assert m.testForestProbs(frame) == orc.forest_probs([g["forest"][0]], [1.0], g["class_vals"], frame, False, False)
+
+
+def test_device_draws_are_chosen_automatically_only_for_ranks_short_of_cores(monkeypatch):
+    """device_draws = None: the device walk of numpy's stream is used when this process is one of several ranks on the
+    box and its share of the host cores is below six (model.device_draws_on); explicit settings always win."""
+    from random_forest_mc_b200 import model as model_mod
+
+    g, m = model_checks.fitted_model("mixed_default")
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    m.device_draws = None
+    assert m.device_draws_on() is False  # one process on the box
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    monkeypatch.setattr(model_mod, "_usable_cores", lambda: 32)
+    assert m.device_draws_on() is True  # 4 cores per rank
+    monkeypatch.setattr(model_mod, "_usable_cores", lambda: 64)
+    assert m.device_draws_on() is False  # 8 cores per rank
+    monkeypatch.setattr(model_mod, "_usable_cores", lambda: 32)
+    m.device_draw_auto_max_rows = 10
+    assert m.device_draws_on() is False  # a frame larger than what the choice was measured on
+    m.device_draws = True
+    assert m.device_draws_on() is True
+    m.device_draws = False
+    m.device_draw_auto_max_rows = 10**9
+    assert m.device_draws_on() is False
