@@ -360,15 +360,25 @@ class RandomForestMC(BaseRandomForestMC):
         dev = None
         if (self.device_draws_on() and n_plan >= self.device_draw_min_slots and int(self._N) <= engine.DRAW_MAX_PER_CLASS
                 and int(self.max_feature) - int(self.min_feature) < 2**31 - 2):
-            dev = engine.DrawPlan(self._dev_dataset, self.encoded.class_rows, st[1], int(st[2]), n_plan, int(self._N),
-                                  int(self.batch_train_pclass), spec, int(self.min_feature), int(self.max_feature) + 1, stream)
             try:
-                K, key, pos = dev.finish()
-            except BaseException:
-                dev.close()
-                raise
+                dev = engine.DrawPlan(self._dev_dataset, self.encoded.class_rows, st[1], int(st[2]), n_plan, int(self._N),
+                                      int(self.batch_train_pclass), spec, int(self.min_feature), int(self.max_feature) + 1, stream)
+                try:
+                    K, key, pos = dev.finish()
+                except BaseException:
+                    dev.close()
+                    raise
+            except engine.EngineError:
+                # Both walks restate the same stream and nothing has been committed yet (numpy's state is set below):
+                # when the device walk was only the automatic choice, a plan it gives up on (it verifies itself and
+                # fails loudly) is drawn by the host walk instead -- same rows, same counts, same stream state.
+                if self.device_draws is not None:
+                    raise
+                log.warning("device draw plan failed; drawing this plan on the host", exc_info=True)
+                dev = None
+                self.device_draw_fallbacks = getattr(self, "device_draw_fallbacks", 0) + 1
             T = V = ksnap = psnap = None
-        else:
+        if dev is None:
             key = st[1].copy()
             T, V, K, ksnap, psnap, pos = engine.legacy_draw_plan(
                 key, int(st[2]), n_plan, self.encoded.class_rows, int(self._N), int(self.batch_train_pclass), spec,

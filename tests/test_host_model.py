@@ -211,3 +211,22 @@ def test_device_draws_are_chosen_automatically_only_for_ranks_short_of_cores(mon
     m.device_draws = False
     m.device_draw_auto_max_rows = 10**9
     assert m.device_draws_on() is False
+
+
+def test_automatic_device_draws_fall_back_to_the_host_walk_when_a_plan_fails(monkeypatch):
+    """device_draws = None (automatic): a device plan that gives up (EngineError) is drawn by the host walk instead --
+    nothing was committed, so the forest, the consumed candidates and both RNG end states are the reference's.  With
+    device_draws = True the error surfaces."""
+    from random_forest_mc_b200 import engine
+    from random_forest_mc_b200.model import RandomForestMC
+
+    class FailingPlan(fake_engine.FakeDrawPlan):
+        def finish(self):
+            raise engine.EngineError("device draw: stream words exhausted")
+
+    monkeypatch.setattr(engine, "DrawPlan", FailingPlan)
+    monkeypatch.setattr(RandomForestMC, "device_draws_on", lambda self: True)
+    g, m = model_checks.check_fit_matches_reference("mixed_default", device_draws=None, device_draw_min_slots=1)
+    assert m.device_draw_fallbacks >= 1
+    with pytest.raises(engine.EngineError):
+        model_checks.fitted_model("mixed_default", device_draws=True, device_draw_min_slots=1)
