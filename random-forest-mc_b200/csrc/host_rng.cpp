@@ -323,14 +323,15 @@ __attribute__((target("avx2"))) void reject_avx2(Stream& st, uint32_t mask, int6
     }
 }
 
-// AVX-512: up to 64 words per loop-carried update of i (a block of 624 words is 9 groups of four
-// vectors and one of three); accepted lanes leave through vpcompressd.  The window shrinks with the
-// mask so that a neighbour-dependent lane stays rare; the last few draws of a level are left to the
-// paths below.
-__attribute__((target("avx512f,avx2"))) void reject_avx512(Stream& st, uint32_t mask, int64_t lo, int64_t& i, uint32_t* A,
-                                                            int64_t& k) {
+// AVX-512: up to 64 words per loop-carried update of i (a block of 624 words is 9 groups of four vectors and one of
+// three); accepted lanes leave through vpcompressd.  Lane l of a group of W words sees i - (accepts before l) >= i - (W-1):
+// a word u <= i - (W-1) is accepted and a word u > i rejected whatever the other lanes do.  The few lanes in between
+// (about W^2 / (mask + 1) per group) are settled exactly, in lane order, against the accepts counted so far -- so the
+// window stays at 64 words down to the small masks instead of shrinking with them.  The last draws of a level (fewer
+// than W steps left) are left to the paths below.
+__attribute__((target("avx512f,avx2,bmi,bmi2,popcnt,lzcnt"))) void reject_avx512(Stream& st, uint32_t mask, int64_t lo, int64_t& i,
+                                                                                 uint32_t* A, int64_t& k) {
     const __m512i vmask = _mm512_set1_epi32((int)mask);
-    const int max_nv = mask >= 131071 ? 4 : (mask >= 32767 ? 2 : 1);
     while (i > lo) {
         if (st.pos == MT_N) st.refill();
         const int avail = MT_N - st.pos;
@@ -339,32 +340,36 @@ __attribute__((target("avx512f,avx2"))) void reject_avx512(Stream& st, uint32_t 
             continue;
         }
         int nv = avail >> 4;
-        if (nv > max_nv) nv = max_nv;
+        if (nv > 4) nv = 4;
         const int W = nv << 4;
         if (i - W < lo) break;
         const uint32_t* w = st.tw + st.pos;
         const __m512i vi = _mm512_set1_epi32((int)i), vs = _mm512_set1_epi32((int)(i - (W - 1)));
         __m512i u[4];
-        __mmask16 g[4];
-        unsigned amb = 0;
+        uint64_t rej = 0, notsure = 0;
 #pragma GCC unroll 4
         for (int v = 0; v < 4; ++v) {
             if (v < nv) {
                 u[v] = _mm512_and_si512(_mm512_loadu_si512(w + 16 * v), vmask);
-                g[v] = _mm512_cmpgt_epi32_mask(u[v], vi);
-                amb |= (unsigned)(g[v] ^ _mm512_cmpgt_epi32_mask(u[v], vs));
+                rej |= (uint64_t)_mm512_cmpgt_epi32_mask(u[v], vi) << (16 * v);
+                notsure |= (uint64_t)_mm512_cmpgt_epi32_mask(u[v], vs) << (16 * v);
             }
         }
-        if (amb) {
-            reject_scalar(st, mask, lo, i, A, k, W);
-            continue;
+        const uint64_t all = W == 64 ? ~0ull : ((1ull << W) - 1);
+        uint64_t acc = ~notsure & all;  // accepted whatever the other lanes do
+        uint64_t am = notsure & ~rej;   // i - (W-1) < u <= i: depends on the accepts before it
+        while (am) {
+            const int l = __builtin_ctzll(am);
+            am &= am - 1;
+            const int before = __builtin_popcountll(acc & ((1ull << l) - 1));
+            if ((w[l] & mask) <= (uint32_t)(i - before)) acc |= 1ull << l;
         }
         uint32_t* dst = A + k;
         int c = 0;
 #pragma GCC unroll 4
         for (int v = 0; v < 4; ++v) {
             if (v < nv) {
-                const __mmask16 m = (__mmask16)~g[v];
+                const __mmask16 m = (__mmask16)(acc >> (16 * v));
                 _mm512_storeu_si512(dst + c, _mm512_maskz_compress_epi32(m, u[v]));
                 c += __builtin_popcount((unsigned)m);
             }
@@ -496,7 +501,7 @@ void draw_accepted(Stream& st, int64_t n, uint32_t* A) {
     while (i >= 1) {
         const int64_t lo = (int64_t)(mask >> 1);  // this mask serves i in (lo, mask]
 #ifdef RFMC_HAVE_AVX2
-        if (avx512 && mask >= 2047) reject_avx512(st, mask, lo, i, A, k);  // leaves the end of the level to the paths below
+        if (avx512 && mask >= 1023) reject_avx512(st, mask, lo, i, A, k);  // leaves the end of the level to the paths below
         if (avx2 && mask >= 1023)
             reject_avx2(st, mask, lo, i, A, k);
         else
