@@ -19,3 +19,20 @@ def test_flattened_voting_equals_reference(name):
         ref = np.array([[d[c] for c in g["class_vals"]] for d in want["probs"]], dtype=np.float64)
         assert np.array_equal(probs, ref), (fname, soft, weighted)
         assert [g["class_vals"][k] for k in labels] == want["labels"], (fname, soft, weighted)
+
+
+def test_flat_feature_lists_behave_like_the_list_of_arrays_they_replace():
+    """engine.FlatFeatureLists (feature ids of a plan's candidates back to back, what rfmc_batch_create takes) is a
+    read-only sequence of per-candidate arrays: length, indexing, negative indices, slices and iteration."""
+    import numpy as np
+
+    from random_forest_mc_b200.engine import FlatFeatureLists
+
+    lists = [np.array([3, 1, 2], dtype=np.int32), np.array([7], dtype=np.int32), np.array([], dtype=np.int32), np.array([5, 0], dtype=np.int32)]
+    flat = FlatFeatureLists(np.concatenate(lists), np.array([[3, 1], [0, 2]]))
+    assert len(flat) == 4 and flat.off.tolist() == [0, 3, 4, 4, 6]
+    for k, want in enumerate(lists):
+        assert flat[k].tolist() == want.tolist() and flat[k - 4].tolist() == want.tolist()
+    assert [x.tolist() for x in flat] == [x.tolist() for x in lists]
+    assert [x.tolist() for x in flat[1:3]] == [x.tolist() for x in lists[1:3]]
+    assert [x.tolist() for x in list(flat)[2:]] == [[], [5, 0]]
